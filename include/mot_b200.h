@@ -1,0 +1,150 @@
+/*
+ * mot_b200.h -- C ABI of the B200-native tracking back end (libmot_b200.so).
+ *
+ * Drop-in boundary for the data-parallel hot path of huangfcn/multiple-object-tracking:
+ *   fHOG  ->  KCF/DCF correlation filter  ->  Kalman predict/update  ->  cost matrix + Hungarian.
+ * Every entry point names the reference interface it replaces (paths relative to the reference root).
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return 0 on success and a
+ * negative code on failure; mot_last_error() gives the text.  Nothing here ever falls back to a CPU
+ * implementation: without a CUDA device (or with an unsupported shape) the call FAILS.
+ *
+ * The reference's own per-object plugin signatures (top/td.cpp:229-261, C++ linkage)
+ *     void* tracker_new(bbox_t*); void tracker_predict(void*, float*, bbox_t*);
+ *     void tracker_update(void*, float*, bbox_t*); void tracker_delete(void*);
+ *     void assignmentoptimal(int*, double*, double*, int, int);
+ *     extern "C" rgb2Gray(...), bilinearInterpolationGray(...)
+ * are provided on top of this ABI by multiple-object-tracking_b200/host/tracker_shim.cpp.
+ */
+#ifndef MOT_B200_H
+#define MOT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)      /* the library itself is built with -fvisibility=hidden */
+#endif
+
+/* top/cnntype.h:36-41 -- layout-identical to bbox_t: inclusive pixel coordinates, field order l,t,b,r. */
+typedef struct mot_bbox_s { int l, t, b, r; int type; float score; } mot_bbox_t;
+
+/* top/cnntype.h:43-47 -- layout-identical to bbox_chain_t (the detector's per-frame output). */
+typedef struct mot_bbox_chain_s { int nbox; mot_bbox_t bbox[128]; } mot_bbox_chain_t;
+
+/* Which of the reference's two link-time tracker plugins a context emulates
+ * (yolo3tracker.vcxproj:134-138 links trackers/kalman.cpp; #define KCF_TRACKER, top/td.cpp:47, selects trackers/kcf.cpp). */
+enum { MOT_TRACKER_KALMAN = 0, MOT_TRACKER_KCF = 1 };
+
+/* Association cost (top/td.cpp:386-457).  REF_CENTROID is the shipped expression; IOU_CLAMPED is the finite form of
+ * the commented-out IoU cost (:404, :439), whose literal form goes negative / -inf and hangs the reference solver. */
+enum { MOT_COST_REF_CENTROID = 0, MOT_COST_IOU_CLAMPED = 1 };
+
+enum {
+    MOT_OK = 0, MOT_ERR_CUDA = -1, MOT_ERR_ARG = -2, MOT_ERR_SHAPE = -3, MOT_ERR_CAPACITY = -4,
+    MOT_ERR_TABLES = -5, MOT_ERR_KIND = -6
+};
+
+typedef struct mot_ctx_s mot_ctx_t;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+
+/* One context per GPU and per host thread (the reference calls the plugin from exactly one thread, top/td.cpp:306).
+ * frame_w/frame_h: the reference hard-codes 1280x720 (top/cnntype.h:5-6); here they are parameters.
+ * max_tracks: track slots (reference cap 256, top/td.cpp:12); n_frame_slots: frames resident at once (one per stream). */
+int mot_ctx_create(mot_ctx_t **out, int device, int frame_w, int frame_h, int max_tracks, int n_frame_slots, int tracker_kind);
+void mot_ctx_destroy(mot_ctx_t *ctx);
+const char *mot_last_error(void);
+/* Run all work of this context on the caller's CUDA stream (a cudaStream_t passed as void*); NULL = the context's own. */
+int mot_ctx_set_stream(mot_ctx_t *ctx, void *cuda_stream);
+int mot_sync(mot_ctx_t *ctx);
+/* MOT_TRACKER_KALMAN or MOT_TRACKER_KCF */
+int mot_ctx_kind(mot_ctx_t *ctx);
+/* Kernels launched by this context since creation (for bench.py's gpu_launches). */
+long mot_launch_count(mot_ctx_t *ctx);
+
+/* ---- frames (replaces the cv::Mat the tracking thread pops, top/td.cpp:330-331) --------------------------- */
+
+/* Copy a host BGR u8 frame (rows of stride_bytes) into frame slot `slot` (async on the context stream). */
+int mot_frame_upload(mot_ctx_t *ctx, int slot, const uint8_t *host_bgr, int stride_bytes);
+/* Zero-copy: make frame slot `slot` refer to a caller-owned DEVICE buffer (BGR u8, rows of stride_bytes). */
+int mot_frame_bind_device(mot_ctx_t *ctx, int slot, const uint8_t *dev_bgr, int stride_bytes);
+
+/* ---- tracker plugin, batched (replaces tracker_new/predict/update/delete, trackers/kcf.cpp:455-491 and
+ *      trackers/kalman.cpp:131-163; one call = the reference's loop over tracks, top/td.cpp:344-384, 512-582) --- */
+
+/* tracker_new for n boxes; writes n handles (slot numbers >= 0). */
+int mot_tracker_new_batch(mot_ctx_t *ctx, int n, const mot_bbox_t *boxes, int *handles_out);
+int mot_tracker_delete_batch(mot_ctx_t *ctx, int n, const int *handles);
+
+/* tracker_predict for n tracks, fused with the crop + gray + resize in front of it (top/td.cpp:348-364):
+ * boxes[i] in  = crop rectangle in frame frame_slots[i] (the caller's tracker_info.bbox),
+ * boxes[i] out = predicted box.  clamp != 0 also applies make_x/y_in_range (top/td.cpp:378-381).
+ * HOST arrays; blocks until the result is back.  For the Kalman kind frame_slots may be NULL. */
+int mot_predict_batch(mot_ctx_t *ctx, int n, const int *handles, const int *frame_slots, mot_bbox_t *boxes, int clamp);
+/* tracker_update for n tracks, fused with crop + gray + resize (top/td.cpp:517-540, 558-580): boxes[i] is both the
+ * crop rectangle and the measurement / new position.  HOST arrays; asynchronous on the context stream. */
+int mot_update_batch(mot_ctx_t *ctx, int n, const int *handles, const int *frame_slots, const mot_bbox_t *boxes);
+
+/* Same two calls with every array already resident on the DEVICE (no copies, no sync): the steady-state path. */
+int mot_predict_batch_dev(mot_ctx_t *ctx, int n, const int *d_handles, const int *d_frame_slots, mot_bbox_t *d_boxes, int clamp);
+int mot_update_batch_dev(mot_ctx_t *ctx, int n, const int *d_handles, const int *d_frame_slots, const mot_bbox_t *d_boxes);
+
+/* The literal plugin form: the caller already cropped/resized a gray patch (column-major rows x cols f32, HOST),
+ * exactly what tracker_predict/tracker_update receive as `rgb` (trackers/kcf.cpp:455-476). */
+int mot_predict_gray(mot_ctx_t *ctx, int handle, const float *gray_host, mot_bbox_t *box_out);
+int mot_update_gray(mot_ctx_t *ctx, int handle, const float *gray_host, const mot_bbox_t *box);
+
+/* ---- patch preprocessing on its own (replaces rgb2Gray + bilinearInterpolationGray, top/drawlib.c:192-240, 542-637) */
+int mot_crop_gray_resize(mot_ctx_t *ctx, int frame_slot, const mot_bbox_t *box, int rows_d, int cols_d, float *gray_host_out);
+
+/* ---- association (replaces the cost loops top/td.cpp:386-457 and assignmentoptimal, trackers/hungarian/hungarian.cpp:29) */
+
+/* n_mat independent problems.  Problem m has T[m] tracker boxes and D[m] detection boxes stored at trk + m*trk_stride,
+ * det + m*det_stride.  Cost matrix m is written column-major with rows = the smaller side (trackers if T<D else
+ * detections) at dist + m*dist_stride (may be NULL to skip the dump); assignment m (one int per ROW, column or -1) at
+ * assign + m*assign_stride; total cost at cost[m].  HOST arrays. */
+int mot_associate_batch(mot_ctx_t *ctx, int n_mat, const int *T, const int *D,
+                        const mot_bbox_t *trk, long trk_stride, const mot_bbox_t *det, long det_stride,
+                        int cost_mode, double *dist, long dist_stride, int *assign, long assign_stride, double *cost);
+/* assignmentoptimal on caller-supplied matrices (column-major nrows x ncols doubles), n_mat of them, HOST arrays. */
+int mot_assign_batch(mot_ctx_t *ctx, int n_mat, const int *nrows, const int *ncols, const double *dist, long dist_stride,
+                     int *assign, long assign_stride, double *cost);
+/* Device-resident forms (no copies, no sync). */
+int mot_associate_batch_dev(mot_ctx_t *ctx, int n_mat, const int *d_T, const int *d_D,
+                            const mot_bbox_t *d_trk, long trk_stride, const mot_bbox_t *d_det, long det_stride,
+                            int cost_mode, double *d_dist, long dist_stride, int *d_assign, long assign_stride, double *d_cost,
+                            int max_dim);
+
+/* ---- frame loop (replaces one iteration of pthread_mtcnn_trkn, top/td.cpp:343-644) -------------------------- */
+typedef struct mot_td_s mot_td_t;
+/* One loop state per stream; frame_slot = where this stream's frames are uploaded. */
+int mot_td_create(mot_td_t **out, mot_ctx_t *ctx, int frame_slot, int cap, int cost_mode);
+void mot_td_destroy(mot_td_t *td);
+/* host_bgr may be NULL when the frame slot was already filled (or for the Kalman kind, which never reads pixels). */
+int mot_td_step(mot_td_t *td, const uint8_t *host_bgr, int stride_bytes, const mot_bbox_t *dets, int ndet);
+/* Lock-step over several streams: one batched predict / associate / update per frame instead of one per stream. */
+int mot_td_step_multi(mot_td_t **tds, int n_streams, const uint8_t *const *host_bgr, int stride_bytes,
+                      const mot_bbox_t *const *dets, const int *ndet);
+int mot_td_ntracks(mot_td_t *td);
+void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *vis, int *invis);
+int mot_td_last(mot_td_t *td, mot_bbox_t *predicted, int *assigned_trackers);
+
+/* ---- test hooks: stage dumps of the fused KCF kernel ------------------------------------------------------- */
+/* Stages: 0 gray | 1 m0 | 2 bin(int) | 3 r1 | 4 norm | 5 feat(xf_tm) | 6 spec(xf_fq, float pairs) | 7 zf | 8 response |
+ *         9 kf | 10 peak(int x2) | 11 margin(float x2).  Enable before a predict/update of ONE track, then fetch. */
+int mot_debug_enable_dumps(mot_ctx_t *ctx, int enable);
+long mot_debug_fetch(mot_ctx_t *ctx, int stage, void *host_out, long max_bytes);
+/* Raw per-slot state: which = 0 xf_md (31*S float pairs) | 1 alpha (S floats) | 2 Kalman x[6] | 3 Kalman P[36] col-major. */
+long mot_debug_state(mot_ctx_t *ctx, int handle, int which, void *host_out, long max_bytes);
+/* Host-harvested SSE tables: which = 0 rsqrt | 1 rcp | 2 acos(20020) ; info[0..3] = rsqrt_bits, rcp_bits, bin_shift, bin_nseg */
+long mot_debug_tables(int which, float *out, long max_floats, int *info);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,317 @@
+// assoc.cu -- batched association: cost matrices and the reference's Munkres solver, one CTA per problem.
+//
+// Replaces the cost loops of top/td.cpp:386-457 and assignmentoptimal + step2a/2b/3/4/5 of
+// trackers/hungarian/hungarian.cpp:29-368.  Assignments must be BIT-EXACT with the reference, ties included, so the
+// solver is not "a" Hungarian algorithm but the reference's, decision for decision:
+//   * the same reductions (row minima when rows <= cols, column minima otherwise) and greedy initial stars,
+//   * the same zero test fabs(x) < DBL_EPSILON on the same doubles (step 5 adds h to covered rows, then subtracts h
+//     from uncovered columns, so doubly-qualified cells see (d+h)-h with both roundings),
+//   * step 3's sweep order: columns ascending, first uncovered zero row of the column, and after covering that row the
+//     sweep CONTINUES with the next column (uncovered columns to the right are visited in the same sweep).
+// What changes is the machinery: the three n^2 bool matrices become index vectors (a row/column holds at most one
+// star, a row at most one prime) plus a column-major ZERO BITMAP in shared memory (n^2 bits), so step 3 is a walk over
+// set bits by one warp instead of an n^2 scan, and step 5 -- the only full-matrix pass -- is done by the whole CTA with
+// coalesced 256-byte rows.  Matrices up to ~160x160 live in shared memory; larger ones stay in global memory / L2.
+#include "assoc.h"
+#include <cfloat>
+
+namespace mot {
+
+constexpr int MUNKRES_THREADS = 512;
+
+__device__ __forceinline__ double cost_cell(const mot_bbox_t &t, const mot_bbox_t &d, int mode, double screen_dis)
+{
+    const int maxl = max(t.l, d.l), maxt = max(t.t, d.t), minr = min(t.r, d.r), minb = min(t.b, d.b);
+    double dista = 0.0;
+    if (mode == MOT_COST_IOU_CLAMPED) {
+        const int iw = max(0, minr - maxl), ih = max(0, minb - maxt);
+        const double inter = (double)(iw * ih);
+        const double uni = __dsub_rn((double)((t.b - t.t) * (t.r - t.l) + (d.b - d.t) * (d.r - d.l)), inter);
+        dista = (uni > 0.0) ? __dsub_rn(1.0, __ddiv_rn(inter, uni)) : 1.0;
+    } else {
+        // top/td.cpp:406-415: centroid distance * SCREEN_DIS
+        const int cxi = (t.l + t.r) >> 1, cyi = (t.t + t.b) >> 1, cxj = (d.l + d.r) >> 1, cyj = (d.t + d.b) >> 1;
+        dista = __dmul_rn(__dsqrt_rn((double)((cxi - cxj) * (cxi - cxj) + (cyi - cyj) * (cyi - cyj))), screen_dis);
+    }
+    if (t.type != d.type) dista = __dadd_rn(dista, 1.0);                   // top/td.cpp:416-419
+    return dista;
+}
+
+__global__ void cost_kernel(const AssocLaunch p)
+{
+    const int m = blockIdx.y;
+    const int T = p.T[m], D = p.D[m];
+    const mot_bbox_t *trk = p.trk + (long)m * p.trk_stride, *det = p.det + (long)m * p.det_stride;
+    double *dist = p.dist + (long)m * p.dist_stride;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < T * D; idx += gridDim.x * blockDim.x) {
+        int i, j;
+        if (T < D) { j = idx / T; i = idx - j * T; }      // rows = trackers  (top/td.cpp:388-421)
+        else       { i = idx / D; j = idx - i * D; }      // rows = detections (top/td.cpp:424-456)
+        dist[idx] = cost_cell(trk[i], det[j], p.cost_mode, p.screen_dis);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct MunkresSmem {
+    double *mat;            // optional shared-memory copy of the working matrix
+    uint32_t *Zc;           // [nC][nWr] zero bitmap, column-major: bit r of word (c, r>>5)
+    uint32_t *covR, *covC;  // cover bit masks
+    int *starOfRow, *starOfCol, *primeOfRow;
+    double *redd;           // [16] reduction scratch
+    int *ctrl;              // [4]: 0 = control word, 1 = aug row, 2 = aug col
+};
+
+__device__ __forceinline__ bool tst(const uint32_t *w, int i) { return (w[i >> 5] >> (i & 31)) & 1u; }
+
+// next index >= from whose bit in `mask` is CLEAR (i.e. next uncovered), or n if none; executed uniformly by a warp
+__device__ __forceinline__ int next_clear(const uint32_t *mask, int from, int n)
+{
+    while (from < n) {
+        const int w = from >> 5;
+        uint32_t bits = ~mask[w] & (0xFFFFFFFFu << (from & 31));
+        if (bits) { const int i = (w << 5) + __ffs(bits) - 1; return i < n ? i : n; }
+        from = (w + 1) << 5;
+    }
+    return n;
+}
+
+enum { CTRL_DONE = 1, CTRL_STEP5 = 2, CTRL_FAIL = 3 };
+
+__global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const AssocLaunch p, const int *rows_cols, const int smem_mat_doubles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = MUNKRES_THREADS, NW = NT / 32;
+    int nR, nC;
+    if (rows_cols) { nR = rows_cols[2 * m]; nC = rows_cols[2 * m + 1]; }
+    else { const int T = p.T[m], D = p.D[m]; if (T < D) { nR = T; nC = D; } else { nR = D; nC = T; } }
+    int *assign = p.assign + (long)m * p.assign_stride;
+    if (nR <= 0 || nC <= 0) { if (tid == 0) p.cost[m] = 0.0; return; }      // the reference skips the call (top/td.cpp:460)
+    const double *distIn = p.dist + (long)m * p.dist_stride;
+    const int minDim = nR <= nC ? nR : nC;
+    const int nWr = (nR + 31) >> 5, nWc = (nC + 31) >> 5;
+    const int md = p.max_dim, mdW = (md + 31) >> 5;
+
+    MunkresSmem s;
+    {
+        unsigned char *q = smem_raw;
+        s.mat = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)smem_mat_doubles;
+        s.redd = reinterpret_cast<double *>(q); q += sizeof(double) * 16;
+        s.Zc = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * (size_t)md * mdW;
+        s.covR = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
+        s.covC = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
+        s.starOfRow = reinterpret_cast<int *>(q); q += sizeof(int) * md;
+        s.starOfCol = reinterpret_cast<int *>(q); q += sizeof(int) * md;
+        s.primeOfRow = reinterpret_cast<int *>(q); q += sizeof(int) * md;
+        s.ctrl = reinterpret_cast<int *>(q);
+    }
+    double *const d = ((long)nR * nC <= smem_mat_doubles) ? s.mat : p.work + (long)m * p.work_stride;
+
+    // working copy (hungarian.cpp:41-54) and state
+    for (int i = tid; i < nR * nC; i += NT) d[i] = distIn[i];
+    for (int i = tid; i < nR; i += NT) { s.starOfRow[i] = -1; s.primeOfRow[i] = -1; assign[i] = -1; }
+    for (int i = tid; i < nC; i += NT) s.starOfCol[i] = -1;
+    for (int i = tid; i < mdW; i += NT) { s.covR[i] = 0; s.covC[i] = 0; }
+    __syncthreads();
+
+    // reduction (hungarian.cpp:65-89 rows, :104-124 columns)
+    if (nR <= nC) {
+        for (int r = tid; r < nR; r += NT) {
+            double mn = d[r];
+            for (int c = 1; c < nC; ++c) { const double v = d[r + (long)nR * c]; if (v < mn) mn = v; }
+            for (int c = 0; c < nC; ++c) d[r + (long)nR * c] = __dsub_rn(d[r + (long)nR * c], mn);
+        }
+    } else {
+        for (int c = tid; c < nC; c += NT) {
+            double *col = d + (long)nR * c, mn = col[0];
+            for (int r = 1; r < nR; ++r) if (col[r] < mn) mn = col[r];
+            for (int r = 0; r < nR; ++r) col[r] = __dsub_rn(col[r], mn);
+        }
+    }
+    __syncthreads();
+    // zero bitmap
+    for (int task = warp; task < nC * nWr; task += NW) {
+        const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
+        const bool z = (r < nR) && (fabs(d[r + (long)nR * c]) < DBL_EPSILON);
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
+        if (lane == 0) s.Zc[c * nWr + w] = word;
+    }
+    __syncthreads();
+
+    // greedy initial stars (hungarian.cpp:91-101 / :126-140) -- sequential by nature, one warp
+    if (warp == 0) {
+        if (nR <= nC) {
+            for (int r = 0; r < nR; ++r) {
+                for (int cb = 0; cb < nC; cb += 32) {
+                    const int c = cb + lane;
+                    const bool ok = (c < nC) && ((s.Zc[c * nWr + (r >> 5)] >> (r & 31)) & 1u) && !tst(s.covC, c);
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+                    if (bal) {
+                        const int cs = cb + __ffs(bal) - 1;
+                        if (lane == 0) { s.starOfRow[r] = cs; s.starOfCol[cs] = r; s.covC[cs >> 5] |= 1u << (cs & 31); }
+                        __syncwarp();
+                        break;
+                    }
+                }
+            }
+        } else {
+            for (int c = 0; c < nC; ++c) {
+                const uint32_t mw = (lane < nWr) ? (s.Zc[c * nWr + lane] & ~s.covR[lane]) : 0u;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mw != 0);
+                if (bal) {
+                    const int fl = __ffs(bal) - 1;
+                    const int r = (fl << 5) + __ffs(__shfl_sync(0xFFFFFFFFu, mw, fl)) - 1;
+                    if (lane == 0) { s.starOfRow[r] = c; s.starOfCol[c] = r; s.covC[c >> 5] |= 1u << (c & 31); s.covR[r >> 5] |= 1u << (r & 31); }
+                    __syncwarp();
+                }
+            }
+            if (lane < mdW) s.covR[lane] = 0;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    long guard = 0;
+    const long guard_max = 8L * md * md + 1024;             // the reference never terminates on -inf / NaN costs; we do
+    bool after_step5 = false;
+    for (;;) {
+        if (warp == 0) {
+            int ctrl = 0;
+            for (;;) {
+                if (!after_step5) {
+                    // step 2b (hungarian.cpp:213-236)
+                    int cnt = (lane < nWc) ? __popc(s.covC[lane]) : 0;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, off);
+                    if (cnt == minDim) { ctrl = CTRL_DONE; break; }
+                }
+                after_step5 = false;
+                // step 3 (hungarian.cpp:239-279)
+                int aug_r = -1, aug_c = -1;
+                bool zerosFound = true;
+                while (zerosFound && aug_r < 0) {
+                    zerosFound = false;
+                    for (int c = next_clear(s.covC, 0, nC); c < nC; c = next_clear(s.covC, c + 1, nC)) {
+                        const uint32_t mw = (lane < nWr) ? (s.Zc[c * nWr + lane] & ~s.covR[lane]) : 0u;
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mw != 0);
+                        if (!bal) continue;
+                        const int fl = __ffs(bal) - 1;
+                        const int r = (fl << 5) + __ffs(__shfl_sync(0xFFFFFFFFu, mw, fl)) - 1;
+                        const int sc = s.starOfRow[r];
+                        if (lane == 0) s.primeOfRow[r] = c;
+                        if (sc < 0) { aug_r = r; aug_c = c; __syncwarp(); break; }
+                        if (lane == 0) { s.covR[r >> 5] |= 1u << (r & 31); s.covC[sc >> 5] &= ~(1u << (sc & 31)); }
+                        zerosFound = true;
+                        __syncwarp();
+                    }
+                }
+                if (aug_r < 0) { ctrl = CTRL_STEP5; break; }
+                // step 4 (hungarian.cpp:282-334): flip stars along the alternating path (old stars drive the walk)
+                if (lane == 0) {
+                    int r = aug_r, c = aug_c;
+                    for (;;) {
+                        const int sr = s.starOfCol[c];
+                        s.starOfRow[r] = c; s.starOfCol[c] = r;
+                        if (sr < 0) break;
+                        r = sr; c = s.primeOfRow[r];
+                    }
+                }
+                __syncwarp();
+                for (int i = lane; i < nR; i += 32) s.primeOfRow[i] = -1;
+                if (lane < mdW) s.covR[lane] = 0;
+                // step 2a (hungarian.cpp:193-210): cover every column that holds a star
+                for (int w = lane; w < nWc; w += 32) {
+                    uint32_t bits = 0;
+                    for (int b = 0; b < 32; ++b) { const int c = (w << 5) + b; if (c < nC && s.starOfCol[c] >= 0) bits |= 1u << b; }
+                    s.covC[w] |= bits;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) s.ctrl[0] = ctrl;
+        }
+        __syncthreads();
+        const int ctrl = s.ctrl[0];
+        if (ctrl != CTRL_STEP5) break;
+        if (++guard > guard_max) { if (tid == 0) s.ctrl[0] = CTRL_FAIL; __syncthreads(); break; }
+
+        // step 5 (hungarian.cpp:337-368), whole CTA.  h = smallest uncovered element
+        double h = DBL_MAX;
+        for (int task = warp; task < nC * nWr; task += NW) {
+            const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
+            if (tst(s.covC, c)) continue;
+            if (r < nR && !tst(s.covR, r)) { const double v = d[r + (long)nR * c]; if (v < h) h = v; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_xor_sync(0xFFFFFFFFu, h, off); if (o < h) h = o; }
+        if (lane == 0) s.redd[warp] = h;
+        __syncthreads();
+        h = s.redd[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) { const double o = s.redd[w]; if (o < h) h = o; }
+        // add h to covered rows, then subtract h from uncovered columns; refresh the zero bits of touched cells
+        for (int task = warp; task < nC * nWr; task += NW) {
+            const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
+            const bool cc = tst(s.covC, c);
+            const uint32_t crw = s.covR[w];
+            if (cc && crw == 0) continue;                         // covered column, no covered row in this word: untouched
+            const uint32_t old = s.Zc[c * nWr + w];
+            bool z = (old >> lane) & 1u;
+            if (r < nR) {
+                const bool rc = (crw >> lane) & 1u;
+                if (rc || !cc) {
+                    double v = d[r + (long)nR * c];
+                    if (rc) v = __dadd_rn(v, h);
+                    if (!cc) v = __dsub_rn(v, h);
+                    d[r + (long)nR * c] = v;
+                    z = fabs(v) < DBL_EPSILON;
+                }
+            }
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
+            if (lane == 0) s.Zc[c * nWr + w] = word;
+        }
+        after_step5 = true;
+        __syncthreads();
+    }
+
+    // buildassignmentvector + computeassignmentcost (hungarian.cpp:161-189); rows summed in ascending order
+    const bool fail = s.ctrl[0] == CTRL_FAIL;
+    for (int r = tid; r < nR; r += NT) assign[r] = fail ? -1 : s.starOfRow[r];
+    if (tid == 0) {
+        double cst = 0.0;
+        if (!fail) for (int r = 0; r < nR; ++r) { const int c = s.starOfRow[r]; if (c >= 0) cst = __dadd_rn(cst, distIn[r + (long)nR * c]); }
+        else cst = nan("");
+        p.cost[m] = cst;
+    }
+}
+
+static size_t munkres_smem(int md, int mat_doubles)
+{
+    const int mdW = (md + 31) >> 5;
+    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * 16 + sizeof(uint32_t) * ((size_t)md * mdW + 2 * mdW) +
+           sizeof(int) * (3 * (size_t)md + 4);
+}
+
+int assoc_cost(const AssocLaunch &p, cudaStream_t s)
+{
+    if (p.n_mat <= 0) return 0;
+    const int cells = p.max_dim * p.max_dim;
+    dim3 grid((unsigned)((cells + 255) / 256 > 64 ? 64 : (cells + 255) / 256), (unsigned)p.n_mat);
+    if (grid.x == 0) grid.x = 1;
+    cost_kernel<<<grid, 256, 0, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int assoc_solve(const AssocLaunch &p, const int *rows_cols, cudaStream_t s)
+{
+    if (p.n_mat <= 0) return 0;
+    if (p.max_dim > 1024 || p.max_dim < 1) return -1001;
+    int mat_doubles = p.max_dim * p.max_dim;
+    if (munkres_smem(p.max_dim, mat_doubles) > 200 * 1024) mat_doubles = 0;
+    const size_t bytes = munkres_smem(p.max_dim, mat_doubles);
+    cudaError_t e = cudaFuncSetAttribute((const void *)munkres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    munkres_kernel<<<p.n_mat, MUNKRES_THREADS, bytes, s>>>(p, rows_cols, mat_doubles);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace mot

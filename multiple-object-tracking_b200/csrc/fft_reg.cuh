@@ -1,0 +1,58 @@
+// fft_reg.cuh -- small power-of-two FFTs held entirely in registers (one transform per thread).
+//
+// Replaces the FFTW 3.3.5 plans the reference creates per tracker (trackers/kcf.cpp:178-195,
+// executed at :265 and :399).  A 2-D r2c of a 32x32 cell grid is 32 length-32 real transforms
+// followed by 17 length-32 complex ones: far too small for a library call per track, so every
+// thread owns one 1-D transform, fully unrolled, twiddles folded into immediates; the 2-D
+// structure (and the transposes between the two passes) lives in shared memory (kcf_fused.cu).
+//
+// Decimation-in-frequency radix-2; the result is left in bit-reversed order and read back
+// through the compile-time permutation brev<N>(k), which costs nothing once unrolled.
+#pragma once
+#include <cuda_runtime.h>
+#include "twiddles64.h"
+
+namespace mot {
+
+template <int N> __host__ __device__ constexpr int log2c() { return N <= 1 ? 0 : 1 + log2c<N / 2>(); }
+
+template <int N> __host__ __device__ constexpr int brev(int k)
+{
+    int r = 0;
+    for (int b = 0; b < log2c<N>(); ++b) r |= ((k >> b) & 1) << (log2c<N>() - 1 - b);
+    return r;
+}
+
+// w = exp(DIR * 2*pi*i * num / den), den | 64, evaluated at compile time after unrolling.
+template <int DIR> __device__ __forceinline__ float2 cmul_tw(float2 v, int num, int den)
+{
+    const int idx = (num * (64 / den)) & 63;
+    if (idx == 0) return v;
+    if (idx == 32) return make_float2(-v.x, -v.y);
+    if (idx == 16) return DIR < 0 ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x);   // * (-i) or * (+i)
+    if (idx == 48) return DIR < 0 ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
+    const float c = tw::C64[idx];
+    const float s = DIR < 0 ? -tw::S64[idx] : tw::S64[idx];
+    return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+}
+
+// In-place complex FFT of N points (N = 2,4,8,16,32,64).  DIR = -1 forward, +1 inverse (un-normalised).
+// On return a[brev<N>(k)] holds X[k].
+template <int N, int DIR> __device__ __forceinline__ void fft_dif(float2 (&a)[N])
+{
+#pragma unroll
+    for (int len = N; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int b = 0; b < N; b += len) {
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float2 u = a[b + i], v = a[b + i + half];
+                a[b + i] = make_float2(u.x + v.x, u.y + v.y);
+                a[b + i + half] = cmul_tw<DIR>(make_float2(u.x - v.x, u.y - v.y), i, len);
+            }
+        }
+    }
+}
+
+}  // namespace mot

@@ -1,0 +1,43 @@
+// fhog_tables.h -- host-built lookup tables that let the GPU reproduce the reference fHOG bit for bit.
+//
+// libhog/gradientMex.cpp:83-84 computes the gradient magnitude with the SSE approximations
+// _mm_rsqrt_ps / _mm_rcp_ps (libhog/sse.hpp:40-41).  Their ~3e-4 relative error is larger than the
+// 1e-4 parity tolerance and feeds a truncating table index (:90) and a nearest-bin quantiser (:130-131),
+// so exact math on the GPU FAILS parity.  Both instructions are pure
+// table look-ups on the top mantissa bits with exact power-of-two exponent scaling; the tables are
+// harvested from the host CPU the process runs on (Intel and AMD differ), verified exhaustively, and
+// uploaded.  The orientation path (acosTable :47-56 + gradQuantize :130-131, built with the host's
+// libm) is folded into one exact "orientation bin" step table.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mot {
+
+struct FhogTables {
+    bool ok = false;
+    std::string error;
+    // rsqrt: value for x in [1,4): index = parity * (1 << rsqrt_bits) + (mantissa >> (23 - rsqrt_bits))
+    int rsqrt_bits = 0;
+    std::vector<float> rsqrt_tab;
+    // rcp: value for x in [1,2): index = mantissa >> (23 - rcp_bits)
+    int rcp_bits = 0;
+    std::vector<float> rcp_tab;
+    // orientation bin: segment = (idx + 10010) >> bin_shift, entry[sign * nseg + segment] = (thr << 8) | base,
+    // bin = base - (idx + 10010 >= thr), then 18 wraps to 0.  idx = (int)(Gx * m * 10000) in [-10010, 10010).
+    int bin_shift = 0, bin_nseg = 0;
+    std::vector<uint32_t> bin_tab;
+    // the raw acos table (20020 floats, index idx + 10010) kept for tests / debugging dumps
+    std::vector<float> acos_tab;
+};
+
+// Harvest + verify (about 50 ms, once per process).  Never throws; check .ok / .error.
+const FhogTables &fhog_tables();
+
+// Host emulation of the two instructions from the tables (used by the self-check and the CPU-side tests).
+float emu_rsqrt(const FhogTables &t, float x);
+float emu_rcp(const FhogTables &t, float x);
+int emu_bin(const FhogTables &t, int idx, int gy_negative);
+
+}  // namespace mot

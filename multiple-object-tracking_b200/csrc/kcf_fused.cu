@@ -1,0 +1,535 @@
+// kcf_fused.cu -- the fused KCF/DCF kernels: one CTA per (track, frame) job, everything between the BGR frame
+// bytes and the updated model in ONE launch, so a track touches HBM once per predict and once per update.
+//
+// Replaces, for one track (reference paths relative to its root):
+//   rgb2Gray + bilinearInterpolationGray      top/drawlib.c:192-240, 542-637   (called top/td.cpp:348-364)
+//   FHoG::extract -> gradMag -> fhog          libhog/fhog.h:16-38, libhog/gradientMex.cpp:59-100, 148-317
+//   kcf_get_features / kcf_fft2_features      trackers/kcf.cpp:245-267 (31 FFTW r2c plans)
+//   predict: kcf_linear_correlation_zf + kcf_predict_ifft2 (+ the clamp of top/td.cpp:378-381)   kcf.cpp:306-362, 397-439
+//   update : kcf_linear_correlation_kf + kcf_update_alpha + kcf_update_xf                         kcf.cpp:269-304, 364-395, 441-476
+//
+// Shared-memory plan for HR x WC cells (floats; 32x32 -> 207 KB, one CTA per SM):
+//   F   [31*NB]              gray patch -> (M/16, orientation bin) -> packed half spectra of all 31 channels, in place
+//   R1  [18*WC*(HR+1)]       SSE look-up tables (gradient phase) -> 18-bin cell histograms -> Nyquist column, zf, response
+//   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies;  wy[HR], wx[WC] Hann vectors
+// The 31-channel feature tensor is never materialised: each channel column is generated from R1 and N in registers,
+// windowed, transformed (real FFT of HR points as a complex FFT of HR/2) and stored PACKED (DC.re, Nyquist.re share one
+// complex slot), so the column pass is exactly HR/2 complex FFTs per channel: 31*16 = 496 thread-sized transforms at 32x32.
+//
+// Arithmetic follows the reference operation by operation where its rounding is observable (gray in double, unfused
+// f32 MUL/ADD in fHOG via __fmul_rn/__fadd_rn, SSE rsqrt/rcp through host-harvested tables, the histogram summed in the
+// reference's pixel order); the FFTs and the spectral products are ordinary f32.
+#include "mot_internal.h"
+#include "fft_reg.cuh"
+
+namespace mot {
+
+template <int HR, int WC> struct Geo {
+    static constexpr int NB = HR * WC;
+    static constexpr int HK = HR / 2;                    // packed complex bins per column
+    static constexpr int SK = HR / 2 + 1;                // FFTW half-spectrum length along rows
+    static constexpr int S = WC * SK;
+    static constexpr int H0 = 4 * HR, W0 = 4 * WC;
+    static constexpr int RMAX = 4 * HR + 3, CMAX = 4 * WC + 3;
+    static constexpr int GS = RMAX;                      // gray column stride (odd -> conflict-free in both directions)
+    static constexpr int RS = HR + 1;                    // histogram / normaliser column stride
+    static constexpr int F_FLOATS = 31 * NB;
+    static constexpr int R1_MIN = 18 * WC * RS;
+    static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
+    static constexpr int PIX_PER_THREAD = (H0 * W0 + KCF_THREADS - 1) / KCF_THREADS;
+    static_assert(CMAX * GS <= F_FLOATS, "gray patch must fit in the F region");
+    static_assert(20 * NB <= F_FLOATS, "M0 + bins must fit in the F region");
+    static_assert((F_FLOATS & 1) == 0, "float2 alignment of the R1 region");
+};
+
+__host__ __device__ inline int r1_region_floats(int r1_min, int lut_floats) { int v = r1_min > lut_floats ? r1_min : lut_floats; return (v + 3) & ~3; }
+
+template <int HR, int WC> size_t smem_bytes(int lut_floats)
+{
+    using G = Geo<HR, WC>;
+    return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats) + G::N_FLOATS + G::NB + HR + WC + 64);
+}
+
+// gray = 0.144*B + 0.587*G + 0.299*R in double, rounded to float (top/drawlib.c:234; yes, 0.144)
+__device__ __forceinline__ float bgr_gray(const uint8_t *p)
+{
+    const double B = p[0], G = p[1], R = p[2];
+    return __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(0.144, B), __dmul_rn(0.587, G)), __dmul_rn(0.299, R)));
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <int HR, int WC, int MODE>
+__global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaunch p, const int lut_floats)
+{
+    using G = Geo<HR, WC>;
+    constexpr int NT = KCF_THREADS, NB = G::NB, HK = G::HK, SK = G::SK, S = G::S, GS = G::GS, RS = G::RS;
+    constexpr int H0 = G::H0, W0 = G::W0;
+    extern __shared__ __align__(16) float smem[];
+    float *const F = smem;
+    float *const R1 = F + G::F_FLOATS;
+    float *const Ns = R1 + r1_region_floats(G::R1_MIN, lut_floats);
+    float *const Es = Ns + G::N_FLOATS;
+    float *const wy_s = Es + NB;
+    float *const wx_s = wy_s + HR;
+    float *const red = wx_s + WC;
+
+    const int tid = threadIdx.x;
+    const int job = blockIdx.x;
+    if (job >= p.n_jobs) return;
+    const int slot = p.slots[job];
+    KcfMeta *const meta = p.meta + slot;
+    const KcfClassDev cls = p.classes[meta->size_class];
+    const int rows = meta->rows, cols = meta->cols;
+    mot_bbox_t box = p.boxes[job];
+
+    // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
+    const bool lut_smem = lut_floats > 0;
+    const float *rs_tab = p.tab.rsqrt_tab, *rc_tab = p.tab.rcp_tab;
+    const uint32_t *bn_tab = p.tab.bin_tab;
+    if (lut_smem) {
+        const int n_rs = 2 << p.tab.rsqrt_bits, n_rc = 1 << p.tab.rcp_bits, n_bn = 2 * p.tab.bin_nseg;
+        for (int i = tid; i < n_rs; i += NT) R1[i] = p.tab.rsqrt_tab[i];
+        for (int i = tid; i < n_rc; i += NT) R1[n_rs + i] = p.tab.rcp_tab[i];
+        for (int i = tid; i < n_bn; i += NT) reinterpret_cast<uint32_t *>(R1)[n_rs + n_rc + i] = p.tab.bin_tab[i];
+        rs_tab = R1; rc_tab = R1 + n_rs; bn_tab = reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc;
+    }
+    if (tid < HR) wy_s[tid] = cls.wy[tid];
+    if (tid < WC) wx_s[tid] = cls.wx[tid];
+
+    if (p.gray != nullptr) {
+        const float *src = p.gray + (long)job * p.gray_stride;
+        for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; F[x * GS + y] = src[idx]; }
+    } else {
+        const uint8_t *frame = p.frame_ptr[p.frames[job]];
+        int l = box.l, t = box.t, r = box.r, b = box.b;
+        if (t > b) { const int q = t; t = b; b = q; }          // top/drawlib.c:203-215
+        if (l > r) { const int q = l; l = r; r = q; }
+        const int rows_s = b - t + 1, cols_s = r - l + 1;
+        const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
+        if (rows_s == rows && cols_s == cols) {
+            // equal sizes: bilinearInterpolationGray degenerates to an exact copy (top/drawlib.c:610-633 with xs = ys = 1)
+            for (int idx = tid; idx < rows * cols; idx += NT) {
+                const int y = idx / cols, x = idx - y * cols;
+                const uint8_t *px = frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + clampi(l + x, 0, Wm) * 3;
+                F[x * GS + y] = bgr_gray(px);
+            }
+        } else {
+            // the reference resamples a column-major crop as if it were row-major height x width; reproduced through
+            // linear indices (top/drawlib.c:542-637, called as (dst, src, rows_s, cols_s, rows_d, cols_d), top/td.cpp:357-364)
+            const float xs = __fdiv_rn((float)cols_s, (float)cols), ys = __fdiv_rn((float)rows_s, (float)rows);
+            for (int k = tid; k < rows * cols; k += NT) {
+                const int yy = k / cols, xx = k - yy * cols;
+                const float sx = __fmul_rn((float)xx, xs), sy = __fmul_rn((float)yy, ys);
+                const int x0 = __float2int_rz(sx), y0 = __float2int_rz(sy);
+                const float fx = __fsub_rn(sx, (float)x0), fy = __fsub_rn(sy, (float)y0);
+                const float ifx = __fsub_rn(1.0f, fx), ify = __fsub_rn(1.0f, fy);
+                const int x1 = (x0 + 1 >= cols_s) ? x0 : x0 + 1, y1 = (y0 + 1 >= rows_s) ? y0 : y0 + 1;
+                float c[4];
+                const int sidx[4] = { y0 * cols_s + x0, y0 * cols_s + x1, y1 * cols_s + x0, y1 * cols_s + x1 };
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int sc = sidx[q] / rows_s, sr = sidx[q] - sc * rows_s;   // column-major crop element
+                    c[q] = bgr_gray(frame + (long)clampi(t + sr, 0, Hm) * p.frame_stride + clampi(l + sc, 0, Wm) * 3);
+                }
+                const float l0 = __fadd_rn(__fmul_rn(ifx, c[0]), __fmul_rn(fx, c[1]));
+                const float l1 = __fadd_rn(__fmul_rn(ifx, c[2]), __fmul_rn(fx, c[3]));
+                const float o = __fadd_rn(__fmul_rn(ify, l0), __fmul_rn(fy, l1));
+                const int dc = k / rows, dr = k - dc * rows;                         // column-major template element
+                F[dc * GS + dr] = o;
+            }
+        }
+    }
+    __syncthreads();
+    if (p.dump.gray) {
+        float *d = p.dump.gray + (long)job * p.dump.stride_px;
+        for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; d[idx] = F[x * GS + y]; }
+    }
+
+    // ------------------------------------------------------------------ P1: gradient magnitude + orientation bin
+    // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin)
+    float m0r[G::PIX_PER_THREAD];
+    unsigned char bnr[G::PIX_PER_THREAD];
+#pragma unroll
+    for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
+        const int idx = tid + q * NT;
+        m0r[q] = 0.f; bnr[q] = 0;
+        if (idx < H0 * W0) {
+            const int x = idx / H0, y = idx - x * H0;
+            const float *g = F + x * GS + y;
+            float gx, gy;
+            if (x == 0) gx = __fsub_rn(g[GS], g[0]);
+            else if (x == cols - 1) gx = __fsub_rn(g[0], g[-GS]);
+            else gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), .5f);
+            if (y == 0) gy = __fsub_rn(g[1], g[0]);
+            else if (y == rows - 1) gy = __fsub_rn(g[0], g[-1]);
+            else gy = __fmul_rn(__fsub_rn(g[1], g[-1]), .5f);
+            const float m2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
+            // RCPSQRT (rsqrtps) from the harvested table: exponent parity + top mantissa bits, exact 2^-q scaling
+            float m;
+            {
+                const uint32_t u = __float_as_uint(m2);
+                if (u < 0x00800000u) m = 1e10f;                       // rsqrtps(+0 / denormal) = +inf -> MIN(.,1e10f)
+                else {
+                    const int e = (int)(u >> 23) - 127;
+                    const uint32_t key = (u & 0x7FFFFFu) >> (23 - p.tab.rsqrt_bits);
+                    const uint32_t T = __float_as_uint(rs_tab[((e & 1) << p.tab.rsqrt_bits) + key]);
+                    m = __uint_as_float(T - ((uint32_t)(e >> 1) << 23));
+                    m = (m < 1e10f) ? m : 1e10f;
+                }
+            }
+            // RCP (rcpps) from the harvested table
+            float M;
+            {
+                const uint32_t u = __float_as_uint(m);
+                const int e = (int)(u >> 23) - 127;
+                const uint32_t U = __float_as_uint(rc_tab[(u & 0x7FFFFFu) >> (23 - p.tab.rcp_bits)]);
+                M = __uint_as_float(U - ((uint32_t)e << 23));
+            }
+            float gn = __fmul_rn(__fmul_rn(gx, m), 10000.0f);
+            gn = __uint_as_float(__float_as_uint(gn) ^ (__float_as_uint(gy) & 0x80000000u));
+            int ai = __float2int_rz(gn) + 10010;
+            ai = clampi(ai, 0, 20019);
+            const uint32_t ent = bn_tab[(gy < 0.f ? p.tab.bin_nseg : 0) + (ai >> p.tab.bin_shift)];
+            int bb = (int)(ent & 0xFFu) - ((uint32_t)ai >= (ent >> 8) ? 1 : 0);
+            if (bb >= 18) bb = 0;
+            m0r[q] = __fmul_rn(M, 0.0625f);                           // M0 = M * (1/bin^2), gradientMex.cpp:143
+            bnr[q] = (unsigned char)bb;
+        }
+    }
+    __syncthreads();
+    // (M0, bin) overwrite the gray patch, de-interleaved along y ([x][y&3][y>>2]) so that the cell-parallel gather below
+    // reads consecutive words
+    float *const M0s = F;
+    unsigned char *const Bs = reinterpret_cast<unsigned char *>(F + 16 * NB);
+#pragma unroll
+    for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
+        const int idx = tid + q * NT;
+        if (idx < H0 * W0) {
+            const int x = idx / H0, y = idx - x * H0;
+            const int a = x * H0 + (y & 3) * HR + (y >> 2);
+            M0s[a] = m0r[q]; Bs[a] = bnr[q];
+            if (p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = m0r[q]; p.dump.bin[(long)job * p.dump.stride_px + idx] = bnr[q]; }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ P2: 18-bin cell histograms by ordered gather
+    // libhog/gradientMex.cpp:183-221 (bilinear spatial interpolation, softBin<0) + :225-230 (boundary x 8/7).
+    // One thread owns one cell and adds its <= 8x8 contributing pixels in the reference's (x outer, y inner) order, so the
+    // sums are deterministic and equal to the reference's sequential scatter.
+    for (int cell = tid; cell < NB; cell += NT) {
+        const int cx = cell / HR, cy = cell - cx * HR;
+        float *const h = R1 + cx * RS + cy;
+#pragma unroll
+        for (int o = 0; o < 18; ++o) h[o * (WC * RS)] = 0.f;
+#pragma unroll 1
+        for (int dx = 0; dx < 8; ++dx) {
+            const int px = 4 * cx - 2 + dx;
+            if (px < 0 || px >= W0) continue;
+            const float wxv = 0.125f + 0.25f * (float)(dx < 4 ? dx : 7 - dx);
+#pragma unroll
+            for (int dy = 0; dy < 8; ++dy) {
+                const int py = 4 * cy - 2 + dy;
+                if (py < 0 || py >= H0) continue;
+                const float wyv = 0.125f + 0.25f * (float)(dy < 4 ? dy : 7 - dy);
+                const int a = px * H0 + (py & 3) * HR + (py >> 2);
+                const float v = __fmul_rn(wxv * wyv, M0s[a]);          // weights are dyadic: the product is exact
+                float *const hb = h + (int)Bs[a] * (WC * RS);
+                *hb = __fadd_rn(*hb, v);
+            }
+        }
+        float e = 0.f;
+        float r[18];
+#pragma unroll
+        for (int o = 0; o < 18; ++o) {
+            float v = h[o * (WC * RS)];
+            if (cx == 0) v = __fmul_rn(v, 8.f / 7.f);
+            if (cy == 0) v = __fmul_rn(v, 8.f / 7.f);
+            if (cx == WC - 1) v = __fmul_rn(v, 8.f / 7.f);
+            if (cy == HR - 1) v = __fmul_rn(v, 8.f / 7.f);
+            h[o * (WC * RS)] = v; r[o] = v;
+        }
+        // cell energy over the 9 contrast-insensitive bins, R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309, :242-243)
+#pragma unroll
+        for (int o = 0; o < 9; ++o) { const float r2 = __fadd_rn(r[o], r[o + 9]); e = __fadd_rn(e, __fmul_rn(r2, r2)); }
+        Es[cx * HR + cy] = e;
+    }
+    __syncthreads();
+    if (p.dump.r1) {
+        float *d = p.dump.r1 + (long)job * p.dump.stride_cell * 18;
+        for (int i = tid; i < 18 * NB; i += NT) { const int o = i / NB, c2 = i - o * NB, x = c2 / HR, y = c2 - x * HR; d[i] = R1[o * (WC * RS) + x * RS + y]; }
+    }
+
+    // ------------------------------------------------------------------ P3: 2x2 block normalisers (hogNormMatrix, :236-253)
+    for (int i = tid; i < G::N_FLOATS; i += NT) {
+        const int X = i / (HR + 1), Y = i - X * (HR + 1);
+        const int x = clampi(X, 1, WC - 1) - 1, y = clampi(Y, 1, HR - 1) - 1;
+        const float eps = 1e-4f / 4 / 4 / 4 / 4 / 4;
+        float e = __fadd_rn(Es[x * HR + y], Es[x * HR + y + 1]);
+        e = __fadd_rn(e, Es[(x + 1) * HR + y]);
+        e = __fadd_rn(e, Es[(x + 1) * HR + y + 1]);
+        e = __fadd_rn(e, eps);
+        Ns[i] = __fdiv_rn(1.0f, __fsqrt_rn(e));
+    }
+    __syncthreads();
+    if (p.dump.nrm) {
+        float *d = p.dump.nrm + (long)job * G::N_FLOATS;
+        for (int i = tid; i < G::N_FLOATS; i += NT) d[i] = Ns[i];
+    }
+
+    // ------------------------------------------------------------------ P4: channel columns -> window -> real FFT along rows
+    // hogChannels types 1 and 2 (gradientMex.cpp:256-280) generate channel c of column j straight into registers;
+    // x cos_win (kcf.cpp:251-258); r2c along the HR rows as one complex FFT of HR/2 points; packed store.
+    float2 *const F2 = reinterpret_cast<float2 *>(F);
+    for (int task = tid; task < KCF_CHAN * WC; task += NT) {
+        const int c = task / WC, j = task - c * WC;
+        float2 z[HK];
+        const float wxj = wx_s[j];
+        const float *const n0 = Ns + j * (HR + 1), *const n1 = n0 + (HR + 1);
+#pragma unroll
+        for (int i = 0; i < HR; ++i) {
+            float hsum;
+            if (c < 27) {
+                float rv;
+                if (c < 18) rv = R1[c * (WC * RS) + j * RS + i];
+                else rv = __fadd_rn(R1[(c - 18) * (WC * RS) + j * RS + i], R1[(c - 9) * (WC * RS) + j * RS + i]);
+                hsum = __fmul_rn(fminf(__fmul_rn(rv, n1[i + 1]), 0.2f), .5f);
+                hsum = __fadd_rn(hsum, __fmul_rn(fminf(__fmul_rn(rv, n1[i]), 0.2f), .5f));
+                hsum = __fadd_rn(hsum, __fmul_rn(fminf(__fmul_rn(rv, n0[i + 1]), 0.2f), .5f));
+                hsum = __fadd_rn(hsum, __fmul_rn(fminf(__fmul_rn(rv, n0[i]), 0.2f), .5f));
+            } else {
+                const int blk = c - 27;
+                const float nv = (blk == 0) ? n1[i + 1] : (blk == 1) ? n1[i] : (blk == 2) ? n0[i + 1] : n0[i];
+                hsum = 0.f;
+#pragma unroll
+                for (int o = 0; o < 18; ++o)
+                    hsum = __fadd_rn(hsum, __fmul_rn(fminf(__fmul_rn(R1[o * (WC * RS) + j * RS + i], nv), 0.2f), .2357f));
+            }
+            const float f = __fmul_rn(hsum, __fmul_rn(wy_s[i], wxj));
+            if (p.dump.feat) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j * HR + i] = f;
+            if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
+        }
+        fft_dif<HK, -1>(z);
+        const int sw = j & (HK - 1);
+        float2 *const dst = F2 + (c * WC + j) * HK;
+        {
+            const float2 z0 = z[0];
+            dst[0 ^ sw] = make_float2(z0.x + z0.y, z0.x - z0.y);      // (DC, Nyquist), both real
+        }
+#pragma unroll
+        for (int k = 1; k <= HK / 2; ++k) {
+            const float2 A = z[brev<HK>(k)], Bc = z[brev<HK>(HK - k)];
+            const int ti = (k * (64 / HR)) & 63;
+            const float cs = tw::C64[ti], sn = tw::S64[ti];
+            // X[k] = 1/2 [ (A + conj(B)) - i w^k (A - conj(B)) ],  w = exp(-2 pi i / HR)
+            {
+                const float sx_ = A.x + Bc.x, sy_ = A.y - Bc.y, dx_ = A.x - Bc.x, dy_ = A.y + Bc.y;
+                dst[k ^ sw] = make_float2(0.5f * (sx_ + dy_ * cs - dx_ * sn), 0.5f * (sy_ - dx_ * cs - dy_ * sn));
+            }
+            if (k != HK - k) {
+                // same formula for k' = HK - k: A' = B, B' = A, cos' = -cos, sin' = sin
+                const float sx_ = Bc.x + A.x, sy_ = Bc.y - A.y, dx_ = Bc.x - A.x, dy_ = Bc.y + A.y;
+                dst[(HK - k) ^ sw] = make_float2(0.5f * (sx_ - dy_ * cs - dx_ * sn), 0.5f * (sy_ + dx_ * cs - dy_ * sn));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ P5: complex FFT along the WC columns + spectral work
+    float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column products [31][WC]
+    float2 *const model = p.model + (long)slot * p.model_stride;
+    const bool first = (MODE == KCF_MODE_UPDATE) && meta->first_update != 0;
+    const float fac = first ? 1.0f : p.factor;                         // kcf.cpp:443
+    const float omf = __fsub_rn(1.0f, fac);
+    for (int task = tid; task < KCF_CHAN * HK; task += NT) {
+        const int c = task / HK, k = task - c * HK;
+        float2 a[WC];
+#pragma unroll
+        for (int j = 0; j < WC; ++j) a[j] = F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))];
+        fft_dif<WC, -1>(a);
+#pragma unroll
+        for (int j = 0; j < WC; ++j) {
+            const float2 x = a[brev<WC>(j)];
+            float2 v0 = x, v1 = make_float2(0.f, 0.f);
+            if (k == 0) {
+                // unpack the two real-input columns that shared slot 0: DC column and Nyquist column
+                const float2 y = a[brev<WC>((WC - j) % WC)];
+                v0 = make_float2(0.5f * (x.x + y.x), 0.5f * (x.y - y.y));
+                v1 = make_float2(0.5f * (x.y + y.y), 0.5f * (y.x - x.x));
+            }
+            const int sp0 = c * S + j * SK + k;                        // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186)
+            const int sp1 = c * S + j * SK + HK;
+            if (p.dump.spec) {
+                p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp0] = v0;
+                if (k == 0) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp1] = v1;
+            }
+            float2 o0, o1 = make_float2(0.f, 0.f);
+            if (MODE == KCF_MODE_PREDICT) {
+                // zf += xf * conj(model)   (kcf.cpp:306-345)
+                const float2 m0 = model[sp0];
+                o0 = make_float2(v0.x * m0.x + v0.y * m0.y, v0.y * m0.x - v0.x * m0.y);
+                if (k == 0) { const float2 m1 = model[sp1]; o1 = make_float2(v1.x * m1.x + v1.y * m1.y, v1.y * m1.x - v1.x * m1.y); }
+            } else {
+                // kf += |xf|^2 (kcf.cpp:269-293); model = (1-f) model + f xf (kcf.cpp:380-395)
+                o0 = make_float2(v0.x * v0.x + v0.y * v0.y, 0.f);
+                if (first) model[sp0] = v0;
+                else { const float2 m0 = model[sp0]; model[sp0] = make_float2(__fadd_rn(__fmul_rn(omf, m0.x), __fmul_rn(fac, v0.x)), __fadd_rn(__fmul_rn(omf, m0.y), __fmul_rn(fac, v0.y))); }
+                if (k == 0) {
+                    o1 = make_float2(v1.x * v1.x + v1.y * v1.y, 0.f);
+                    if (first) model[sp1] = v1;
+                    else { const float2 m1 = model[sp1]; model[sp1] = make_float2(__fadd_rn(__fmul_rn(omf, m1.x), __fmul_rn(fac, v1.x)), __fadd_rn(__fmul_rn(omf, m1.y), __fmul_rn(fac, v1.y))); }
+                }
+            }
+            F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))] = o0;
+            if (k == 0) FN[c * WC + j] = o1;
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ P6: sum over the 31 channels (in channel order)
+    float2 *const zf_s = FN + KCF_CHAN * WC;                           // [WC][SK]
+    float *const alpha = p.alpha + (long)slot * p.alpha_stride;
+    for (int e = tid; e < S; e += NT) {
+        const int j = e / SK, k = e - j * SK;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int c = 0; c < KCF_CHAN; ++c) {
+            const float2 v = (k < HK) ? F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))] : FN[c * WC + j];
+            if (c == 0) acc = v; else { acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); }
+        }
+        if (MODE == KCF_MODE_PREDICT) {
+            const float al = alpha[e];
+            acc.x = __fmul_rn(__fmul_rn(acc.x, al), cls.norm);         // kcf.cpp:356-357
+            acc.y = __fmul_rn(__fmul_rn(acc.y, al), cls.norm);
+            zf_s[e] = acc;
+            if (p.dump.zf) p.dump.zf[(long)job * p.dump.stride_spec + e] = acc;
+        } else {
+            const float kf = __fmul_rn(acc.x, cls.norm);               // kcf.cpp:295-303
+            if (p.dump.kf) p.dump.kf[(long)job * p.dump.stride_spec + e] = kf;
+            const float an = __fdiv_rn(cls.yf_re[e], __fadd_rn(kf, p.lamda));                // kcf.cpp:373
+            alpha[e] = __fadd_rn(__fmul_rn(omf, alpha[e]), __fmul_rn(fac, an));              // kcf.cpp:374
+        }
+    }
+    if (MODE == KCF_MODE_UPDATE) {
+        if (tid == 0) {
+            // tracker_update, kcf.cpp:462-476
+            meta->pos = box;
+            meta->scale_horiz = __fdiv_rn((float)(box.r - box.l + 1), (float)cols);
+            meta->scale_vert = __fdiv_rn((float)(box.b - box.t + 1), (float)rows);
+            meta->first_update = 0;
+        }
+        return;
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ P7: response = c2r(zf), first-max argmax, box shift
+    float *const resp = reinterpret_cast<float *>(zf_s + S);           // [WC][HR]
+    if (tid < SK) {
+        // inverse complex FFT along the WC columns for half-spectrum row k = tid
+        float2 a[WC];
+#pragma unroll
+        for (int j = 0; j < WC; ++j) a[j] = zf_s[j * SK + tid];
+        fft_dif<WC, +1>(a);
+#pragma unroll
+        for (int j = 0; j < WC; ++j) zf_s[j * SK + tid] = a[brev<WC>(j)];
+    }
+    __syncthreads();
+    if (tid < WC) {
+        // c2r along the HR rows of column j = tid: Hermitian half spectrum -> HR reals through one complex FFT of HR/2
+        const float2 *Y = zf_s + tid * SK;
+        float2 q[HK];
+        q[0] = make_float2(Y[0].x + Y[HK].x, Y[0].x - Y[HK].x);      // c2r ignores Im(DC), Im(Nyquist)
+#pragma unroll
+        for (int k = 1; k < HK; ++k) {
+            const float2 A = Y[k], B = Y[HK - k];
+            const int ti = (k * (64 / HR)) & 63;
+            const float cs = tw::C64[ti], sn = tw::S64[ti];
+            const float sx_ = A.x + B.x, sy_ = A.y - B.y, dx_ = A.x - B.x, dy_ = A.y + B.y;
+            // Q[k] = (A + conj(B)) + i exp(+2 pi i k / HR) (A - conj(B))
+            q[k] = make_float2(sx_ - dx_ * sn - dy_ * cs, sy_ + dx_ * cs - dy_ * sn);
+        }
+        fft_dif<HK, +1>(q);
+#pragma unroll
+        for (int m = 0; m < HK; ++m) { const float2 v = q[brev<HK>(m)]; resp[tid * HR + 2 * m] = v.x; resp[tid * HR + 2 * m + 1] = v.y; }
+    }
+    __syncthreads();
+    if (p.dump.resp) {
+        float *d = p.dump.resp + (long)job * p.dump.stride_cell;
+        for (int i = tid; i < NB; i += NT) d[i] = resp[i];
+    }
+    // first maximum in memory order (j outer, i inner), strict '>' from -99999 (kcf.cpp:402-417)
+    float best = -99999.0f; int besti = 0x7FFFFFFF;
+    for (int i = tid; i < NB; i += NT) { const float v = resp[i]; if (v > best) { best = v; besti = i; } }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_down_sync(0xFFFFFFFFu, best, off);
+        const int oi = __shfl_down_sync(0xFFFFFFFFu, besti, off);
+        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    int *const redi = reinterpret_cast<int *>(red) + 32;
+    if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = besti; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; ++w) { const float ov = red[w]; const int oi = redi[w]; if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; } }
+        int vd = 1, hd = 1;                                            // reference leaves these uninitialised when nothing beats -99999
+        if (besti != 0x7FFFFFFF) { hd = besti / HR + 1; vd = besti - (hd - 1) * HR + 1; }
+        if (p.dump.peak) { p.dump.peak[2 * job] = vd; p.dump.peak[2 * job + 1] = hd; }
+        if (vd > HR / 2) vd -= HR;                                     // kcf.cpp:419-420
+        if (hd > WC / 2) hd -= WC;
+        mot_bbox_t pos = meta->pos;
+        const float dv = __fmul_rn((float)(KCF_CELL * (vd - 1)), meta->scale_vert);
+        const float dh = __fmul_rn((float)(KCF_CELL * (hd - 1)), meta->scale_horiz);
+        pos.t = __float2int_rz(__fadd_rn((float)pos.t, dv));           // kcf.cpp:423-426 (float math, truncation)
+        pos.b = __float2int_rz(__fadd_rn((float)pos.b, dv));
+        pos.l = __float2int_rz(__fadd_rn((float)pos.l, dh));
+        pos.r = __float2int_rz(__fadd_rn((float)pos.r, dh));
+        meta->pos = pos;
+        if (p.clamp_to_frame) {                                        // top/td.cpp:378-381
+            pos.l = clampi(pos.l, 0, p.frame_w - 1); pos.r = clampi(pos.r, 0, p.frame_w - 1);
+            pos.t = clampi(pos.t, 0, p.frame_h - 1); pos.b = clampi(pos.b, 0, p.frame_h - 1);
+        }
+        p.boxes[job] = pos;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <int HR, int WC> static int launch_t(int mode, const KcfLaunch &p, cudaStream_t s)
+{
+    static bool configured[2] = { false, false };
+    const FhogTablesDev &t = p.tab;
+    int lut_floats = (2 << t.rsqrt_bits) + (1 << t.rcp_bits) + 2 * t.bin_nseg;
+    if (lut_floats > 8192) lut_floats = 0;                                      // too large: read the tables from global memory
+    const size_t bytes = smem_bytes<HR, WC>(lut_floats);
+    auto kp = kcf_fused_kernel<HR, WC, KCF_MODE_PREDICT>;
+    auto ku = kcf_fused_kernel<HR, WC, KCF_MODE_UPDATE>;
+    if (!configured[mode]) {
+        cudaError_t e = cudaFuncSetAttribute(mode == KCF_MODE_PREDICT ? (const void *)kp : (const void *)ku,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        configured[mode] = true;
+    }
+    if (mode == KCF_MODE_PREDICT) kp<<<p.n_jobs, KCF_THREADS, bytes, s>>>(p, lut_floats);
+    else                          ku<<<p.n_jobs, KCF_THREADS, bytes, s>>>(p, lut_floats);
+    return (int)cudaGetLastError();
+}
+
+#define MOT_KCF_SIZES(X) X(8, 8) X(8, 16) X(16, 8) X(16, 16) X(16, 32) X(32, 16) X(32, 32) X(8, 32) X(32, 8)
+
+int kcf_launch_fast(int mode, int hr, int wc, const KcfLaunch &p, cudaStream_t s)
+{
+#define X(H, W) if (hr == H && wc == W) return launch_t<H, W>(mode, p, s);
+    MOT_KCF_SIZES(X)
+#undef X
+    return -1000;
+}
+
+size_t kcf_fast_smem_bytes(int hr, int wc)
+{
+#define X(H, W) if (hr == H && wc == W) return smem_bytes<H, W>(4254);
+    MOT_KCF_SIZES(X)
+#undef X
+    return 0;
+}
+
+}  // namespace mot

@@ -1,0 +1,717 @@
+// mot_capi.cu -- the C ABI declared in include/mot_b200.h: context, frames, tracker slots, batched launches.
+// Host-side only bookkeeping; every numeric step of the hot path runs in the CUDA kernels of this directory.
+// There is deliberately NO CPU fallback: a missing device, a failed launch or an unsupported shape is an error.
+#include "mot_internal.h"
+#include "fhog_tables.h"
+#include "kalman.h"
+#include "assoc.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mot;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(MOT_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+
+namespace {
+
+struct SizeClass { int hr, wc, live; float *d_wy, *d_wx, *d_yf; float norm; };
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        n = std::max(want, n * 2);
+        return cudaMalloc(&p, sizeof(T) * n);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+template <class T> struct PinBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        n = std::max(want, n * 2);
+        return cudaMallocHost(&p, sizeof(T) * n);
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct mot_ctx_s {
+    int device = 0, W = 0, H = 0, max_tracks = 0, n_frames = 0, kind = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    long launches = 0;
+    // frames
+    std::vector<uint8_t *> frame_owned;
+    std::vector<const uint8_t *> frame_ptr_h;
+    const uint8_t **d_frame_ptr = nullptr;
+    bool frame_ptr_dirty = true;
+    int frame_stride = 0;
+    // track slots
+    std::vector<int> free_slots;
+    std::vector<char> used;
+    std::vector<KcfMeta> meta_h;          // host mirror of the immutable part (rows, cols, hr, wc, size_class)
+    KcfMeta *d_meta = nullptr;
+    float2 *d_model = nullptr; long model_stride = 0;
+    float *d_alpha = nullptr; long alpha_stride = 0;
+    std::vector<SizeClass> classes;
+    KcfClassDev *d_classes = nullptr;
+    FhogTablesDev tab{};
+    float *d_tab_rsqrt = nullptr, *d_tab_rcp = nullptr; uint32_t *d_tab_bin = nullptr;
+    KalmanState kal{};
+    // staging
+    DevBuf<int> d_slots, d_frames, d_TD, d_assign;
+    DevBuf<mot_bbox_t> d_boxes, d_trk, d_det;
+    DevBuf<KcfMeta> d_meta_stage;
+    DevBuf<float> d_gray;
+    DevBuf<double> d_dist, d_work, d_cost;
+    PinBuf<int> h_slots, h_frames, h_TD, h_assign;
+    PinBuf<mot_bbox_t> h_boxes, h_trk, h_det;
+    PinBuf<KcfMeta> h_meta_stage;
+    PinBuf<double> h_dist, h_cost;
+    // dumps
+    bool dumps = false;
+    KcfDump dump{};
+    int dump_hr = 0, dump_wc = 0, dump_rows = 0, dump_cols = 0;
+};
+
+static constexpr int MAX_CLASSES = 1024;
+
+__global__ void meta_scatter_kernel(KcfMeta *meta, const KcfMeta *src, const int *slots, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) meta[slots[i]] = src[i];
+}
+
+__global__ void zero_state_kernel(float2 *model, long model_stride, float *alpha, long alpha_stride, const int *slots, long n_model, long n_alpha)
+{
+    const int s = slots[blockIdx.y];
+    float2 *m = model + (long)s * model_stride;
+    float *a = alpha + (long)s * alpha_stride;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n_model; i += (long)gridDim.x * blockDim.x) m[i] = make_float2(0.f, 0.f);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n_alpha; i += (long)gridDim.x * blockDim.x) a[i] = 0.f;
+}
+
+// ---- per-size constants (trackers/kcf.cpp:96-144, 203-207) computed on the host in the reference's precision -------------
+static void hann_f(int N, std::vector<float> &h)
+{
+    const double PI_2 = 6.28318530717958647692;                     // include/sigpack/base/base.h:14
+    h.resize(N);
+    for (int i = 0; i < N; ++i) h[i] = (float)(0.5 - 0.5 * std::cos(1.0 * PI_2 * i / (N - 1)));   // window.h:34-48, 83-89
+}
+
+static void label_spectrum_re(int hr, int wc, std::vector<float> &yf_re)
+{
+    // gaussian_shaped_labels(0.7289, f_rows, f_cols) + circshift (kcf.cpp:96-122, 78-94), then Re(fft2) (kcf.cpp:132-144)
+    const float sigma = 0.7289f;
+    const float sinv = (float)(1.0 / (sigma * sigma));
+    std::vector<float> gx(hr), gy(wc), lab((size_t)hr * wc);
+    const int x0 = -hr / 2, y0 = -wc / 2;
+    for (int i = 0; i < hr; ++i) { const int x = x0 + i; gx[i] = (float)std::exp(-0.5 * x * x * sinv); }
+    for (int j = 0; j < wc; ++j) { const int y = y0 + j; gy[j] = (float)std::exp(-0.5 * y * y * sinv); }
+    for (int j = 0; j < wc; ++j) {
+        int jj = (j + y0) % wc; if (jj < 0) jj += wc;
+        for (int i = 0; i < hr; ++i) { int ii = (i + x0) % hr; if (ii < 0) ii += hr; lab[(size_t)jj * hr + ii] = gx[i] * gy[j]; }
+    }
+    // Y[j][k] = sum_a sum_b lab[a][b] exp(-2 pi i (j a / wc + k b / hr)); separable evaluation in double
+    const int sk = hr / 2 + 1;
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<double> tr((size_t)wc * sk), ti((size_t)wc * sk);
+    for (int a = 0; a < wc; ++a)
+        for (int k = 0; k < sk; ++k) {
+            double sr = 0, si = 0;
+            for (int b = 0; b < hr; ++b) {
+                const double ang = two_pi * (double)((long)k * b % hr) / hr;
+                sr += lab[(size_t)a * hr + b] * std::cos(ang); si -= lab[(size_t)a * hr + b] * std::sin(ang);
+            }
+            tr[(size_t)a * sk + k] = sr; ti[(size_t)a * sk + k] = si;
+        }
+    yf_re.resize((size_t)wc * sk);
+    for (int j = 0; j < wc; ++j)
+        for (int k = 0; k < sk; ++k) {
+            double sr = 0;
+            for (int a = 0; a < wc; ++a) {
+                const double ang = two_pi * (double)((long)j * a % wc) / wc;
+                sr += tr[(size_t)a * sk + k] * std::cos(ang) + ti[(size_t)a * sk + k] * std::sin(ang);
+            }
+            yf_re[(size_t)j * sk + k] = (float)sr;
+        }
+}
+
+static int get_class(mot_ctx_t *c, int hr, int wc, int *out)
+{
+    for (size_t i = 0; i < c->classes.size(); ++i) if (c->classes[i].hr == hr && c->classes[i].wc == wc) { *out = (int)i; return 0; }
+    if ((int)c->classes.size() >= MAX_CLASSES) return fail(MOT_ERR_CAPACITY, "too many distinct window sizes (%d)", MAX_CLASSES);
+    SizeClass sc{}; sc.hr = hr; sc.wc = wc; sc.live = 0;
+    sc.norm = (float)(1.0 / ((float)(wc * hr * 31)));                // kcf.cpp:197
+    std::vector<float> wy, wx, yf;
+    hann_f(hr, wy); hann_f(wc, wx); label_spectrum_re(hr, wc, yf);
+    CU(cudaMalloc(&sc.d_wy, sizeof(float) * hr)); CU(cudaMalloc(&sc.d_wx, sizeof(float) * wc)); CU(cudaMalloc(&sc.d_yf, sizeof(float) * yf.size()));
+    CU(cudaMemcpy(sc.d_wy, wy.data(), sizeof(float) * hr, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sc.d_wx, wx.data(), sizeof(float) * wc, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sc.d_yf, yf.data(), sizeof(float) * yf.size(), cudaMemcpyHostToDevice));
+    KcfClassDev kd{ hr, wc, sc.d_wy, sc.d_wx, sc.d_yf, sc.norm };
+    CU(cudaMemcpy(c->d_classes + c->classes.size(), &kd, sizeof(kd), cudaMemcpyHostToDevice));
+    c->classes.push_back(sc);
+    *out = (int)c->classes.size() - 1;
+    return 0;
+}
+
+static int sync_frame_ptrs(mot_ctx_t *c)
+{
+    if (!c->frame_ptr_dirty) return 0;
+    CU(cudaMemcpyAsync(c->d_frame_ptr, c->frame_ptr_h.data(), sizeof(void *) * c->n_frames, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));      // the host vector may change right after
+    c->frame_ptr_dirty = false;
+    return 0;
+}
+
+// =====================================================================================================================
+extern "C" {
+
+const char *mot_last_error(void) { return g_err.c_str(); }
+
+int mot_ctx_create(mot_ctx_t **out, int device, int frame_w, int frame_h, int max_tracks, int n_frame_slots, int tracker_kind)
+{
+    if (!out || frame_w <= 0 || frame_h <= 0 || max_tracks <= 0 || n_frame_slots <= 0) return fail(MOT_ERR_ARG, "mot_ctx_create: bad argument");
+    if (tracker_kind != MOT_TRACKER_KALMAN && tracker_kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "unknown tracker kind %d", tracker_kind);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return fail(MOT_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(MOT_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    const FhogTables &ft = fhog_tables();
+    if (!ft.ok) return fail(MOT_ERR_TABLES, "%s", ft.error.c_str());
+    mot_ctx_t *c = new mot_ctx_t();
+    c->device = device; c->W = frame_w; c->H = frame_h; c->max_tracks = max_tracks; c->n_frames = n_frame_slots; c->kind = tracker_kind;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    c->frame_owned.assign(n_frame_slots, nullptr);
+    c->frame_ptr_h.assign(n_frame_slots, nullptr);
+    c->frame_stride = frame_w * 3;
+    CU(cudaMalloc(&c->d_frame_ptr, sizeof(void *) * n_frame_slots));
+    c->used.assign(max_tracks, 0);
+    c->meta_h.assign(max_tracks, KcfMeta{});
+    for (int i = max_tracks - 1; i >= 0; --i) c->free_slots.push_back(i);
+    if (tracker_kind == MOT_TRACKER_KCF) {
+        c->model_stride = (long)KCF_CHAN * NB_MAX;                   // S <= nb <= NB_MAX
+        c->alpha_stride = NB_MAX;
+        CU(cudaMalloc(&c->d_meta, sizeof(KcfMeta) * max_tracks));
+        CU(cudaMalloc(&c->d_model, sizeof(float2) * c->model_stride * max_tracks));
+        CU(cudaMalloc(&c->d_alpha, sizeof(float) * c->alpha_stride * max_tracks));
+        CU(cudaMalloc(&c->d_classes, sizeof(KcfClassDev) * MAX_CLASSES));
+        CU(cudaMalloc(&c->d_tab_rsqrt, sizeof(float) * ft.rsqrt_tab.size()));
+        CU(cudaMalloc(&c->d_tab_rcp, sizeof(float) * ft.rcp_tab.size()));
+        CU(cudaMalloc(&c->d_tab_bin, sizeof(uint32_t) * ft.bin_tab.size()));
+        CU(cudaMemcpy(c->d_tab_rsqrt, ft.rsqrt_tab.data(), sizeof(float) * ft.rsqrt_tab.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_tab_rcp, ft.rcp_tab.data(), sizeof(float) * ft.rcp_tab.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_tab_bin, ft.bin_tab.data(), sizeof(uint32_t) * ft.bin_tab.size(), cudaMemcpyHostToDevice));
+        c->tab = FhogTablesDev{ c->d_tab_rsqrt, ft.rsqrt_bits, c->d_tab_rcp, ft.rcp_bits, c->d_tab_bin, ft.bin_shift, ft.bin_nseg };
+    } else {
+        c->kal.cap = max_tracks;
+        CU(cudaMalloc(&c->kal.x, sizeof(double) * 6 * max_tracks));
+        CU(cudaMalloc(&c->kal.P, sizeof(double) * 36 * max_tracks));
+    }
+    *out = c;
+    return 0;
+}
+
+void mot_ctx_destroy(mot_ctx_t *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto p : c->frame_owned) if (p) cudaFree(p);
+    cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
+    cudaFree(c->d_tab_rsqrt); cudaFree(c->d_tab_rcp); cudaFree(c->d_tab_bin); cudaFree(c->kal.x); cudaFree(c->kal.P);
+    for (auto &sc : c->classes) { cudaFree(sc.d_wy); cudaFree(sc.d_wx); cudaFree(sc.d_yf); }
+    c->d_slots.release(); c->d_frames.release(); c->d_TD.release(); c->d_assign.release(); c->d_boxes.release(); c->d_trk.release();
+    c->d_det.release(); c->d_meta_stage.release(); c->d_gray.release(); c->d_dist.release(); c->d_work.release(); c->d_cost.release();
+    c->h_slots.release(); c->h_frames.release(); c->h_TD.release(); c->h_assign.release(); c->h_boxes.release(); c->h_trk.release();
+    c->h_det.release(); c->h_meta_stage.release(); c->h_dist.release(); c->h_cost.release();
+    cudaFree(c->dump.gray); cudaFree(c->dump.m0); cudaFree(c->dump.bin); cudaFree(c->dump.r1); cudaFree(c->dump.nrm); cudaFree(c->dump.feat);
+    cudaFree(c->dump.spec); cudaFree(c->dump.zf); cudaFree(c->dump.resp); cudaFree(c->dump.kf); cudaFree(c->dump.peak); cudaFree(c->dump.margin);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int mot_ctx_set_stream(mot_ctx_t *c, void *s) { if (!c) return fail(MOT_ERR_ARG, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
+int mot_sync(mot_ctx_t *c) { if (!c) return fail(MOT_ERR_ARG, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+long mot_launch_count(mot_ctx_t *c) { return c ? c->launches : 0; }
+int mot_ctx_kind(mot_ctx_t *c) { return c ? c->kind : MOT_ERR_ARG; }
+
+// ---- frames ----------------------------------------------------------------------------------------------------------
+int mot_frame_upload(mot_ctx_t *c, int slot, const uint8_t *host_bgr, int stride_bytes)
+{
+    if (!c || slot < 0 || slot >= c->n_frames || !host_bgr) return fail(MOT_ERR_ARG, "mot_frame_upload: bad argument");
+    CU(cudaSetDevice(c->device));
+    if (!c->frame_owned[slot]) CU(cudaMalloc(&c->frame_owned[slot], (size_t)c->W * 3 * c->H));
+    if (c->frame_ptr_h[slot] != c->frame_owned[slot]) { c->frame_ptr_h[slot] = c->frame_owned[slot]; c->frame_ptr_dirty = true; }
+    if (c->frame_stride != c->W * 3) return fail(MOT_ERR_ARG, "mixing bound device frames of another stride with uploaded frames");
+    CU(cudaMemcpy2DAsync(c->frame_owned[slot], (size_t)c->W * 3, host_bgr, (size_t)stride_bytes, (size_t)c->W * 3, c->H, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int mot_frame_bind_device(mot_ctx_t *c, int slot, const uint8_t *dev_bgr, int stride_bytes)
+{
+    if (!c || slot < 0 || slot >= c->n_frames || !dev_bgr || stride_bytes < c->W * 3) return fail(MOT_ERR_ARG, "mot_frame_bind_device: bad argument");
+    bool any_other = false;
+    for (int i = 0; i < c->n_frames; ++i) if (i != slot && c->frame_ptr_h[i]) any_other = true;
+    if (any_other && stride_bytes != c->frame_stride) return fail(MOT_ERR_ARG, "all frame slots must share one stride (%d vs %d)", stride_bytes, c->frame_stride);
+    c->frame_stride = stride_bytes;
+    if (c->frame_ptr_h[slot] != dev_bgr) { c->frame_ptr_h[slot] = dev_bgr; c->frame_ptr_dirty = true; }
+    return 0;
+}
+
+// ---- tracker slots -----------------------------------------------------------------------------------------------------
+int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *handles_out)
+{
+    if (!c || n < 0 || (n && (!boxes || !handles_out))) return fail(MOT_ERR_ARG, "mot_tracker_new_batch: bad argument");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    if ((int)c->free_slots.size() < n) return fail(MOT_ERR_CAPACITY, "out of track slots (%d requested, %zu free)", n, c->free_slots.size());
+    CU(c->h_slots.ensure(n)); CU(c->d_slots.ensure(n));
+    if (c->kind == MOT_TRACKER_KCF) {
+        CU(c->h_meta_stage.ensure(n)); CU(c->d_meta_stage.ensure(n));
+        // validate everything first so that a failure leaves no half-created trackers
+        for (int i = 0; i < n; ++i) {
+            const int rows = boxes[i].b - boxes[i].t + 1, cols = boxes[i].r - boxes[i].l + 1;          // kcf.cpp:148-149
+            const int hr = rows / KCF_CELL, wc = cols / KCF_CELL;
+            if (hr < 2 || wc < 2) return fail(MOT_ERR_SHAPE, "window %dx%d px is smaller than 2x2 cells", rows, cols);
+            if (kcf_fast_smem_bytes(hr, wc) == 0)
+                return fail(MOT_ERR_SHAPE, "window %dx%d px = %dx%d cells: this build has fused kernels for 8/16/32-cell sides only", rows, cols, hr, wc);
+        }
+        long max_model = 0, max_alpha = 0;
+        for (int i = 0; i < n; ++i) {
+            KcfMeta m{};
+            m.rows = boxes[i].b - boxes[i].t + 1; m.cols = boxes[i].r - boxes[i].l + 1;
+            m.hr = m.rows / KCF_CELL; m.wc = m.cols / KCF_CELL;
+            m.pos = boxes[i]; m.scale_horiz = 1.0f; m.scale_vert = 1.0f; m.first_update = 1;          // kcf.cpp:200-209
+            int cls = 0; const int rc = get_class(c, m.hr, m.wc, &cls); if (rc) return rc;
+            m.size_class = cls;
+            const int slot = c->free_slots.back(); c->free_slots.pop_back();
+            c->used[slot] = 1; c->meta_h[slot] = m; c->classes[cls].live++;
+            c->h_slots.p[i] = slot; c->h_meta_stage.p[i] = m; handles_out[i] = slot;
+            const long S = (long)m.wc * (m.hr / 2 + 1);
+            max_model = std::max(max_model, KCF_CHAN * S); max_alpha = std::max(max_alpha, S);
+        }
+        CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_meta_stage.p, c->h_meta_stage.p, sizeof(KcfMeta) * n, cudaMemcpyHostToDevice, c->stream));
+        meta_scatter_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_meta, c->d_meta_stage.p, c->d_slots.p, n);
+        // xf_md and alpha start at zero (kcf.cpp:172-174)
+        zero_state_kernel<<<dim3(8, n), 256, 0, c->stream>>>(c->d_model, c->model_stride, c->d_alpha, c->alpha_stride, c->d_slots.p, max_model, max_alpha);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));      // staging buffers are reused by the next call
+    } else {
+        CU(c->h_boxes.ensure(n)); CU(c->d_boxes.ensure(n));
+        for (int i = 0; i < n; ++i) {
+            const int slot = c->free_slots.back(); c->free_slots.pop_back();
+            c->used[slot] = 1; c->h_slots.p[i] = slot; c->h_boxes.p[i] = boxes[i]; handles_out[i] = slot;
+        }
+        CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_boxes.p, c->h_boxes.p, sizeof(mot_bbox_t) * n, cudaMemcpyHostToDevice, c->stream));
+        const int rc = kalman_init(c->kal, n, c->d_slots.p, c->d_boxes.p, c->stream);
+        if (rc) return fail(MOT_ERR_CUDA, "kalman_init launch failed (%d)", rc);
+        c->launches += 1;
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int mot_tracker_delete_batch(mot_ctx_t *c, int n, const int *handles)
+{
+    if (!c || n < 0 || (n && !handles)) return fail(MOT_ERR_ARG, "mot_tracker_delete_batch: bad argument");
+    for (int i = 0; i < n; ++i) {
+        const int s = handles[i];
+        if (s < 0 || s >= c->max_tracks || !c->used[s]) return fail(MOT_ERR_ARG, "delete of invalid handle %d", s);
+        c->used[s] = 0;
+        if (c->kind == MOT_TRACKER_KCF) c->classes[c->meta_h[s].size_class].live--;
+        c->free_slots.push_back(s);
+    }
+    return 0;
+}
+
+// ---- KCF launches --------------------------------------------------------------------------------------------------------
+static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, const int *d_frames, mot_bbox_t *d_boxes, int clamp)
+{
+    L = KcfLaunch{};
+    L.n_jobs = n; L.slots = d_slots; L.frames = d_frames; L.boxes = d_boxes;
+    L.frame_ptr = c->d_frame_ptr; L.frame_w = c->W; L.frame_h = c->H; L.frame_stride = c->frame_stride;
+    L.gray = nullptr; L.gray_stride = 0;
+    L.meta = c->d_meta; L.model = c->d_model; L.model_stride = c->model_stride; L.alpha = c->d_alpha; L.alpha_stride = c->alpha_stride;
+    L.classes = c->d_classes; L.tab = c->tab; L.clamp_to_frame = clamp;
+    L.factor = 0.05f; L.lamda = 0.0001f;                                 // kcf.cpp:211-212
+    if (c->dumps) L.dump = c->dump;
+}
+
+static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
+{
+    const int rc = kcf_launch_fast(mode, hr, wc, L, c->stream);
+    if (rc == -1000) return fail(MOT_ERR_SHAPE, "no fused kernel for %dx%d cells", hr, wc);
+    if (rc) return fail(MOT_ERR_CUDA, "KCF launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
+}
+
+// host arrays: group the jobs by window size, one launch per size
+static int kcf_batch_host(mot_ctx_t *c, int mode, int n, const int *handles, const int *frame_slots, mot_bbox_t *boxes, int clamp, bool read_back)
+{
+    if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
+    if (n == 0) return 0;
+    if (!handles || !frame_slots || !boxes) return fail(MOT_ERR_ARG, "null array");
+    CU(cudaSetDevice(c->device));
+    { const int rc = sync_frame_ptrs(c); if (rc) return rc; }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) {
+        const int s = handles[i];
+        if (s < 0 || s >= c->max_tracks || !c->used[s]) return fail(MOT_ERR_ARG, "invalid handle %d", s);
+        if (frame_slots[i] < 0 || frame_slots[i] >= c->n_frames || !c->frame_ptr_h[frame_slots[i]]) return fail(MOT_ERR_ARG, "frame slot %d is empty", frame_slots[i]);
+        order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->meta_h[handles[a]].size_class < c->meta_h[handles[b]].size_class; });
+    CU(c->h_slots.ensure(n)); CU(c->h_frames.ensure(n)); CU(c->h_boxes.ensure(n));
+    CU(c->d_slots.ensure(n)); CU(c->d_frames.ensure(n)); CU(c->d_boxes.ensure(n));
+    for (int i = 0; i < n; ++i) { c->h_slots.p[i] = handles[order[i]]; c->h_frames.p[i] = frame_slots[order[i]]; c->h_boxes.p[i] = boxes[order[i]]; }
+    CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_frames.p, c->h_frames.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_boxes.p, c->h_boxes.p, sizeof(mot_bbox_t) * n, cudaMemcpyHostToDevice, c->stream));
+    for (int a = 0; a < n;) {
+        const int cls = c->meta_h[c->h_slots.p[a]].size_class;
+        int b = a; while (b < n && c->meta_h[c->h_slots.p[b]].size_class == cls) ++b;
+        KcfLaunch L; fill_launch(c, L, b - a, c->d_slots.p + a, c->d_frames.p + a, c->d_boxes.p + a, clamp);
+        if (c->dumps) { c->dump_hr = c->classes[cls].hr; c->dump_wc = c->classes[cls].wc; c->dump_rows = c->meta_h[c->h_slots.p[a]].rows; c->dump_cols = c->meta_h[c->h_slots.p[a]].cols; if (b - a != 1 || n != 1) return fail(MOT_ERR_ARG, "stage dumps need a batch of exactly one job"); }
+        const int rc = kcf_run(c, mode, c->classes[cls].hr, c->classes[cls].wc, L); if (rc) return rc;
+        a = b;
+    }
+    if (read_back) {
+        CU(cudaMemcpyAsync(c->h_boxes.p, c->d_boxes.p, sizeof(mot_bbox_t) * n, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < n; ++i) boxes[order[i]] = c->h_boxes.p[i];
+    } else {
+        CU(cudaStreamSynchronize(c->stream));     // staging buffers are reused by the next call
+    }
+    return 0;
+}
+
+static int kcf_batch_dev(mot_ctx_t *c, int mode, int n, const int *d_handles, const int *d_frame_slots, mot_bbox_t *d_boxes, int clamp)
+{
+    if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    { const int rc = sync_frame_ptrs(c); if (rc) return rc; }
+    int cls = -1;
+    for (size_t i = 0; i < c->classes.size(); ++i) if (c->classes[i].live > 0) { if (cls >= 0) return fail(MOT_ERR_SHAPE, "device-array batches need all live trackers to share one window size; use the host-array call"); cls = (int)i; }
+    if (cls < 0) return fail(MOT_ERR_ARG, "no live trackers");
+    KcfLaunch L; fill_launch(c, L, n, d_handles, d_frame_slots, d_boxes, clamp);
+    L.dump = KcfDump{};
+    return kcf_run(c, mode, c->classes[cls].hr, c->classes[cls].wc, L);
+}
+
+static int kalman_batch_host(mot_ctx_t *c, int mode, int n, const int *handles, mot_bbox_t *boxes, int clamp)
+{
+    if (n == 0) return 0;
+    if (!handles || !boxes) return fail(MOT_ERR_ARG, "null array");
+    CU(cudaSetDevice(c->device));
+    for (int i = 0; i < n; ++i) if (handles[i] < 0 || handles[i] >= c->max_tracks || !c->used[handles[i]]) return fail(MOT_ERR_ARG, "invalid handle %d", handles[i]);
+    CU(c->h_slots.ensure(n)); CU(c->h_boxes.ensure(n)); CU(c->d_slots.ensure(n)); CU(c->d_boxes.ensure(n));
+    memcpy(c->h_slots.p, handles, sizeof(int) * n); memcpy(c->h_boxes.p, boxes, sizeof(mot_bbox_t) * n);
+    CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_boxes.p, c->h_boxes.p, sizeof(mot_bbox_t) * n, cudaMemcpyHostToDevice, c->stream));
+    int rc;
+    if (mode == KCF_MODE_PREDICT) rc = kalman_predict(c->kal, n, c->d_slots.p, c->d_boxes.p, clamp, c->W, c->H, c->stream);
+    else rc = kalman_update(c->kal, n, c->d_slots.p, c->d_boxes.p, c->stream);
+    if (rc) return fail(MOT_ERR_CUDA, "Kalman launch failed (%d)", rc);
+    c->launches += 1;
+    if (mode == KCF_MODE_PREDICT) CU(cudaMemcpyAsync(c->h_boxes.p, c->d_boxes.p, sizeof(mot_bbox_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (mode == KCF_MODE_PREDICT) memcpy(boxes, c->h_boxes.p, sizeof(mot_bbox_t) * n);
+    return 0;
+}
+
+int mot_predict_batch(mot_ctx_t *c, int n, const int *handles, const int *frame_slots, mot_bbox_t *boxes, int clamp)
+{
+    if (!c || n < 0) return fail(MOT_ERR_ARG, "mot_predict_batch: bad argument");
+    if (c->kind == MOT_TRACKER_KCF) return kcf_batch_host(c, KCF_MODE_PREDICT, n, handles, frame_slots, boxes, clamp, true);
+    return kalman_batch_host(c, KCF_MODE_PREDICT, n, handles, boxes, clamp);
+}
+
+int mot_update_batch(mot_ctx_t *c, int n, const int *handles, const int *frame_slots, const mot_bbox_t *boxes)
+{
+    if (!c || n < 0) return fail(MOT_ERR_ARG, "mot_update_batch: bad argument");
+    if (c->kind == MOT_TRACKER_KCF) return kcf_batch_host(c, KCF_MODE_UPDATE, n, handles, frame_slots, const_cast<mot_bbox_t *>(boxes), 0, false);
+    return kalman_batch_host(c, KCF_MODE_UPDATE, n, handles, const_cast<mot_bbox_t *>(boxes), 0);
+}
+
+int mot_predict_batch_dev(mot_ctx_t *c, int n, const int *d_handles, const int *d_frame_slots, mot_bbox_t *d_boxes, int clamp)
+{
+    if (!c || n < 0) return fail(MOT_ERR_ARG, "mot_predict_batch_dev: bad argument");
+    if (c->kind == MOT_TRACKER_KCF) return kcf_batch_dev(c, KCF_MODE_PREDICT, n, d_handles, d_frame_slots, d_boxes, clamp);
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    const int rc = kalman_predict(c->kal, n, d_handles, d_boxes, clamp, c->W, c->H, c->stream);
+    if (rc) return fail(MOT_ERR_CUDA, "Kalman launch failed (%d)", rc);
+    c->launches += 1;
+    return 0;
+}
+
+int mot_update_batch_dev(mot_ctx_t *c, int n, const int *d_handles, const int *d_frame_slots, const mot_bbox_t *d_boxes)
+{
+    if (!c || n < 0) return fail(MOT_ERR_ARG, "mot_update_batch_dev: bad argument");
+    if (c->kind == MOT_TRACKER_KCF) return kcf_batch_dev(c, KCF_MODE_UPDATE, n, d_handles, d_frame_slots, const_cast<mot_bbox_t *>(d_boxes), 0);
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    const int rc = kalman_update(c->kal, n, d_handles, d_boxes, c->stream);
+    if (rc) return fail(MOT_ERR_CUDA, "Kalman launch failed (%d)", rc);
+    c->launches += 1;
+    return 0;
+}
+
+static int kcf_gray(mot_ctx_t *c, int mode, int handle, const float *gray_host, mot_bbox_t *box)
+{
+    if (!c || !box) return fail(MOT_ERR_ARG, "null argument");
+    if (c->kind != MOT_TRACKER_KCF) return kalman_batch_host(c, mode, 1, &handle, box, 0);     // Kalman ignores the patch (kalman.cpp:131-139)
+    if (!gray_host) return fail(MOT_ERR_ARG, "null gray patch");
+    if (handle < 0 || handle >= c->max_tracks || !c->used[handle]) return fail(MOT_ERR_ARG, "invalid handle %d", handle);
+    CU(cudaSetDevice(c->device));
+    const KcfMeta &m = c->meta_h[handle];
+    const size_t npx = (size_t)m.rows * m.cols;
+    CU(c->d_gray.ensure(npx)); CU(c->d_slots.ensure(1)); CU(c->d_boxes.ensure(1)); CU(c->h_boxes.ensure(1)); CU(c->h_slots.ensure(1));
+    c->h_slots.p[0] = handle; c->h_boxes.p[0] = *box;
+    CU(cudaMemcpyAsync(c->d_gray.p, gray_host, sizeof(float) * npx, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_boxes.p, c->h_boxes.p, sizeof(mot_bbox_t), cudaMemcpyHostToDevice, c->stream));
+    KcfLaunch L; fill_launch(c, L, 1, c->d_slots.p, nullptr, c->d_boxes.p, 0);
+    L.gray = c->d_gray.p; L.gray_stride = (long)npx;
+    if (c->dumps) { c->dump_hr = m.hr; c->dump_wc = m.wc; c->dump_rows = m.rows; c->dump_cols = m.cols; }
+    const int rc = kcf_run(c, mode, m.hr, m.wc, L); if (rc) return rc;
+    if (mode == KCF_MODE_PREDICT) CU(cudaMemcpyAsync(c->h_boxes.p, c->d_boxes.p, sizeof(mot_bbox_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (mode == KCF_MODE_PREDICT) *box = c->h_boxes.p[0];
+    return 0;
+}
+
+int mot_predict_gray(mot_ctx_t *c, int handle, const float *gray_host, mot_bbox_t *box_out) { return kcf_gray(c, KCF_MODE_PREDICT, handle, gray_host, box_out); }
+int mot_update_gray(mot_ctx_t *c, int handle, const float *gray_host, const mot_bbox_t *box) { mot_bbox_t b = *box; return kcf_gray(c, KCF_MODE_UPDATE, handle, gray_host, &b); }
+
+// ---- association ---------------------------------------------------------------------------------------------------------
+int mot_associate_batch_dev(mot_ctx_t *c, int n_mat, const int *d_T, const int *d_D, const mot_bbox_t *d_trk, long trk_stride,
+                            const mot_bbox_t *d_det, long det_stride, int cost_mode, double *d_dist, long dist_stride,
+                            int *d_assign, long assign_stride, double *d_cost, int max_dim)
+{
+    if (!c || n_mat < 0 || max_dim < 1 || max_dim > 1024) return fail(MOT_ERR_ARG, "mot_associate_batch_dev: bad argument (max_dim %d)", max_dim);
+    if (n_mat == 0) return 0;
+    if (!d_dist || dist_stride < (long)max_dim * max_dim) return fail(MOT_ERR_ARG, "the cost matrices need a device buffer of max_dim^2 doubles per problem");
+    CU(cudaSetDevice(c->device));
+    AssocLaunch A{};
+    A.n_mat = n_mat; A.T = d_T; A.D = d_D; A.trk = d_trk; A.trk_stride = trk_stride; A.det = d_det; A.det_stride = det_stride;
+    A.cost_mode = cost_mode; A.screen_dis = 1.0 / (double)c->W;
+    A.dist = d_dist; A.dist_stride = dist_stride; A.assign = d_assign; A.assign_stride = assign_stride; A.cost = d_cost; A.max_dim = max_dim;
+    CU(c->d_work.ensure((size_t)n_mat * max_dim * max_dim));
+    A.work = c->d_work.p; A.work_stride = (long)max_dim * max_dim;
+    int rc = assoc_cost(A, c->stream); if (rc) return fail(MOT_ERR_CUDA, "cost kernel launch failed (%d)", rc);
+    rc = assoc_solve(A, nullptr, c->stream); if (rc) return fail(MOT_ERR_CUDA, "munkres kernel launch failed (%d)", rc);
+    c->launches += 2;
+    return 0;
+}
+
+int mot_associate_batch(mot_ctx_t *c, int n_mat, const int *T, const int *D, const mot_bbox_t *trk, long trk_stride,
+                        const mot_bbox_t *det, long det_stride, int cost_mode, double *dist, long dist_stride,
+                        int *assign, long assign_stride, double *cost)
+{
+    if (!c || n_mat < 0 || (n_mat && (!T || !D || !trk || !det || !assign))) return fail(MOT_ERR_ARG, "mot_associate_batch: bad argument");
+    if (n_mat == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    int md = 1; long nt = 0, nd = 0;
+    for (int m = 0; m < n_mat; ++m) { md = std::max(md, std::max(T[m], D[m])); nt = std::max<long>(nt, T[m]); nd = std::max<long>(nd, D[m]); }
+    if (md > 1024) return fail(MOT_ERR_SHAPE, "association problems larger than 1024 are not supported (%d)", md);
+    nt = std::max<long>(nt, 1); nd = std::max<long>(nd, 1);
+    const long ds = (long)md * md;
+    CU(c->h_TD.ensure(2 * n_mat)); CU(c->d_TD.ensure(2 * n_mat));
+    CU(c->h_trk.ensure(nt * n_mat)); CU(c->d_trk.ensure(nt * n_mat)); CU(c->h_det.ensure(nd * n_mat)); CU(c->d_det.ensure(nd * n_mat));
+    CU(c->d_dist.ensure(ds * n_mat)); CU(c->d_assign.ensure((size_t)md * n_mat)); CU(c->d_cost.ensure(n_mat));
+    CU(c->h_assign.ensure((size_t)md * n_mat)); CU(c->h_cost.ensure(n_mat));
+    for (int m = 0; m < n_mat; ++m) {
+        c->h_TD.p[m] = T[m]; c->h_TD.p[n_mat + m] = D[m];
+        memcpy(c->h_trk.p + nt * m, trk + trk_stride * m, sizeof(mot_bbox_t) * T[m]);
+        memcpy(c->h_det.p + nd * m, det + det_stride * m, sizeof(mot_bbox_t) * D[m]);
+    }
+    CU(cudaMemcpyAsync(c->d_TD.p, c->h_TD.p, sizeof(int) * 2 * n_mat, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_trk.p, c->h_trk.p, sizeof(mot_bbox_t) * nt * n_mat, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_det.p, c->h_det.p, sizeof(mot_bbox_t) * nd * n_mat, cudaMemcpyHostToDevice, c->stream));
+    const int rc = mot_associate_batch_dev(c, n_mat, c->d_TD.p, c->d_TD.p + n_mat, c->d_trk.p, nt, c->d_det.p, nd, cost_mode,
+                                           c->d_dist.p, ds, c->d_assign.p, md, c->d_cost.p, md);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_assign.p, c->d_assign.p, sizeof(int) * (size_t)md * n_mat, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_cost.p, c->d_cost.p, sizeof(double) * n_mat, cudaMemcpyDeviceToHost, c->stream));
+    if (dist) { CU(c->h_dist.ensure(ds * n_mat)); CU(cudaMemcpyAsync(c->h_dist.p, c->d_dist.p, sizeof(double) * ds * n_mat, cudaMemcpyDeviceToHost, c->stream)); }
+    CU(cudaStreamSynchronize(c->stream));
+    for (int m = 0; m < n_mat; ++m) {
+        const int nr = T[m] < D[m] ? T[m] : D[m];
+        memcpy(assign + assign_stride * m, c->h_assign.p + (size_t)md * m, sizeof(int) * nr);
+        if (cost) cost[m] = c->h_cost.p[m];
+        if (dist) memcpy(dist + dist_stride * m, c->h_dist.p + ds * m, sizeof(double) * (size_t)T[m] * D[m]);
+    }
+    return 0;
+}
+
+int mot_assign_batch(mot_ctx_t *c, int n_mat, const int *nrows, const int *ncols, const double *dist, long dist_stride,
+                     int *assign, long assign_stride, double *cost)
+{
+    if (!c || n_mat < 0 || (n_mat && (!nrows || !ncols || !dist || !assign))) return fail(MOT_ERR_ARG, "mot_assign_batch: bad argument");
+    if (n_mat == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    int md = 1;
+    for (int m = 0; m < n_mat; ++m) md = std::max(md, std::max(nrows[m], ncols[m]));
+    if (md > 1024) return fail(MOT_ERR_SHAPE, "association problems larger than 1024 are not supported (%d)", md);
+    const long ds = (long)md * md;
+    CU(c->h_TD.ensure(2 * n_mat)); CU(c->d_TD.ensure(2 * n_mat));
+    CU(c->d_dist.ensure(ds * n_mat)); CU(c->h_dist.ensure(ds * n_mat)); CU(c->d_work.ensure(ds * n_mat));
+    CU(c->d_assign.ensure((size_t)md * n_mat)); CU(c->d_cost.ensure(n_mat)); CU(c->h_assign.ensure((size_t)md * n_mat)); CU(c->h_cost.ensure(n_mat));
+    for (int m = 0; m < n_mat; ++m) {
+        c->h_TD.p[2 * m] = nrows[m]; c->h_TD.p[2 * m + 1] = ncols[m];
+        memcpy(c->h_dist.p + ds * m, dist + dist_stride * m, sizeof(double) * (size_t)nrows[m] * ncols[m]);
+    }
+    CU(cudaMemcpyAsync(c->d_TD.p, c->h_TD.p, sizeof(int) * 2 * n_mat, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_dist.p, c->h_dist.p, sizeof(double) * ds * n_mat, cudaMemcpyHostToDevice, c->stream));
+    AssocLaunch A{};
+    A.n_mat = n_mat; A.dist = c->d_dist.p; A.dist_stride = ds; A.work = c->d_work.p; A.work_stride = ds;
+    A.assign = c->d_assign.p; A.assign_stride = md; A.cost = c->d_cost.p; A.max_dim = md;
+    const int rc = assoc_solve(A, c->d_TD.p, c->stream); if (rc) return fail(MOT_ERR_CUDA, "munkres kernel launch failed (%d)", rc);
+    c->launches += 1;
+    CU(cudaMemcpyAsync(c->h_assign.p, c->d_assign.p, sizeof(int) * (size_t)md * n_mat, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_cost.p, c->d_cost.p, sizeof(double) * n_mat, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int m = 0; m < n_mat; ++m) {
+        memcpy(assign + assign_stride * m, c->h_assign.p + (size_t)md * m, sizeof(int) * nrows[m]);
+        if (cost) cost[m] = c->h_cost.p[m];
+    }
+    return 0;
+}
+
+// ---- stand-alone crop + gray + resize ----------------------------------------------------------------------------------------
+int mot_crop_gray_resize(mot_ctx_t *c, int frame_slot, const mot_bbox_t *box, int rows_d, int cols_d, float *gray_host_out)
+{
+    // Served by the fused kernel's own front end through the stage dump, so there is exactly one implementation of it.
+    if (!c || !box || !gray_host_out) return fail(MOT_ERR_ARG, "null argument");
+    if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
+    mot_bbox_t tb{ 0, 0, rows_d - 1, cols_d - 1, 0, 0.f };
+    int h = -1;
+    int rc = mot_tracker_new_batch(c, 1, &tb, &h); if (rc) return rc;
+    const bool was = c->dumps;
+    rc = mot_debug_enable_dumps(c, 1);
+    mot_bbox_t b = *box;
+    if (!rc) rc = mot_predict_batch(c, 1, &h, &frame_slot, &b, 0);
+    if (!rc) { const long got = mot_debug_fetch(c, 0, gray_host_out, (long)sizeof(float) * rows_d * cols_d); if (got < 0) rc = (int)got; }
+    if (!was) mot_debug_enable_dumps(c, 0);
+    mot_tracker_delete_batch(c, 1, &h);
+    return rc;
+}
+
+// ---- test hooks ------------------------------------------------------------------------------------------------------------
+int mot_debug_enable_dumps(mot_ctx_t *c, int enable)
+{
+    if (!c) return fail(MOT_ERR_ARG, "null ctx");
+    if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
+    CU(cudaSetDevice(c->device));
+    if (enable && !c->dump.gray) {
+        const long px = 16L * NB_MAX + 64L * 64, cell = NB_MAX, spec = NB_MAX;
+        KcfDump &d = c->dump;
+        d.stride_px = px; d.stride_cell = cell; d.stride_spec = spec;
+        CU(cudaMalloc(&d.gray, sizeof(float) * px)); CU(cudaMalloc(&d.m0, sizeof(float) * px)); CU(cudaMalloc(&d.bin, sizeof(int) * px));
+        CU(cudaMalloc(&d.r1, sizeof(float) * cell * 18)); CU(cudaMalloc(&d.nrm, sizeof(float) * (cell + 4 * 64 + 8)));
+        CU(cudaMalloc(&d.feat, sizeof(float) * cell * KCF_CHAN)); CU(cudaMalloc(&d.spec, sizeof(float2) * spec * KCF_CHAN));
+        CU(cudaMalloc(&d.zf, sizeof(float2) * spec)); CU(cudaMalloc(&d.resp, sizeof(float) * cell)); CU(cudaMalloc(&d.kf, sizeof(float) * spec));
+        CU(cudaMalloc(&d.peak, sizeof(int) * 2)); CU(cudaMalloc(&d.margin, sizeof(float) * 2));
+    }
+    c->dumps = enable != 0;
+    return 0;
+}
+
+long mot_debug_fetch(mot_ctx_t *c, int stage, void *host_out, long max_bytes)
+{
+    if (!c || !host_out || !c->dump.gray) return fail(MOT_ERR_ARG, "dumps are not enabled");
+    cudaSetDevice(c->device);
+    const long hr = c->dump_hr, wc = c->dump_wc, nb = hr * wc, S = wc * (hr / 2 + 1), px = (long)c->dump_rows * c->dump_cols, px0 = 16 * nb;
+    const void *src = nullptr; long bytes = 0;
+    switch (stage) {
+    case 0: src = c->dump.gray; bytes = 4 * px; break;
+    case 1: src = c->dump.m0; bytes = 4 * px0; break;
+    case 2: src = c->dump.bin; bytes = 4 * px0; break;
+    case 3: src = c->dump.r1; bytes = 4 * 18 * nb; break;
+    case 4: src = c->dump.nrm; bytes = 4 * (wc + 1) * (hr + 1); break;
+    case 5: src = c->dump.feat; bytes = 4 * KCF_CHAN * nb; break;
+    case 6: src = c->dump.spec; bytes = 8 * KCF_CHAN * S; break;
+    case 7: src = c->dump.zf; bytes = 8 * S; break;
+    case 8: src = c->dump.resp; bytes = 4 * nb; break;
+    case 9: src = c->dump.kf; bytes = 4 * S; break;
+    case 10: src = c->dump.peak; bytes = 8; break;
+    default: return fail(MOT_ERR_ARG, "unknown stage %d", stage);
+    }
+    if (bytes > max_bytes) return fail(MOT_ERR_ARG, "buffer too small (%ld > %ld)", bytes, max_bytes);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(host_out, src, bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(MOT_ERR_CUDA, "dump fetch: %s", cudaGetErrorString(e));
+    return bytes;
+}
+
+long mot_debug_state(mot_ctx_t *c, int handle, int which, void *host_out, long max_bytes)
+{
+    if (!c || !host_out || handle < 0 || handle >= c->max_tracks || !c->used[handle]) return fail(MOT_ERR_ARG, "mot_debug_state: bad argument");
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(MOT_ERR_CUDA, "sync: %s", cudaGetErrorString(e));
+    if (c->kind == MOT_TRACKER_KCF) {
+        const KcfMeta &m = c->meta_h[handle];
+        const long S = (long)m.wc * (m.hr / 2 + 1);
+        if (which == 0) {
+            const long bytes = 8 * KCF_CHAN * S; if (bytes > max_bytes) return fail(MOT_ERR_ARG, "buffer too small");
+            e = cudaMemcpy(host_out, c->d_model + (long)handle * c->model_stride, bytes, cudaMemcpyDeviceToHost);
+            return e == cudaSuccess ? bytes : fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
+        }
+        if (which == 1) {
+            const long bytes = 4 * S; if (bytes > max_bytes) return fail(MOT_ERR_ARG, "buffer too small");
+            e = cudaMemcpy(host_out, c->d_alpha + (long)handle * c->alpha_stride, bytes, cudaMemcpyDeviceToHost);
+            return e == cudaSuccess ? bytes : fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
+        }
+        return fail(MOT_ERR_ARG, "unknown state %d for a KCF context", which);
+    }
+    if (which == 2 || which == 3) {
+        const int n = which == 2 ? 6 : 36;
+        if ((long)sizeof(double) * n > max_bytes) return fail(MOT_ERR_ARG, "buffer too small");
+        const double *base = which == 2 ? c->kal.x : c->kal.P;
+        e = cudaMemcpy2D(host_out, sizeof(double), base + handle, sizeof(double) * c->kal.cap, sizeof(double), n, cudaMemcpyDeviceToHost);
+        return e == cudaSuccess ? (long)sizeof(double) * n : fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
+    }
+    return fail(MOT_ERR_ARG, "unknown state %d for a Kalman context", which);
+}
+
+long mot_debug_tables(int which, float *out, long max_floats, int *info)
+{
+    const FhogTables &t = fhog_tables();
+    if (!t.ok) return fail(MOT_ERR_TABLES, "%s", t.error.c_str());
+    if (info) { info[0] = t.rsqrt_bits; info[1] = t.rcp_bits; info[2] = t.bin_shift; info[3] = t.bin_nseg; }
+    const std::vector<float> *v = which == 0 ? &t.rsqrt_tab : which == 1 ? &t.rcp_tab : which == 2 ? &t.acos_tab : nullptr;
+    if (!v) return fail(MOT_ERR_ARG, "unknown table %d", which);
+    if (out) { if ((long)v->size() > max_floats) return fail(MOT_ERR_ARG, "buffer too small"); memcpy(out, v->data(), sizeof(float) * v->size()); }
+    return (long)v->size();
+}
+
+}  // extern "C"

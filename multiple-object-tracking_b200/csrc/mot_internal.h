@@ -1,0 +1,80 @@
+// mot_internal.h -- device-side data model shared by the kernels and the C-ABI host layer.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/mot_b200.h"
+
+namespace mot {
+
+constexpr int KCF_CHAN = 31;          // trackers/kcf.cpp:157 f_chan = 32 - 1
+constexpr int KCF_CELL = 4;           // trackers/kcf.cpp:488
+constexpr int KCF_THREADS = 512;      // one CTA per track job
+constexpr int NB_MAX = 1152;          // cells per window the fused kernel can hold in shared memory (32x32 = 1024 named shape)
+
+// Per-track persistent state (one per slot), trackers/kcf.cpp:27-76 minus everything derivable.
+struct KcfMeta {
+    int rows, cols;                   // template size frozen at tracker_new (kcf.cpp:148-152)
+    int hr, wc;                       // f_rows, f_cols
+    mot_bbox_t pos;                   // pkcf->pos
+    float scale_horiz, scale_vert;    // kcf.cpp:470-472
+    int first_update;                 // kcf.cpp:209
+    int size_class;                   // index into the per-size constant tables
+};
+
+// Per-size constants shared by every track of the same window (kcf.cpp:203-207 are size-only).
+struct KcfClassDev {
+    int hr, wc;
+    const float *wy, *wx;             // hann_f(hr), hann_f(wc): cos_win = wy * wx^T (kcf.cpp:124-130)
+    const float *yf_re;               // Re(fft2(labels)), S floats (only the real part is ever used, kcf.cpp:373)
+    float norm;                       // feature_norm_ratio = 1/(wc*hr*31) (kcf.cpp:197)
+};
+
+struct FhogTablesDev {
+    const float *rsqrt_tab; int rsqrt_bits;
+    const float *rcp_tab; int rcp_bits;
+    const uint32_t *bin_tab; int bin_shift, bin_nseg;
+};
+
+// Optional stage dumps (all may be null).  Index = job * stride of that stage.
+struct KcfDump {
+    float *gray;        // rows*cols, column-major
+    float *m0;          // w0*h0 (x-major, y fastest): M * 1/16
+    int   *bin;         // w0*h0
+    float *r1;          // 18*wc*hr
+    float *nrm;         // (wc+1)*(hr+1)
+    float *feat;        // 31*wc*hr  (windowed features = xf_tm)
+    float2 *spec;       // 31*S      (xf_fq)
+    float2 *zf;         // S
+    float *resp;        // wc*hr
+    float *kf;          // S (real part)
+    int   *peak;        // 2 ints: vert_delta, horiz_delta (1-based, before wrap)
+    float *margin;      // 2 floats: best, second best response
+    long stride_px, stride_cell, stride_spec;   // per-job strides (elements) for px-sized / cell-sized / S-sized dumps
+};
+
+struct KcfLaunch {
+    int n_jobs;
+    const int *slots;                 // [n] track slot of each job
+    const int *frames;                // [n] frame slot of each job (ignored when gray != null)
+    mot_bbox_t *boxes;                // [n] predict: in = crop box, out = predicted box; update: in = new position / crop box
+    const uint8_t *const *frame_ptr;  // [n_frame_slots] device base pointers of BGR u8 frames
+    int frame_w, frame_h, frame_stride;
+    const float *gray;                // optional: [n] pre-cropped gray patches (rows*cols col-major, stride gray_stride floats)
+    long gray_stride;
+    KcfMeta *meta;
+    float2 *model; long model_stride; // xf_md, slot stride in float2
+    float *alpha; long alpha_stride;  // slot stride in floats
+    const KcfClassDev *classes;
+    FhogTablesDev tab;
+    int clamp_to_frame;               // fold top/td.cpp:378-381 into predict
+    float factor, lamda;              // kcf.cpp:211-212
+    KcfDump dump;
+};
+
+enum { KCF_MODE_PREDICT = 0, KCF_MODE_UPDATE = 1 };
+
+// returns 0 when (hr, wc) has a register-FFT instantiation
+int kcf_launch_fast(int mode, int hr, int wc, const KcfLaunch &p, cudaStream_t s);
+size_t kcf_fast_smem_bytes(int hr, int wc);
+
+}  // namespace mot

@@ -1,0 +1,54 @@
+"""CPU-side checks of the product library: it builds, loads, exports every symbol include/mot_b200.h declares,
+and refuses to run without a CUDA device (no CPU fallback).  No compute calls are made here."""
+import os
+import re
+
+import pytest
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import mot_b200
+    mot_b200.build()
+    L = mot_b200.lib()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "mot_b200.h")).read()
+    declared = set(re.findall(r"\b(mot_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(L, name), "libmot_b200.so does not export %s" % name
+    assert declared == set(mot_b200.EXPORTS), declared ^ set(mot_b200.EXPORTS)
+
+
+def test_reference_plugin_symbols_are_exported():
+    """The C++-linkage symbols top/td.cpp:229-234 declares must be link-compatible."""
+    import subprocess
+    import mot_b200
+    out = subprocess.run(["nm", "-D", "--defined-only", mot_b200.LIB_PATH], capture_output=True, text=True).stdout
+    for mangled in ("_Z11tracker_newP10mot_bbox_s", "_Z15tracker_predictPvPfP10mot_bbox_s", "_Z14tracker_updatePvPfP10mot_bbox_s",
+                    "_Z14tracker_deletePv", "_Z17assignmentoptimalPiPdS0_ii"):
+        assert mangled in out, mangled
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    import mot_b200
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(mot_b200.MotError):
+        mot_b200.Context(640, 480)
+
+
+def test_sse_tables_match_the_oracle_acos_table(port):
+    """The host-harvested tables are part of the product; pin the acos table against the oracle's (bit-exact)."""
+    import ctypes as C
+    import numpy as np
+    import mot_b200
+    info = (C.c_int * 4)()
+    n = mot_b200.lib().mot_debug_tables(2, None, 0, info)
+    assert n == 20020
+    a = np.zeros(n, np.float32)
+    assert mot_b200.lib().mot_debug_tables(2, a.ctypes.data_as(C.c_void_p), n, info) == n
+    b = np.zeros(20020, np.float32)
+    port.kcf.port_acos_table(b.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(a, b)
+    assert 6 <= info[0] <= 14 and 6 <= info[1] <= 14

@@ -1,0 +1,64 @@
+"""GPU parity: the batched frame loop (host/td_loop.cpp over the C ABI) vs the oracle's loop, both tracker kinds."""
+import numpy as np
+import pytest
+
+from synth import Scene
+from gpu_common import require_gpu, mot
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tracker,mode", [("kal", 0), ("kal", 1), ("kcf", 0)])
+def test_frame_loop_trace(oracle, tracker, mode):
+    require_gpu()
+    M = mot()
+    W, H = 1280, 720
+    n = 24 if tracker == "kal" else 10
+    sc = Scene(211 + mode, W, H, n, tsize=40, win=64)
+    ctx = M.Context(W, H, max_tracks=128, n_frame_slots=1, kind=M.TRACKER_KCF if tracker == "kcf" else M.TRACKER_KALMAN)
+    td = ctx.td(0, cap=64, cost_mode=mode)
+    ref = oracle.td_new(tracker, W, H, 64, mode)
+    drng = np.random.default_rng(4)
+    for f in range(60 if tracker == "kal" else 25):
+        sc.step()
+        frame = sc.render()
+        dets = sc.windows(jitter=2)
+        keep = drng.random(len(dets)) > 0.1
+        dets = np.ascontiguousarray(dets[keep])
+        if f % 7 == 3:          # a false positive now and then (spawns a short-lived track)
+            fp = dets[:1].copy(); fp["l"] += 300; fp["r"] += 300; fp["l"] %= (W - 80); fp["r"] = fp["l"] + 63
+            dets = np.ascontiguousarray(np.concatenate([dets, fp]))
+        td.step(frame, dets); ref.step(frame, dets)
+        a, b = td.tracks(), ref.tracks()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (f, k)
+        pa, aa = td.last(); pb, ab = ref.last()
+        assert np.array_equal(pa, pb), f
+        assert np.array_equal(aa, ab), f
+    td.close(); ref.close(); ctx.close()
+
+
+def test_multi_stream_lockstep_equals_single(oracle):
+    require_gpu()
+    M = mot()
+    W, H = 640, 480
+    ns = 3
+    scs = [Scene(900 + s, W, H, 5, tsize=32, win=64) for s in range(ns)]
+    ctx = M.Context(W, H, max_tracks=128, n_frame_slots=ns, kind=M.TRACKER_KCF)
+    tds = [ctx.td(s, cap=32) for s in range(ns)]
+    refs = [oracle.td_new("kcf", W, H, 32, 0) for _ in range(ns)]
+    for f in range(10):
+        frames, dets = [], []
+        for sc in scs:
+            sc.step(); frames.append(sc.render()); dets.append(sc.windows(jitter=1))
+        M.step_multi(tds, frames, dets)
+        for s in range(ns):
+            refs[s].step(frames[s], dets[s])
+            a, b = tds[s].tracks(), refs[s].tracks()
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (f, s, k)
+    for t in tds:
+        t.close()
+    for r in refs:
+        r.close()
+    ctx.close()
