@@ -1,4 +1,4 @@
-// kcf_fused.cu -- the fused KCF/DCF kernels: one CTA per (track, frame) job, everything between the BGR frame
+// kcf_fused.cuh -- the fused KCF/DCF kernels: one CTA per (track, frame) job, everything between the BGR frame
 // bytes and the updated model in ONE launch, so a track touches HBM once per predict and once per update.
 //
 // Replaces, for one track (reference paths relative to its root):
@@ -19,6 +19,7 @@
 // Arithmetic follows the reference operation by operation where its rounding is observable (gray in double, unfused
 // f32 MUL/ADD in fHOG via __fmul_rn/__fadd_rn, SSE rsqrt/rcp through host-harvested tables, the histogram summed in the
 // reference's pixel order); the FFTs and the spectral products are ordinary f32.
+#pragma once
 #include "mot_internal.h"
 #include "fft_reg.cuh"
 
@@ -59,7 +60,9 @@ __device__ __forceinline__ float bgr_gray(const uint8_t *p)
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-template <int HR, int WC, int MODE>
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int HR, int WC, int MODE, bool DUMP>
 __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaunch p, const int lut_floats)
 {
     using G = Geo<HR, WC>;
@@ -82,6 +85,14 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     const KcfClassDev cls = p.classes[meta->size_class];
     const int rows = meta->rows, cols = meta->cols;
     mot_bbox_t box = p.boxes[job];
+
+    // The model (31*S complex) is not needed before P5, tens of microseconds from now: pull it into L2 now so that P5
+    // sees L2 latency instead of HBM latency (there is no shared memory left to stage it in).
+    if (MODE == KCF_MODE_PREDICT || meta->first_update == 0) {
+        const char *mp = reinterpret_cast<const char *>(p.model + (long)slot * p.model_stride);
+        for (int o = tid * 128; o < KCF_CHAN * S * 8; o += NT * 128) prefetch_l2(mp + o);
+    }
+    if (tid < (S * 4 + 127) / 128) prefetch_l2(reinterpret_cast<const char *>(p.alpha + (long)slot * p.alpha_stride) + tid * 128);
 
     // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
     const bool lut_smem = lut_floats > 0;
@@ -109,10 +120,19 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
         if (rows_s == rows && cols_s == cols) {
             // equal sizes: bilinearInterpolationGray degenerates to an exact copy (top/drawlib.c:610-633 with xs = ys = 1)
-            for (int idx = tid; idx < rows * cols; idx += NT) {
-                const int y = idx / cols, x = idx - y * cols;
-                const uint8_t *px = frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + clampi(l + x, 0, Wm) * 3;
-                F[x * GS + y] = bgr_gray(px);
+            // one warp per frame row (coalesced 3-byte pixels), two rows in flight per warp
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int y = warp; y < rows; y += 2 * (NT / 32)) {
+                const int y2 = y + NT / 32;
+                const uint8_t *r0 = frame + (long)clampi(t + y, 0, Hm) * p.frame_stride;
+                const uint8_t *r1 = frame + (long)clampi(t + (y2 < rows ? y2 : y), 0, Hm) * p.frame_stride;
+#pragma unroll 2
+                for (int x = lane; x < cols; x += 32) {
+                    const int xo = clampi(l + x, 0, Wm) * 3;
+                    const float g0 = bgr_gray(r0 + xo), g1 = bgr_gray(r1 + xo);
+                    F[x * GS + y] = g0;
+                    if (y2 < rows) F[x * GS + y2] = g1;
+                }
             }
         } else {
             // the reference resamples a column-major crop as if it were row-major height x width; reproduced through
@@ -141,7 +161,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         }
     }
     __syncthreads();
-    if (p.dump.gray) {
+    if (DUMP && p.dump.gray) {
         float *d = p.dump.gray + (long)job * p.dump.stride_px;
         for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; d[idx] = F[x * GS + y]; }
     }
@@ -157,13 +177,11 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         if (idx < H0 * W0) {
             const int x = idx / H0, y = idx - x * H0;
             const float *g = F + x * GS + y;
-            float gx, gy;
-            if (x == 0) gx = __fsub_rn(g[GS], g[0]);
-            else if (x == cols - 1) gx = __fsub_rn(g[0], g[-GS]);
-            else gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), .5f);
-            if (y == 0) gy = __fsub_rn(g[1], g[0]);
-            else if (y == rows - 1) gy = __fsub_rn(g[0], g[-1]);
-            else gy = __fmul_rn(__fsub_rn(g[1], g[-1]), .5f);
+            // grad1: one-sided difference (x1) on the border, central difference (x0.5) inside -- as clamped neighbours
+            const int xm = x > 0 ? -GS : 0, xp = x < cols - 1 ? GS : 0, ym = y > 0 ? -1 : 0, yp = y < rows - 1 ? 1 : 0;
+            const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f, ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
+            const float gx = __fmul_rn(__fsub_rn(g[xp], g[xm]), rx);
+            const float gy = __fmul_rn(__fsub_rn(g[yp], g[ym]), ry);
             const float m2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
             // RCPSQRT (rsqrtps) from the harvested table: exponent parity + top mantissa bits, exact 2^-q scaling
             float m;
@@ -209,7 +227,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             const int x = idx / H0, y = idx - x * H0;
             const int a = x * H0 + (y & 3) * HR + (y >> 2);
             M0s[a] = m0r[q]; Bs[a] = bnr[q];
-            if (p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = m0r[q]; p.dump.bin[(long)job * p.dump.stride_px + idx] = bnr[q]; }
+            if (DUMP && p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = m0r[q]; p.dump.bin[(long)job * p.dump.stride_px + idx] = bnr[q]; }
         }
     }
     __syncthreads();
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         Es[cx * HR + cy] = e;
     }
     __syncthreads();
-    if (p.dump.r1) {
+    if (DUMP && p.dump.r1) {
         float *d = p.dump.r1 + (long)job * p.dump.stride_cell * 18;
         for (int i = tid; i < 18 * NB; i += NT) { const int o = i / NB, c2 = i - o * NB, x = c2 / HR, y = c2 - x * HR; d[i] = R1[o * (WC * RS) + x * RS + y]; }
     }
@@ -273,42 +291,70 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         Ns[i] = __fdiv_rn(1.0f, __fsqrt_rn(e));
     }
     __syncthreads();
-    if (p.dump.nrm) {
+    if (DUMP && p.dump.nrm) {
         float *d = p.dump.nrm + (long)job * G::N_FLOATS;
         for (int i = tid; i < G::N_FLOATS; i += NT) d[i] = Ns[i];
     }
 
-    // ------------------------------------------------------------------ P4: channel columns -> window -> real FFT along rows
-    // hogChannels types 1 and 2 (gradientMex.cpp:256-280) generate channel c of column j straight into registers;
-    // x cos_win (kcf.cpp:251-258); r2c along the HR rows as one complex FFT of HR/2 points; packed store.
+    // ------------------------------------------------------------------ P4a: the four texture channels (hogChannels type 2)
+    // gradientMex.cpp:271-275: channel 27+blk = sum over the 18 orientations of min(R1*N_blk, 0.2) * 0.2357, accumulated in
+    // orientation order.  One thread per cell shares each R1 load between the four block normalisers.  The values go, as
+    // plain floats rotated by the column index (bank-conflict free for the column-wise reader below), into the F slots of
+    // channels 27..30, which P4b then transforms in place.
+    for (int cell = tid; cell < NB; cell += NT) {
+        const int j = cell / HR, i = cell - j * HR;
+        const float *const n0 = Ns + j * (HR + 1) + i, *const n1 = n0 + (HR + 1);
+        const float nv0 = n1[1], nv1 = n1[0], nv2 = n0[1], nv3 = n0[0];      // GETT(0), GETT(1), GETT(hb1), GETT(hb1+1)
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+        const float *rp = R1 + j * RS + i;
+#pragma unroll 6
+        for (int o = 0; o < 18; ++o) {
+            const float rv = rp[o * (WC * RS)];
+            h0 = __fadd_rn(h0, __fmul_rn(fminf(__fmul_rn(rv, nv0), 0.2f), .2357f));
+            h1 = __fadd_rn(h1, __fmul_rn(fminf(__fmul_rn(rv, nv1), 0.2f), .2357f));
+            h2 = __fadd_rn(h2, __fmul_rn(fminf(__fmul_rn(rv, nv2), 0.2f), .2357f));
+            h3 = __fadd_rn(h3, __fmul_rn(fminf(__fmul_rn(rv, nv3), 0.2f), .2357f));
+        }
+        const int rot = (i + j) & (HR - 1);
+        F[(27 * WC + j) * HR + rot] = h0; F[(28 * WC + j) * HR + rot] = h1;
+        F[(29 * WC + j) * HR + rot] = h2; F[(30 * WC + j) * HR + rot] = h3;
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ P4b: channel columns -> window -> real FFT along rows
+    // hogChannels type 1 (gradientMex.cpp:266-270) generates channel c of column j straight into registers: the four
+    // clipped products are halved and added in block order; halving commutes exactly with the additions, so the sum is
+    // formed first and halved once.  x cos_win (kcf.cpp:251-258); r2c along the HR rows as ONE complex FFT of HR/2 points;
+    // packed store (DC and Nyquist, both real, share slot 0).
     float2 *const F2 = reinterpret_cast<float2 *>(F);
     for (int task = tid; task < KCF_CHAN * WC; task += NT) {
         const int c = task / WC, j = task - c * WC;
         float2 z[HK];
         const float wxj = wx_s[j];
-        const float *const n0 = Ns + j * (HR + 1), *const n1 = n0 + (HR + 1);
+        if (c < 27) {
+            const float *const n0 = Ns + j * (HR + 1), *const n1 = n0 + (HR + 1);
+            const float *const ra = R1 + (c < 18 ? c : c - 18) * (WC * RS) + j * RS;
+            const float *const rb = R1 + (c < 18 ? c : c - 9) * (WC * RS) + j * RS;
 #pragma unroll
-        for (int i = 0; i < HR; ++i) {
-            float hsum;
-            if (c < 27) {
-                float rv;
-                if (c < 18) rv = R1[c * (WC * RS) + j * RS + i];
-                else rv = __fadd_rn(R1[(c - 18) * (WC * RS) + j * RS + i], R1[(c - 9) * (WC * RS) + j * RS + i]);
-                hsum = __fmul_rn(fminf(__fmul_rn(rv, n1[i + 1]), 0.2f), .5f);
-                hsum = __fadd_rn(hsum, __fmul_rn(fminf(__fmul_rn(rv, n1[i]), 0.2f), .5f));
-                hsum = __fadd_rn(hsum, __fmul_rn(fminf(__fmul_rn(rv, n0[i + 1]), 0.2f), .5f));
-                hsum = __fadd_rn(hsum, __fmul_rn(fminf(__fmul_rn(rv, n0[i]), 0.2f), .5f));
-            } else {
-                const int blk = c - 27;
-                const float nv = (blk == 0) ? n1[i + 1] : (blk == 1) ? n1[i] : (blk == 2) ? n0[i + 1] : n0[i];
-                hsum = 0.f;
-#pragma unroll
-                for (int o = 0; o < 18; ++o)
-                    hsum = __fadd_rn(hsum, __fmul_rn(fminf(__fmul_rn(R1[o * (WC * RS) + j * RS + i], nv), 0.2f), .2357f));
+            for (int i = 0; i < HR; ++i) {
+                const float rv = (c < 18) ? ra[i] : __fadd_rn(ra[i], rb[i]);       // R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309)
+                float hsum = __fadd_rn(fminf(__fmul_rn(rv, n1[i + 1]), 0.2f), fminf(__fmul_rn(rv, n1[i]), 0.2f));
+                hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i + 1]), 0.2f));
+                hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i]), 0.2f));
+                const float f = __fmul_rn(__fmul_rn(hsum, .5f), __fmul_rn(wy_s[i], wxj));
+                if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
             }
-            const float f = __fmul_rn(hsum, __fmul_rn(wy_s[i], wxj));
-            if (p.dump.feat) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j * HR + i] = f;
-            if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
+        } else {
+            const float *const tp = F + (c * WC + j) * HR;
+#pragma unroll
+            for (int i = 0; i < HR; ++i) {
+                const float f = __fmul_rn(tp[(i + j) & (HR - 1)], __fmul_rn(wy_s[i], wxj));
+                if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
+            }
+        }
+        if (DUMP && p.dump.feat) {
+#pragma unroll
+            for (int i = 0; i < HR; ++i) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j * HR + i] = (i & 1) ? z[i >> 1].y : z[i >> 1].x;
         }
         fft_dif<HK, -1>(z);
         const int sw = j & (HK - 1);
@@ -337,52 +383,99 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     __syncthreads();
 
     // ------------------------------------------------------------------ P5: complex FFT along the WC columns + spectral work
+    // Tasks (channel c, packed bin k).  Bins k >= 1 are ordinary columns; bin 0 carries two real-input columns (DC and
+    // Nyquist) that are separated after the transform.  The two kinds are kept in different warps (no divergence):
+    // threads [0, 31*(HK-1)) take k >= 1, the warp(s) from K0_BASE on take k = 0.
     float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column products [31][WC]
     float2 *const model = p.model + (long)slot * p.model_stride;
     const bool first = (MODE == KCF_MODE_UPDATE) && meta->first_update != 0;
     const float fac = first ? 1.0f : p.factor;                         // kcf.cpp:443
     const float omf = __fsub_rn(1.0f, fac);
-    for (int task = tid; task < KCF_CHAN * HK; task += NT) {
-        const int c = task / HK, k = task - c * HK;
+    constexpr int N_K1 = KCF_CHAN * (HK - 1);
+    constexpr int K0_BASE = (N_K1 + 31) & ~31;
+    static_assert(K0_BASE + KCF_CHAN <= NT, "P5 task layout");
+    if (tid < N_K1 || (tid >= K0_BASE && tid < K0_BASE + KCF_CHAN)) {
+        const bool k0 = tid >= K0_BASE;
+        const int c = k0 ? tid - K0_BASE : tid / (HK - 1);
+        const int k = k0 ? 0 : tid - c * (HK - 1) + 1;
+        const float2 *const mrow = model + c * S + k;                  // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186): + j*SK
+        constexpr int CH = 8, C0 = 4;                                  // model values in flight per thread (k >= 1 / k = 0 tasks)
+        float2 mpre[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) mpre[q] = make_float2(0.f, 0.f);
+        const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
+        if (need_model) {
+#pragma unroll
+            for (int q = 0; q < CH; ++q) if (!k0 || q < C0) mpre[q] = mrow[q * SK];   // first chunk: its latency hides behind the FFT below
+        }
         float2 a[WC];
 #pragma unroll
         for (int j = 0; j < WC; ++j) a[j] = F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))];
         fft_dif<WC, -1>(a);
+        if (!k0) {
 #pragma unroll
-        for (int j = 0; j < WC; ++j) {
-            const float2 x = a[brev<WC>(j)];
-            float2 v0 = x, v1 = make_float2(0.f, 0.f);
-            if (k == 0) {
-                // unpack the two real-input columns that shared slot 0: DC column and Nyquist column
-                const float2 y = a[brev<WC>((WC - j) % WC)];
-                v0 = make_float2(0.5f * (x.x + y.x), 0.5f * (x.y - y.y));
-                v1 = make_float2(0.5f * (x.y + y.y), 0.5f * (y.x - x.x));
-            }
-            const int sp0 = c * S + j * SK + k;                        // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186)
-            const int sp1 = c * S + j * SK + HK;
-            if (p.dump.spec) {
-                p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp0] = v0;
-                if (k == 0) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp1] = v1;
-            }
-            float2 o0, o1 = make_float2(0.f, 0.f);
-            if (MODE == KCF_MODE_PREDICT) {
-                // zf += xf * conj(model)   (kcf.cpp:306-345)
-                const float2 m0 = model[sp0];
-                o0 = make_float2(v0.x * m0.x + v0.y * m0.y, v0.y * m0.x - v0.x * m0.y);
-                if (k == 0) { const float2 m1 = model[sp1]; o1 = make_float2(v1.x * m1.x + v1.y * m1.y, v1.y * m1.x - v1.x * m1.y); }
-            } else {
-                // kf += |xf|^2 (kcf.cpp:269-293); model = (1-f) model + f xf (kcf.cpp:380-395)
-                o0 = make_float2(v0.x * v0.x + v0.y * v0.y, 0.f);
-                if (first) model[sp0] = v0;
-                else { const float2 m0 = model[sp0]; model[sp0] = make_float2(__fadd_rn(__fmul_rn(omf, m0.x), __fmul_rn(fac, v0.x)), __fadd_rn(__fmul_rn(omf, m0.y), __fmul_rn(fac, v0.y))); }
-                if (k == 0) {
-                    o1 = make_float2(v1.x * v1.x + v1.y * v1.y, 0.f);
-                    if (first) model[sp1] = v1;
-                    else { const float2 m1 = model[sp1]; model[sp1] = make_float2(__fadd_rn(__fmul_rn(omf, m1.x), __fmul_rn(fac, v1.x)), __fadd_rn(__fmul_rn(omf, m1.y), __fmul_rn(fac, v1.y))); }
+            for (int jb = 0; jb < WC; jb += CH) {
+                float2 mv[CH];
+#pragma unroll
+                for (int q = 0; q < CH; ++q) mv[q] = mpre[q];
+                if (need_model && jb + CH < WC) {
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) mpre[q] = mrow[(jb + CH + q) * SK];
+                }
+#pragma unroll
+                for (int q = 0; q < CH; ++q) {
+                    const int j = jb + q;
+                    const float2 v = a[brev<WC>(j)];
+                    if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + c * S + j * SK + k] = v;
+                    float2 o;
+                    if (MODE == KCF_MODE_PREDICT) {
+                        o = make_float2(v.x * mv[q].x + v.y * mv[q].y, v.y * mv[q].x - v.x * mv[q].y);     // xf * conj(model), kcf.cpp:306-345
+                    } else {
+                        o = make_float2(v.x * v.x + v.y * v.y, 0.f);                                         // |xf|^2, kcf.cpp:269-293
+                        // model = (1-f) model + f xf, kcf.cpp:380-395 (f = 1 on the first update: the old model drops out)
+                        model[c * S + j * SK + k] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, mv[q].x), __fmul_rn(fac, v.x)),
+                                                                              __fadd_rn(__fmul_rn(omf, mv[q].y), __fmul_rn(fac, v.y)));
+                    }
+                    F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))] = o;
                 }
             }
-            F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))] = o0;
-            if (k == 0) FN[c * WC + j] = o1;
+        } else {
+            // slot 0 = FFT(DC_j + i Nyq_j): separate the DC column (k = 0) and the Nyquist column (k = HR/2)
+#pragma unroll
+            for (int jb = 0; jb < WC; jb += C0) {
+                float2 mv[C0], mn[C0];
+#pragma unroll
+                for (int q = 0; q < C0; ++q) mv[q] = mpre[q];
+                if (need_model) {
+#pragma unroll
+                    for (int q = 0; q < C0; ++q) mn[q] = mrow[(jb + q) * SK + HK];
+                    if (jb + C0 < WC) {
+#pragma unroll
+                        for (int q = 0; q < C0; ++q) mpre[q] = mrow[(jb + C0 + q) * SK];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < C0; ++q) {
+                    const int j = jb + q;
+                    const float2 x = a[brev<WC>(j)], y = a[brev<WC>((WC - j) % WC)];
+                    const float2 v0 = make_float2(0.5f * (x.x + y.x), 0.5f * (x.y - y.y));
+                    const float2 v1 = make_float2(0.5f * (x.y + y.y), 0.5f * (y.x - x.x));
+                    const int sp0 = c * S + j * SK, sp1 = sp0 + HK;
+                    if (DUMP && p.dump.spec) { p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp0] = v0; p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp1] = v1; }
+                    float2 o0, o1;
+                    if (MODE == KCF_MODE_PREDICT) {
+                        o0 = make_float2(v0.x * mv[q].x + v0.y * mv[q].y, v0.y * mv[q].x - v0.x * mv[q].y);
+                        o1 = make_float2(v1.x * mn[q].x + v1.y * mn[q].y, v1.y * mn[q].x - v1.x * mn[q].y);
+                    } else {
+                        o0 = make_float2(v0.x * v0.x + v0.y * v0.y, 0.f);
+                        o1 = make_float2(v1.x * v1.x + v1.y * v1.y, 0.f);
+                        model[sp0] = first ? v0 : make_float2(__fadd_rn(__fmul_rn(omf, mv[q].x), __fmul_rn(fac, v0.x)), __fadd_rn(__fmul_rn(omf, mv[q].y), __fmul_rn(fac, v0.y)));
+                        model[sp1] = first ? v1 : make_float2(__fadd_rn(__fmul_rn(omf, mn[q].x), __fmul_rn(fac, v1.x)), __fadd_rn(__fmul_rn(omf, mn[q].y), __fmul_rn(fac, v1.y)));
+                    }
+                    F2[(c * WC + j) * HK + (0 ^ (j & (HK - 1)))] = o0;
+                    FN[c * WC + j] = o1;
+                }
+            }
         }
     }
     __syncthreads();
@@ -403,10 +496,10 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             acc.x = __fmul_rn(__fmul_rn(acc.x, al), cls.norm);         // kcf.cpp:356-357
             acc.y = __fmul_rn(__fmul_rn(acc.y, al), cls.norm);
             zf_s[e] = acc;
-            if (p.dump.zf) p.dump.zf[(long)job * p.dump.stride_spec + e] = acc;
+            if (DUMP && p.dump.zf) p.dump.zf[(long)job * p.dump.stride_spec + e] = acc;
         } else {
             const float kf = __fmul_rn(acc.x, cls.norm);               // kcf.cpp:295-303
-            if (p.dump.kf) p.dump.kf[(long)job * p.dump.stride_spec + e] = kf;
+            if (DUMP && p.dump.kf) p.dump.kf[(long)job * p.dump.stride_spec + e] = kf;
             const float an = __fdiv_rn(cls.yf_re[e], __fadd_rn(kf, p.lamda));                // kcf.cpp:373
             alpha[e] = __fadd_rn(__fmul_rn(omf, alpha[e]), __fmul_rn(fac, an));              // kcf.cpp:374
         }
@@ -454,7 +547,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         for (int m = 0; m < HK; ++m) { const float2 v = q[brev<HK>(m)]; resp[tid * HR + 2 * m] = v.x; resp[tid * HR + 2 * m + 1] = v.y; }
     }
     __syncthreads();
-    if (p.dump.resp) {
+    if (DUMP && p.dump.resp) {
         float *d = p.dump.resp + (long)job * p.dump.stride_cell;
         for (int i = tid; i < NB; i += NT) d[i] = resp[i];
     }
@@ -474,7 +567,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         for (int w = 1; w < NT / 32; ++w) { const float ov = red[w]; const int oi = redi[w]; if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; } }
         int vd = 1, hd = 1;                                            // reference leaves these uninitialised when nothing beats -99999
         if (besti != 0x7FFFFFFF) { hd = besti / HR + 1; vd = besti - (hd - 1) * HR + 1; }
-        if (p.dump.peak) { p.dump.peak[2 * job] = vd; p.dump.peak[2 * job + 1] = hd; }
+        if (DUMP && p.dump.peak) { p.dump.peak[2 * job] = vd; p.dump.peak[2 * job + 1] = hd; }
         if (vd > HR / 2) vd -= HR;                                     // kcf.cpp:419-420
         if (hd > WC / 2) hd -= WC;
         mot_bbox_t pos = meta->pos;
@@ -494,42 +587,21 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <int HR, int WC> static int launch_t(int mode, const KcfLaunch &p, cudaStream_t s)
+template <int HR, int WC> int kcf_launch_size(int mode, const KcfLaunch &p, cudaStream_t s)
 {
-    static bool configured[2] = { false, false };
     const FhogTablesDev &t = p.tab;
     int lut_floats = (2 << t.rsqrt_bits) + (1 << t.rcp_bits) + 2 * t.bin_nseg;
     if (lut_floats > 8192) lut_floats = 0;                                      // too large: read the tables from global memory
     const size_t bytes = smem_bytes<HR, WC>(lut_floats);
-    auto kp = kcf_fused_kernel<HR, WC, KCF_MODE_PREDICT>;
-    auto ku = kcf_fused_kernel<HR, WC, KCF_MODE_UPDATE>;
-    if (!configured[mode]) {
-        cudaError_t e = cudaFuncSetAttribute(mode == KCF_MODE_PREDICT ? (const void *)kp : (const void *)ku,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return (int)e;
-        configured[mode] = true;
-    }
-    if (mode == KCF_MODE_PREDICT) kp<<<p.n_jobs, KCF_THREADS, bytes, s>>>(p, lut_floats);
-    else                          ku<<<p.n_jobs, KCF_THREADS, bytes, s>>>(p, lut_floats);
-    return (int)cudaGetLastError();
-}
-
-#define MOT_KCF_SIZES(X) X(8, 8) X(8, 16) X(16, 8) X(16, 16) X(16, 32) X(32, 16) X(32, 32) X(8, 32) X(32, 8)
-
-int kcf_launch_fast(int mode, int hr, int wc, const KcfLaunch &p, cudaStream_t s)
-{
-#define X(H, W) if (hr == H && wc == W) return launch_t<H, W>(mode, p, s);
-    MOT_KCF_SIZES(X)
-#undef X
-    return -1000;
-}
-
-size_t kcf_fast_smem_bytes(int hr, int wc)
-{
-#define X(H, W) if (hr == H && wc == W) return smem_bytes<H, W>(4254);
-    MOT_KCF_SIZES(X)
-#undef X
-    return 0;
+    const bool dump = p.dump.gray != nullptr;
+    const void *fn;
+    if (mode == KCF_MODE_PREDICT) fn = dump ? (const void *)kcf_fused_kernel<HR, WC, KCF_MODE_PREDICT, true> : (const void *)kcf_fused_kernel<HR, WC, KCF_MODE_PREDICT, false>;
+    else                          fn = dump ? (const void *)kcf_fused_kernel<HR, WC, KCF_MODE_UPDATE, true> : (const void *)kcf_fused_kernel<HR, WC, KCF_MODE_UPDATE, false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    void *args[2] = { (void *)&p, (void *)&lut_floats };
+    e = cudaLaunchKernel(fn, dim3((unsigned)p.n_jobs), dim3(KCF_THREADS), args, bytes, s);
+    return (int)e;
 }
 
 }  // namespace mot
