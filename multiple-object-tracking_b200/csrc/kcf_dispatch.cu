@@ -18,7 +18,7 @@ int kcf_launch_fast(int mode, int hr, int wc, const KcfLaunch &p, cudaStream_t s
 
 size_t kcf_fast_smem_bytes(int hr, int wc)
 {
-#define X(H, W) if (hr == H && wc == W) return kcf_smem_##H##_##W(4254);
+#define X(H, W) if (hr == H && wc == W) return kcf_smem_##H##_##W(4256);
     MOT_KCF_SIZES(X)
 #undef X
     return 0;

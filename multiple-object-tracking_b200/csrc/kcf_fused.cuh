@@ -34,21 +34,34 @@ template <int HR, int WC> struct Geo {
     static constexpr int RMAX = 4 * HR + 3, CMAX = 4 * WC + 3;
     static constexpr int GS = RMAX;                      // gray column stride (odd -> conflict-free in both directions)
     static constexpr int RS = HR + 1;                    // histogram / normaliser column stride
-    static constexpr int F_FLOATS = 31 * NB;
+    // (M/16, bin) per pixel with a 2..5-pixel zero border, de-interleaved along y: [x+2][(y+2)&3][(y+2)>>2]
+    static constexpr int PC = 4 * (HR + 2);                // column pitch of the padded layout
+    static constexpr int PADM = (W0 + 8) * PC;             // floats of M0 (the bins take PADM bytes after it)
+    static constexpr int RAW_PITCH = 432;                  // bytes per staged frame row: 3*(4*32+3) + 2*15 alignment slack, 16-byte multiple
+    static constexpr int RAW_FLOATS = RMAX * RAW_PITCH / 4;
+    static constexpr int F_MIN = 31 * NB;
+    static constexpr int F_A = CMAX * GS > PADM + PADM / 4 ? CMAX * GS : PADM + PADM / 4;
+    static constexpr int F_FLOATS = ((F_MIN > F_A ? F_MIN : F_A) + 3) & ~3;
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
     static constexpr int PIX_PER_THREAD = (H0 * W0 + KCF_THREADS - 1) / KCF_THREADS;
-    static_assert(CMAX * GS <= F_FLOATS, "gray patch must fit in the F region");
-    static_assert(20 * NB <= F_FLOATS, "M0 + bins must fit in the F region");
+    static_assert(3 * CMAX + 30 <= RAW_PITCH, "staged row pitch");
+    static_assert(PADM % 4 == 0, "bin array alignment");
     static_assert((F_FLOATS & 1) == 0, "float2 alignment of the R1 region");
 };
 
-__host__ __device__ inline int r1_region_floats(int r1_min, int lut_floats) { int v = r1_min > lut_floats ? r1_min : lut_floats; return (v + 3) & ~3; }
+// R1 region: cell histograms later, but first the SSE tables (lut_floats) and the staged frame rows (raw_floats)
+__host__ __device__ inline int r1_region_floats(int r1_min, int lut_floats, int raw_floats)
+{
+    const int early = ((lut_floats + 3) & ~3) + raw_floats;
+    const int v = r1_min > early ? r1_min : early;
+    return (v + 3) & ~3;
+}
 
 template <int HR, int WC> size_t smem_bytes(int lut_floats)
 {
     using G = Geo<HR, WC>;
-    return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats) + G::N_FLOATS + G::NB + HR + WC + 64);
+    return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS) + G::N_FLOATS + G::NB + HR + WC + 64);
 }
 
 // gray = 0.144*B + 0.587*G + 0.299*R in double, rounded to float (top/drawlib.c:234; yes, 0.144)
@@ -62,6 +75,28 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ---- bulk asynchronous copies global -> shared on an mbarrier (the copy engine that TMA uses; SASS: UBLKCP) --------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tMBW_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MBW_DONE;\n\tbra MBW_LOOP;\n\tMBW_DONE:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 template <int HR, int WC, int MODE, bool DUMP>
 __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaunch p, const int lut_floats)
 {
@@ -71,15 +106,18 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     extern __shared__ __align__(16) float smem[];
     float *const F = smem;
     float *const R1 = F + G::F_FLOATS;
-    float *const Ns = R1 + r1_region_floats(G::R1_MIN, lut_floats);
+    float *const Ns = R1 + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS);
     float *const Es = Ns + G::N_FLOATS;
     float *const wy_s = Es + NB;
     float *const wx_s = wy_s + HR;
     float *const red = wx_s + WC;
 
+    __shared__ __align__(8) uint64_t mbar;
     const int tid = threadIdx.x;
     const int job = blockIdx.x;
     if (job >= p.n_jobs) return;
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
     const int slot = p.slots[job];
     KcfMeta *const meta = p.meta + slot;
     const KcfClassDev cls = p.classes[meta->size_class];
@@ -95,71 +133,91 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     if (tid < (S * 4 + 127) / 128) prefetch_l2(reinterpret_cast<const char *>(p.alpha + (long)slot * p.alpha_stride) + tid * 128);
 
     // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
+    // The SSE tables and the frame rows of the ROI are pulled into shared memory by the bulk-copy engine
+    // (cp.async.bulk on an mbarrier) while the threads fetch the per-track metadata; rows start on arbitrary byte offsets,
+    // so each row is fetched as the enclosing 16-byte-aligned span.
     const bool lut_smem = lut_floats > 0;
+    const int n_rs = 2 << p.tab.rsqrt_bits, n_rc = 1 << p.tab.rcp_bits, n_bn = (2 * p.tab.bin_nseg + 3) & ~3;
     const float *rs_tab = p.tab.rsqrt_tab, *rc_tab = p.tab.rcp_tab;
     const uint32_t *bn_tab = p.tab.bin_tab;
-    if (lut_smem) {
-        const int n_rs = 2 << p.tab.rsqrt_bits, n_rc = 1 << p.tab.rcp_bits, n_bn = 2 * p.tab.bin_nseg;
-        for (int i = tid; i < n_rs; i += NT) R1[i] = p.tab.rsqrt_tab[i];
-        for (int i = tid; i < n_rc; i += NT) R1[n_rs + i] = p.tab.rcp_tab[i];
-        for (int i = tid; i < n_bn; i += NT) reinterpret_cast<uint32_t *>(R1)[n_rs + n_rc + i] = p.tab.bin_tab[i];
-        rs_tab = R1; rc_tab = R1 + n_rs; bn_tab = reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc;
+    if (lut_smem) { rs_tab = R1; rc_tab = R1 + n_rs; bn_tab = reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc; }
+    unsigned char *const raw = reinterpret_cast<unsigned char *>(R1 + ((lut_floats + 3) & ~3));
+
+    const uint8_t *frame = nullptr;
+    int l = box.l, t = box.t, r = box.r, b = box.b;
+    if (t > b) { const int q = t; t = b; b = q; }              // top/drawlib.c:203-215
+    if (l > r) { const int q = l; l = r; r = q; }
+    const int rows_s = b - t + 1, cols_s = r - l + 1;
+    const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
+    if (p.gray == nullptr) frame = p.frame_ptr[p.frames[job]];
+    const bool identity = (p.gray == nullptr) && rows_s == rows && cols_s == cols;
+    // bulk staging needs 16-byte aligned rows: frame base and stride multiples of 16 (true for every common frame width)
+    const bool staged = identity && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0;
+    const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols - 1, 0, Wm);
+    const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;      // aligned byte span of a frame row
+    if (tid < 32) {
+        const uint32_t lut_bytes = lut_smem ? (uint32_t)(n_rs + n_rc + n_bn) * 4u : 0u;
+        const uint32_t roi_bytes = staged ? (uint32_t)rows * (uint32_t)(a1 - a0) : 0u;
+        if (tid == 0) mbar_expect_tx(&mbar, lut_bytes + roi_bytes);
+        __syncwarp();
+        if (lut_smem) {
+            if (tid == 0) bulk_g2s(R1, p.tab.rsqrt_tab, n_rs * 4, &mbar);
+            if (tid == 1) bulk_g2s(R1 + n_rs, p.tab.rcp_tab, n_rc * 4, &mbar);
+            if (tid == 2) bulk_g2s(R1 + n_rs + n_rc, p.tab.bin_tab, n_bn * 4, &mbar);
+        }
+        if (staged)
+            for (int y = tid; y < rows; y += 32)
+                bulk_g2s(raw + y * G::RAW_PITCH, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar);
     }
-    if (tid < HR) wy_s[tid] = cls.wy[tid];
-    if (tid < WC) wx_s[tid] = cls.wx[tid];
+    if (tid >= 32 && tid < 32 + HR) wy_s[tid - 32] = cls.wy[tid - 32];
+    if (tid >= 64 && tid < 64 + WC) wx_s[tid - 64] = cls.wx[tid - 64];
 
     if (p.gray != nullptr) {
         const float *src = p.gray + (long)job * p.gray_stride;
         for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; F[x * GS + y] = src[idx]; }
+    } else if (staged) {
+        mbar_wait(&mbar, 0);
+        // staged bytes -> gray: one warp per row, lanes along x (3-byte pixels: conflict-free shared loads)
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int y = warp; y < rows; y += NT / 32) {
+            const unsigned char *rrow = raw + y * G::RAW_PITCH - a0;
+#pragma unroll 4
+            for (int x = lane; x < cols; x += 32) F[x * GS + y] = bgr_gray(rrow + clampi(l + x, 0, Wm) * 3);
+        }
+    } else if (identity) {
+        // unaligned frames: plain loads.  Equal sizes: bilinearInterpolationGray is an exact copy (top/drawlib.c:610-633, xs = ys = 1)
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int y = warp; y < rows; y += NT / 32) {
+            const uint8_t *r0 = frame + (long)clampi(t + y, 0, Hm) * p.frame_stride;
+#pragma unroll 4
+            for (int x = lane; x < cols; x += 32) F[x * GS + y] = bgr_gray(r0 + clampi(l + x, 0, Wm) * 3);
+        }
     } else {
-        const uint8_t *frame = p.frame_ptr[p.frames[job]];
-        int l = box.l, t = box.t, r = box.r, b = box.b;
-        if (t > b) { const int q = t; t = b; b = q; }          // top/drawlib.c:203-215
-        if (l > r) { const int q = l; l = r; r = q; }
-        const int rows_s = b - t + 1, cols_s = r - l + 1;
-        const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
-        if (rows_s == rows && cols_s == cols) {
-            // equal sizes: bilinearInterpolationGray degenerates to an exact copy (top/drawlib.c:610-633 with xs = ys = 1)
-            // one warp per frame row (coalesced 3-byte pixels), two rows in flight per warp
-            const int warp = tid >> 5, lane = tid & 31;
-            for (int y = warp; y < rows; y += 2 * (NT / 32)) {
-                const int y2 = y + NT / 32;
-                const uint8_t *r0 = frame + (long)clampi(t + y, 0, Hm) * p.frame_stride;
-                const uint8_t *r1 = frame + (long)clampi(t + (y2 < rows ? y2 : y), 0, Hm) * p.frame_stride;
-#pragma unroll 2
-                for (int x = lane; x < cols; x += 32) {
-                    const int xo = clampi(l + x, 0, Wm) * 3;
-                    const float g0 = bgr_gray(r0 + xo), g1 = bgr_gray(r1 + xo);
-                    F[x * GS + y] = g0;
-                    if (y2 < rows) F[x * GS + y2] = g1;
-                }
-            }
-        } else {
-            // the reference resamples a column-major crop as if it were row-major height x width; reproduced through
-            // linear indices (top/drawlib.c:542-637, called as (dst, src, rows_s, cols_s, rows_d, cols_d), top/td.cpp:357-364)
-            const float xs = __fdiv_rn((float)cols_s, (float)cols), ys = __fdiv_rn((float)rows_s, (float)rows);
-            for (int k = tid; k < rows * cols; k += NT) {
-                const int yy = k / cols, xx = k - yy * cols;
-                const float sx = __fmul_rn((float)xx, xs), sy = __fmul_rn((float)yy, ys);
-                const int x0 = __float2int_rz(sx), y0 = __float2int_rz(sy);
-                const float fx = __fsub_rn(sx, (float)x0), fy = __fsub_rn(sy, (float)y0);
-                const float ifx = __fsub_rn(1.0f, fx), ify = __fsub_rn(1.0f, fy);
-                const int x1 = (x0 + 1 >= cols_s) ? x0 : x0 + 1, y1 = (y0 + 1 >= rows_s) ? y0 : y0 + 1;
-                float c[4];
-                const int sidx[4] = { y0 * cols_s + x0, y0 * cols_s + x1, y1 * cols_s + x0, y1 * cols_s + x1 };
+        // the reference resamples a column-major crop as if it were row-major height x width; reproduced through
+        // linear indices (top/drawlib.c:542-637, called as (dst, src, rows_s, cols_s, rows_d, cols_d), top/td.cpp:357-364)
+        const float xs = __fdiv_rn((float)cols_s, (float)cols), ys = __fdiv_rn((float)rows_s, (float)rows);
+        for (int k = tid; k < rows * cols; k += NT) {
+            const int yy = k / cols, xx = k - yy * cols;
+            const float sx = __fmul_rn((float)xx, xs), sy = __fmul_rn((float)yy, ys);
+            const int x0 = __float2int_rz(sx), y0 = __float2int_rz(sy);
+            const float fx = __fsub_rn(sx, (float)x0), fy = __fsub_rn(sy, (float)y0);
+            const float ifx = __fsub_rn(1.0f, fx), ify = __fsub_rn(1.0f, fy);
+            const int x1 = (x0 + 1 >= cols_s) ? x0 : x0 + 1, y1 = (y0 + 1 >= rows_s) ? y0 : y0 + 1;
+            float c[4];
+            const int sidx[4] = { y0 * cols_s + x0, y0 * cols_s + x1, y1 * cols_s + x0, y1 * cols_s + x1 };
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int sc = sidx[q] / rows_s, sr = sidx[q] - sc * rows_s;   // column-major crop element
-                    c[q] = bgr_gray(frame + (long)clampi(t + sr, 0, Hm) * p.frame_stride + clampi(l + sc, 0, Wm) * 3);
-                }
-                const float l0 = __fadd_rn(__fmul_rn(ifx, c[0]), __fmul_rn(fx, c[1]));
-                const float l1 = __fadd_rn(__fmul_rn(ifx, c[2]), __fmul_rn(fx, c[3]));
-                const float o = __fadd_rn(__fmul_rn(ify, l0), __fmul_rn(fy, l1));
-                const int dc = k / rows, dr = k - dc * rows;                         // column-major template element
-                F[dc * GS + dr] = o;
+            for (int q = 0; q < 4; ++q) {
+                const int sc = sidx[q] / rows_s, sr = sidx[q] - sc * rows_s;   // column-major crop element
+                c[q] = bgr_gray(frame + (long)clampi(t + sr, 0, Hm) * p.frame_stride + clampi(l + sc, 0, Wm) * 3);
             }
+            const float l0 = __fadd_rn(__fmul_rn(ifx, c[0]), __fmul_rn(fx, c[1]));
+            const float l1 = __fadd_rn(__fmul_rn(ifx, c[2]), __fmul_rn(fx, c[3]));
+            const float o = __fadd_rn(__fmul_rn(ify, l0), __fmul_rn(fy, l1));
+            const int dc = k / rows, dr = k - dc * rows;                         // column-major template element
+            F[dc * GS + dr] = o;
         }
     }
+    if (!staged && lut_smem) mbar_wait(&mbar, 0);              // the tables still arrive through the mbarrier
     __syncthreads();
     if (DUMP && p.dump.gray) {
         float *d = p.dump.gray + (long)job * p.dump.stride_px;
@@ -216,62 +274,87 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         }
     }
     __syncthreads();
-    // (M0, bin) overwrite the gray patch, de-interleaved along y ([x][y&3][y>>2]) so that the cell-parallel gather below
-    // reads consecutive words
+    // (M0, bin) overwrite the gray patch in a zero-bordered layout de-interleaved along y, [x+2][(y+2)&3][(y+2)>>2], so
+    // that the cell-parallel gather below reads consecutive words and needs no bounds checks (a zero magnitude adds +0)
+    constexpr int PC = G::PC;
     float *const M0s = F;
-    unsigned char *const Bs = reinterpret_cast<unsigned char *>(F + 16 * NB);
+    unsigned char *const Bs = reinterpret_cast<unsigned char *>(F + G::PADM);
 #pragma unroll
     for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
         const int idx = tid + q * NT;
         if (idx < H0 * W0) {
             const int x = idx / H0, y = idx - x * H0;
-            const int a = x * H0 + (y & 3) * HR + (y >> 2);
+            const int a = (x + 2) * PC + ((y + 2) & 3) * (HR + 2) + ((y + 2) >> 2);
             M0s[a] = m0r[q]; Bs[a] = bnr[q];
             if (DUMP && p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = m0r[q]; p.dump.bin[(long)job * p.dump.stride_px + idx] = bnr[q]; }
         }
+    }
+    // zero border: 8 full columns (x+2 in {0,1,W0+2..W0+7}) and 8 rows of the interior columns (y+2 in {0,1,H0+2..H0+7})
+    for (int k = tid; k < 8 * (H0 + 8) + 8 * W0; k += NT) {
+        int xs, ys;
+        if (k < 8 * (H0 + 8)) { const int cxx = k / (H0 + 8); ys = k - cxx * (H0 + 8); xs = cxx < 2 ? cxx : W0 + cxx; }
+        else { const int k2 = k - 8 * (H0 + 8); const int ry = k2 / W0; xs = 2 + (k2 - ry * W0); ys = ry < 2 ? ry : H0 + ry; }
+        const int a = xs * PC + (ys & 3) * (HR + 2) + (ys >> 2);
+        M0s[a] = 0.f; Bs[a] = 0;
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ P2: 18-bin cell histograms by ordered gather
     // libhog/gradientMex.cpp:183-221 (bilinear spatial interpolation, softBin<0) + :225-230 (boundary x 8/7).
-    // One thread owns one cell and adds its <= 8x8 contributing pixels in the reference's (x outer, y inner) order, so the
-    // sums are deterministic and equal to the reference's sequential scatter.
-    for (int cell = tid; cell < NB; cell += NT) {
-        const int cx = cell / HR, cy = cell - cx * HR;
-        float *const h = R1 + cx * RS + cy;
+    // One thread owns a cell (two, interleaved, at 32x32) and adds its 8x8 contributing pixels in the reference's
+    // (x outer, y inner) order, so the sums are deterministic and equal to the reference's sequential scatter.
+    constexpr int CPT = (NB + NT - 1) / NT;                    // cells per thread
+    {
+        int ccx[CPT], ccy[CPT]; bool live[CPT]; float *h[CPT]; int base[CPT];
 #pragma unroll
-        for (int o = 0; o < 18; ++o) h[o * (WC * RS)] = 0.f;
-#pragma unroll 1
+        for (int u = 0; u < CPT; ++u) {
+            const int cell = tid + u * NT;
+            live[u] = cell < NB;
+            const int cc = live[u] ? cell : 0;
+            ccx[u] = cc / HR; ccy[u] = cc - ccx[u] * HR;
+            h[u] = R1 + ccx[u] * RS + ccy[u];
+            base[u] = (4 * ccx[u]) * PC + ccy[u];
+            if (live[u]) {
+#pragma unroll
+                for (int o = 0; o < 18; ++o) h[u][o * (WC * RS)] = 0.f;
+            }
+        }
+#pragma unroll 2
         for (int dx = 0; dx < 8; ++dx) {
-            const int px = 4 * cx - 2 + dx;
-            if (px < 0 || px >= W0) continue;
             const float wxv = 0.125f + 0.25f * (float)(dx < 4 ? dx : 7 - dx);
 #pragma unroll
             for (int dy = 0; dy < 8; ++dy) {
-                const int py = 4 * cy - 2 + dy;
-                if (py < 0 || py >= H0) continue;
-                const float wyv = 0.125f + 0.25f * (float)(dy < 4 ? dy : 7 - dy);
-                const int a = px * H0 + (py & 3) * HR + (py >> 2);
-                const float v = __fmul_rn(wxv * wyv, M0s[a]);          // weights are dyadic: the product is exact
-                float *const hb = h + (int)Bs[a] * (WC * RS);
-                *hb = __fadd_rn(*hb, v);
+                const float w = wxv * (0.125f + 0.25f * (float)(dy < 4 ? dy : 7 - dy));     // dyadic weights: exact product
+#pragma unroll
+                for (int u = 0; u < CPT; ++u) {
+                    if (!live[u]) continue;
+                    const int a = base[u] + dx * PC + (dy & 3) * (HR + 2) + (dy >> 2);
+                    const float v = __fmul_rn(w, M0s[a]);
+                    float *const hb = h[u] + (int)Bs[a] * (WC * RS);
+                    *hb = __fadd_rn(*hb, v);
+                }
             }
         }
-        float e = 0.f;
-        float r[18];
 #pragma unroll
-        for (int o = 0; o < 18; ++o) {
-            float v = h[o * (WC * RS)];
-            if (cx == 0) v = __fmul_rn(v, 8.f / 7.f);
-            if (cy == 0) v = __fmul_rn(v, 8.f / 7.f);
-            if (cx == WC - 1) v = __fmul_rn(v, 8.f / 7.f);
-            if (cy == HR - 1) v = __fmul_rn(v, 8.f / 7.f);
-            h[o * (WC * RS)] = v; r[o] = v;
+        for (int u = 0; u < CPT; ++u) {
+            if (!live[u]) continue;
+            const int cx = ccx[u], cy = ccy[u];
+            float e = 0.f;
+            float r[18];
+#pragma unroll
+            for (int o = 0; o < 18; ++o) {
+                float v = h[u][o * (WC * RS)];
+                if (cx == 0) v = __fmul_rn(v, 8.f / 7.f);
+                if (cy == 0) v = __fmul_rn(v, 8.f / 7.f);
+                if (cx == WC - 1) v = __fmul_rn(v, 8.f / 7.f);
+                if (cy == HR - 1) v = __fmul_rn(v, 8.f / 7.f);
+                h[u][o * (WC * RS)] = v; r[o] = v;
+            }
+            // cell energy over the 9 contrast-insensitive bins, R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309, :242-243)
+#pragma unroll
+            for (int o = 0; o < 9; ++o) { const float r2 = __fadd_rn(r[o], r[o + 9]); e = __fadd_rn(e, __fmul_rn(r2, r2)); }
+            Es[cx * HR + cy] = e;
         }
-        // cell energy over the 9 contrast-insensitive bins, R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309, :242-243)
-#pragma unroll
-        for (int o = 0; o < 9; ++o) { const float r2 = __fadd_rn(r[o], r[o + 9]); e = __fadd_rn(e, __fmul_rn(r2, r2)); }
-        Es[cx * HR + cy] = e;
     }
     __syncthreads();
     if (DUMP && p.dump.r1) {
@@ -590,7 +673,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 template <int HR, int WC> int kcf_launch_size(int mode, const KcfLaunch &p, cudaStream_t s)
 {
     const FhogTablesDev &t = p.tab;
-    int lut_floats = (2 << t.rsqrt_bits) + (1 << t.rcp_bits) + 2 * t.bin_nseg;
+    int lut_floats = (2 << t.rsqrt_bits) + (1 << t.rcp_bits) + ((2 * t.bin_nseg + 3) & ~3);
     if (lut_floats > 8192) lut_floats = 0;                                      // too large: read the tables from global memory
     const size_t bytes = smem_bytes<HR, WC>(lut_floats);
     const bool dump = p.dump.gray != nullptr;

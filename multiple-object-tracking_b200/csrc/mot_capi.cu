@@ -219,7 +219,8 @@ int mot_ctx_create(mot_ctx_t **out, int device, int frame_w, int frame_h, int ma
         CU(cudaMalloc(&c->d_classes, sizeof(KcfClassDev) * MAX_CLASSES));
         CU(cudaMalloc(&c->d_tab_rsqrt, sizeof(float) * ft.rsqrt_tab.size()));
         CU(cudaMalloc(&c->d_tab_rcp, sizeof(float) * ft.rcp_tab.size()));
-        CU(cudaMalloc(&c->d_tab_bin, sizeof(uint32_t) * ft.bin_tab.size()));
+        CU(cudaMalloc(&c->d_tab_bin, sizeof(uint32_t) * (ft.bin_tab.size() + 4)));      // bulk copies move 16-byte multiples
+        CU(cudaMemset(c->d_tab_bin, 0, sizeof(uint32_t) * (ft.bin_tab.size() + 4)));
         CU(cudaMemcpy(c->d_tab_rsqrt, ft.rsqrt_tab.data(), sizeof(float) * ft.rsqrt_tab.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_tab_rcp, ft.rcp_tab.data(), sizeof(float) * ft.rcp_tab.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_tab_bin, ft.bin_tab.data(), sizeof(uint32_t) * ft.bin_tab.size(), cudaMemcpyHostToDevice));
