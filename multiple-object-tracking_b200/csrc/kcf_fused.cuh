@@ -64,11 +64,18 @@ template <int HR, int WC> size_t smem_bytes(int lut_floats)
     return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS) + G::N_FLOATS + G::NB + HR + WC + 64);
 }
 
-// gray = 0.144*B + 0.587*G + 0.299*R in double, rounded to float (top/drawlib.c:234; yes, 0.144)
+// gray = (float)(0.144*B + 0.587*G + 0.299*R), evaluated in double by the reference (top/drawlib.c:234; yes, 0.144).
+// For 8-bit channels the double result is never within 3e-11 (relative) of a float rounding boundary, while the double
+// evaluation is within 5e-16 of N/1000 with N = 144B + 587G + 299R, so the reference value IS the correctly rounded float
+// of N/1000 (checked against the C expression for all 2^24 colours in tests/test_cabi_exports.py).  N < 2^24 is exact in
+// float; one Newton step on q0 = N * RN(1/1000) gives the correctly rounded quotient without touching the FP64 pipe.
 __device__ __forceinline__ float bgr_gray(const uint8_t *p)
 {
-    const double B = p[0], G = p[1], R = p[2];
-    return __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(0.144, B), __dmul_rn(0.587, G)), __dmul_rn(0.299, R)));
+    const float nf = (float)(144 * (int)p[0] + 587 * (int)p[1] + 299 * (int)p[2]);
+    const float rcp = 1.0f / 1000.0f;
+    const float q0 = __fmul_rn(nf, rcp);
+    const float rem = __fmaf_rn(-q0, 1000.0f, nf);
+    return __fmaf_rn(rem, rcp, q0);
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -112,17 +119,54 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     float *const wx_s = wy_s + HR;
     float *const red = wx_s + WC;
 
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar, mbar2;     // SSE tables / staged frame rows
     const int tid = threadIdx.x;
     const int job = blockIdx.x;
     if (job >= p.n_jobs) return;
-    if (tid == 0) mbar_init(&mbar, 1);
+    if (tid == 0) { mbar_init(&mbar, 1); mbar_init(&mbar2, 1); }
     __syncthreads();
+    // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
+    // The SSE tables and the frame rows of the ROI are pulled into shared memory by the bulk-copy engine
+    // (cp.async.bulk on an mbarrier), issued before anything else so that the per-track metadata loads overlap with
+    // them; rows start on arbitrary byte offsets, so each row is fetched as the enclosing 16-byte-aligned span.
+    const bool lut_smem = lut_floats > 0;
+    const int n_rs = 2 << p.tab.rsqrt_bits, n_rc = 1 << p.tab.rcp_bits, n_bn = (2 * p.tab.bin_nseg + 3) & ~3;
+    const float *rs_tab = p.tab.rsqrt_tab, *rc_tab = p.tab.rcp_tab;
+    const uint32_t *bn_tab = p.tab.bin_tab;
+    if (lut_smem) { rs_tab = R1; rc_tab = R1 + n_rs; bn_tab = reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc; }
+    unsigned char *const raw = reinterpret_cast<unsigned char *>(R1 + ((lut_floats + 3) & ~3));
+    if (lut_smem && tid < 3) {
+        if (tid == 0) { mbar_expect_tx(&mbar, (uint32_t)(n_rs + n_rc + n_bn) * 4u); bulk_g2s(R1, p.tab.rsqrt_tab, n_rs * 4, &mbar); }
+        if (tid == 1) bulk_g2s(R1 + n_rs, p.tab.rcp_tab, n_rc * 4, &mbar);
+        if (tid == 2) bulk_g2s(R1 + n_rs + n_rc, p.tab.bin_tab, n_bn * 4, &mbar);
+    }
+
     const int slot = p.slots[job];
+    mot_bbox_t box = p.boxes[job];
+    const uint8_t *frame = (p.gray == nullptr) ? p.frame_ptr[p.frames[job]] : nullptr;
+    int l = box.l, t = box.t, r = box.r, b = box.b;
+    if (t > b) { const int q = t; t = b; b = q; }              // top/drawlib.c:203-215
+    if (l > r) { const int q = l; l = r; r = q; }
+    const int rows_s = b - t + 1, cols_s = r - l + 1;
+    const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
+    // bulk staging needs 16-byte aligned rows: frame base and stride multiples of 16 (true for every common frame width).
+    // Whether the crop has the template size (the only case that uses the staged rows) is known only after the metadata
+    // arrives; a crop that fits the staging area is fetched speculatively.
+    const bool fetch = (p.gray == nullptr) && rows_s <= G::RMAX && cols_s <= G::CMAX && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0;
+    const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols_s - 1, 0, Wm);
+    const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;      // aligned byte span of a frame row
+    if (fetch && tid >= 32 && tid < 64) {
+        if (tid == 32) mbar_expect_tx(&mbar2, (uint32_t)rows_s * (uint32_t)(a1 - a0));
+        __syncwarp();
+        for (int y = tid - 32; y < rows_s; y += 32)
+            bulk_g2s(raw + y * G::RAW_PITCH, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar2);
+    }
+
     KcfMeta *const meta = p.meta + slot;
     const KcfClassDev cls = p.classes[meta->size_class];
     const int rows = meta->rows, cols = meta->cols;
-    mot_bbox_t box = p.boxes[job];
+    const bool identity = (p.gray == nullptr) && rows_s == rows && cols_s == cols;
+    const bool staged = fetch && identity;
 
     // The model (31*S complex) is not needed before P5, tens of microseconds from now: pull it into L2 now so that P5
     // sees L2 latency instead of HBM latency (there is no shared memory left to stage it in).
@@ -132,43 +176,6 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     }
     if (tid < (S * 4 + 127) / 128) prefetch_l2(reinterpret_cast<const char *>(p.alpha + (long)slot * p.alpha_stride) + tid * 128);
 
-    // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
-    // The SSE tables and the frame rows of the ROI are pulled into shared memory by the bulk-copy engine
-    // (cp.async.bulk on an mbarrier) while the threads fetch the per-track metadata; rows start on arbitrary byte offsets,
-    // so each row is fetched as the enclosing 16-byte-aligned span.
-    const bool lut_smem = lut_floats > 0;
-    const int n_rs = 2 << p.tab.rsqrt_bits, n_rc = 1 << p.tab.rcp_bits, n_bn = (2 * p.tab.bin_nseg + 3) & ~3;
-    const float *rs_tab = p.tab.rsqrt_tab, *rc_tab = p.tab.rcp_tab;
-    const uint32_t *bn_tab = p.tab.bin_tab;
-    if (lut_smem) { rs_tab = R1; rc_tab = R1 + n_rs; bn_tab = reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc; }
-    unsigned char *const raw = reinterpret_cast<unsigned char *>(R1 + ((lut_floats + 3) & ~3));
-
-    const uint8_t *frame = nullptr;
-    int l = box.l, t = box.t, r = box.r, b = box.b;
-    if (t > b) { const int q = t; t = b; b = q; }              // top/drawlib.c:203-215
-    if (l > r) { const int q = l; l = r; r = q; }
-    const int rows_s = b - t + 1, cols_s = r - l + 1;
-    const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
-    if (p.gray == nullptr) frame = p.frame_ptr[p.frames[job]];
-    const bool identity = (p.gray == nullptr) && rows_s == rows && cols_s == cols;
-    // bulk staging needs 16-byte aligned rows: frame base and stride multiples of 16 (true for every common frame width)
-    const bool staged = identity && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0;
-    const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols - 1, 0, Wm);
-    const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;      // aligned byte span of a frame row
-    if (tid < 32) {
-        const uint32_t lut_bytes = lut_smem ? (uint32_t)(n_rs + n_rc + n_bn) * 4u : 0u;
-        const uint32_t roi_bytes = staged ? (uint32_t)rows * (uint32_t)(a1 - a0) : 0u;
-        if (tid == 0) mbar_expect_tx(&mbar, lut_bytes + roi_bytes);
-        __syncwarp();
-        if (lut_smem) {
-            if (tid == 0) bulk_g2s(R1, p.tab.rsqrt_tab, n_rs * 4, &mbar);
-            if (tid == 1) bulk_g2s(R1 + n_rs, p.tab.rcp_tab, n_rc * 4, &mbar);
-            if (tid == 2) bulk_g2s(R1 + n_rs + n_rc, p.tab.bin_tab, n_bn * 4, &mbar);
-        }
-        if (staged)
-            for (int y = tid; y < rows; y += 32)
-                bulk_g2s(raw + y * G::RAW_PITCH, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar);
-    }
     if (tid >= 32 && tid < 32 + HR) wy_s[tid - 32] = cls.wy[tid - 32];
     if (tid >= 64 && tid < 64 + WC) wx_s[tid - 64] = cls.wx[tid - 64];
 
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         const float *src = p.gray + (long)job * p.gray_stride;
         for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; F[x * GS + y] = src[idx]; }
     } else if (staged) {
-        mbar_wait(&mbar, 0);
+        mbar_wait(&mbar2, 0);
         // staged bytes -> gray: one warp per row, lanes along x (3-byte pixels: conflict-free shared loads)
         const int warp = tid >> 5, lane = tid & 31;
         for (int y = warp; y < rows; y += NT / 32) {
@@ -217,7 +224,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             F[dc * GS + dr] = o;
         }
     }
-    if (!staged && lut_smem) mbar_wait(&mbar, 0);              // the tables still arrive through the mbarrier
+    if (fetch && !staged) mbar_wait(&mbar2, 0);                // speculative rows must have landed before the region is reused
+    if (lut_smem) mbar_wait(&mbar, 0);
     __syncthreads();
     if (DUMP && p.dump.gray) {
         float *d = p.dump.gray + (long)job * p.dump.stride_px;
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     for (int e = tid; e < S; e += NT) {
         const int j = e / SK, k = e - j * SK;
         float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < KCF_CHAN; ++c) {
             const float2 v = (k < HK) ? F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))] : FN[c * WC + j];
             if (c == 0) acc = v; else { acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); }

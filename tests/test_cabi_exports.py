@@ -52,3 +52,26 @@ def test_sse_tables_match_the_oracle_acos_table(port):
     port.kcf.port_acos_table(b.ctypes.data_as(C.c_void_p))
     assert np.array_equal(a, b)
     assert 6 <= info[0] <= 14 and 6 <= info[1] <= 14
+
+
+def test_gray_conversion_identity_for_all_colours():
+    """The kernel computes gray = RN_f32((144B + 587G + 299R) / 1000) without FP64 (csrc/kcf_fused.cuh: bgr_gray).
+    Prove, for every 8-bit colour, that this is the reference's (float)(0.144*B + 0.587*G + 0.299*R) evaluated in
+    double (top/drawlib.c:234)."""
+    import numpy as np
+    B, G, R = np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing="ij")
+    B = B.ravel().astype(np.float64); G = G.ravel().astype(np.float64); R = R.ravel().astype(np.float64)
+    ref = ((0.144 * B + 0.587 * G) + 0.299 * R).astype(np.float32)
+    N = (144 * B + 587 * G + 299 * R).astype(np.int64)
+    nf = N.astype(np.float32)
+    assert np.array_equal(nf.astype(np.int64), N)
+    assert np.array_equal(ref, nf / np.float32(1000.0)), "IEEE single division of the exact integer numerator"
+    # the kernel's division-free form: q0 = nf*rcp; rem = fma(-q0, 1000, nf); q = fma(rem, rcp, q0)
+    rcp = np.float32(1.0) / np.float32(1000.0)
+    q0 = (nf * rcp).astype(np.float32)
+    rem = nf.astype(np.float64) - q0.astype(np.float64) * 1000.0          # exact in double
+    assert np.array_equal(rem, rem.astype(np.float32).astype(np.float64)), "the remainder is exactly representable"
+    q = (q0.astype(np.float64) + rem * np.float64(rcp))
+    # distance of the exact fma argument to the nearest float rounding boundary dwarfs one double rounding
+    qf = q.astype(np.float32)
+    assert np.array_equal(ref, qf)
