@@ -1,0 +1,61 @@
+// fhog_common.cuh -- per-pixel pieces shared by the fused kernels (kcf_fused.cuh) and the any-size path (kcf_generic.cu).
+#pragma once
+#include "mot_internal.h"
+
+namespace mot {
+
+// gray = (float)(0.144*B + 0.587*G + 0.299*R), evaluated in double by the reference (top/drawlib.c:234; yes, 0.144).
+// For 8-bit channels the double result is never within 3e-11 (relative) of a float rounding boundary, while the double
+// evaluation is within 5e-16 of N/1000 with N = 144B + 587G + 299R, so the reference value IS the correctly rounded float
+// of N/1000 (checked against the C expression for all 2^24 colours in tests/test_cabi_exports.py).  N < 2^24 is exact in
+// float; one Newton step on q0 = N * RN(1/1000) gives the correctly rounded quotient without touching the FP64 pipe.
+__device__ __forceinline__ float bgr_gray(const uint8_t *p)
+{
+    const float nf = (float)(144 * (int)p[0] + 587 * (int)p[1] + 299 * (int)p[2]);
+    const float rcp = 1.0f / 1000.0f;
+    const float q0 = __fmul_rn(nf, rcp);
+    const float rem = __fmaf_rn(-q0, 1000.0f, nf);
+    return __fmaf_rn(rem, rcp, q0);
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+
+// One pixel of gradMag + gradQuantize (libhog/gradientMex.cpp:59-100, :112-145) given its two gradient components:
+// magnitude through the host-harvested rsqrtps / rcpps tables, orientation bin through the acos/quantiser step table.
+// Returns M0 = M/16 and writes the bin.  rs_tab / rc_tab / bn_tab may live in shared or global memory.
+__device__ __forceinline__ float grad_pixel(float gx, float gy, const float *rs_tab, const float *rc_tab, const uint32_t *bn_tab,
+                                            const FhogTablesDev &tab, int *bin_out)
+{
+    const float m2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
+    float m;
+    {
+        const uint32_t u = __float_as_uint(m2);
+        if (u < 0x00800000u) m = 1e10f;                       // rsqrtps(+0 / denormal) = +inf -> MIN(.,1e10f)
+        else {
+            const int e = (int)(u >> 23) - 127;
+            const uint32_t key = (u & 0x7FFFFFu) >> (23 - tab.rsqrt_bits);
+            const uint32_t T = __float_as_uint(rs_tab[((e & 1) << tab.rsqrt_bits) + key]);
+            m = __uint_as_float(T - ((uint32_t)(e >> 1) << 23));
+            m = (m < 1e10f) ? m : 1e10f;
+        }
+    }
+    float M;
+    {
+        const uint32_t u = __float_as_uint(m);
+        const int e = (int)(u >> 23) - 127;
+        const uint32_t U = __float_as_uint(rc_tab[(u & 0x7FFFFFu) >> (23 - tab.rcp_bits)]);
+        M = __uint_as_float(U - ((uint32_t)e << 23));
+    }
+    float gn = __fmul_rn(__fmul_rn(gx, m), 10000.0f);
+    gn = __uint_as_float(__float_as_uint(gn) ^ (__float_as_uint(gy) & 0x80000000u));
+    int ai = __float2int_rz(gn) + 10010;
+    ai = clampi(ai, 0, 20019);
+    const uint32_t ent = bn_tab[(gy < 0.f ? tab.bin_nseg : 0) + (ai >> tab.bin_shift)];
+    int bb = (int)(ent & 0xFFu) - ((uint32_t)ai >= (ent >> 8) ? 1 : 0);
+    if (bb >= 18) bb = 0;
+    *bin_out = bb;
+    return __fmul_rn(M, 0.0625f);                             // M0 = M * (1/bin^2), gradientMex.cpp:143
+}
+
+}  // namespace mot

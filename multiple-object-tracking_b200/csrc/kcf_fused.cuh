@@ -21,6 +21,7 @@
 // reference's pixel order); the FFTs and the spectral products are ordinary f32.
 #pragma once
 #include "mot_internal.h"
+#include "fhog_common.cuh"
 #include "fft_reg.cuh"
 
 namespace mot {
@@ -63,22 +64,6 @@ template <int HR, int WC> size_t smem_bytes(int lut_floats)
     using G = Geo<HR, WC>;
     return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS) + G::N_FLOATS + G::NB + HR + WC + 64);
 }
-
-// gray = (float)(0.144*B + 0.587*G + 0.299*R), evaluated in double by the reference (top/drawlib.c:234; yes, 0.144).
-// For 8-bit channels the double result is never within 3e-11 (relative) of a float rounding boundary, while the double
-// evaluation is within 5e-16 of N/1000 with N = 144B + 587G + 299R, so the reference value IS the correctly rounded float
-// of N/1000 (checked against the C expression for all 2^24 colours in tests/test_cabi_exports.py).  N < 2^24 is exact in
-// float; one Newton step on q0 = N * RN(1/1000) gives the correctly rounded quotient without touching the FP64 pipe.
-__device__ __forceinline__ float bgr_gray(const uint8_t *p)
-{
-    const float nf = (float)(144 * (int)p[0] + 587 * (int)p[1] + 299 * (int)p[2]);
-    const float rcp = 1.0f / 1000.0f;
-    const float q0 = __fmul_rn(nf, rcp);
-    const float rem = __fmaf_rn(-q0, 1000.0f, nf);
-    return __fmaf_rn(rem, rcp, q0);
-}
-
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

@@ -29,7 +29,7 @@ static int fail(int code, const char *fmt, ...)
 
 namespace {
 
-struct SizeClass { int hr, wc, live; float *d_wy, *d_wx, *d_yf; float norm; };
+struct SizeClass { int hr, wc, live; bool fast; float *d_wy, *d_wx, *d_yf; double2 *d_twh, *d_tww; float norm; };
 
 template <class T> struct DevBuf {
     T *p = nullptr; size_t n = 0;
@@ -81,6 +81,7 @@ struct mot_ctx_s {
     DevBuf<mot_bbox_t> d_boxes, d_trk, d_det;
     DevBuf<KcfMeta> d_meta_stage;
     DevBuf<float> d_gray;
+    DevBuf<char> d_scratch;               // per-job intermediates of the any-size KCF path
     DevBuf<double> d_dist, d_work, d_cost;
     PinBuf<int> h_slots, h_frames, h_TD, h_assign;
     PinBuf<mot_bbox_t> h_boxes, h_trk, h_det;
@@ -93,6 +94,7 @@ struct mot_ctx_s {
 };
 
 static constexpr int MAX_CLASSES = 1024;
+static constexpr long DUMP_NB_MAX = 4096;       // stage dumps (test hook) are available for windows up to 64x64 cells
 
 __global__ void meta_scatter_kernel(KcfMeta *meta, const KcfMeta *src, const int *slots, int n)
 {
@@ -167,7 +169,18 @@ static int get_class(mot_ctx_t *c, int hr, int wc, int *out)
     CU(cudaMemcpy(sc.d_wy, wy.data(), sizeof(float) * hr, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.d_wx, wx.data(), sizeof(float) * wc, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.d_yf, yf.data(), sizeof(float) * yf.size(), cudaMemcpyHostToDevice));
-    KcfClassDev kd{ hr, wc, sc.d_wy, sc.d_wx, sc.d_yf, sc.norm };
+    sc.fast = kcf_fast_smem_bytes(hr, wc) != 0;
+    {
+        // exp(-2 pi i t / n) tables for the any-size DFT path, evaluated in double with exact argument reduction
+        const double two_pi = 6.283185307179586476925286766559;
+        std::vector<double2> th(hr), tw(wc);
+        for (int t = 0; t < hr; ++t) th[t] = make_double2(std::cos(two_pi * t / hr), -std::sin(two_pi * t / hr));
+        for (int t = 0; t < wc; ++t) tw[t] = make_double2(std::cos(two_pi * t / wc), -std::sin(two_pi * t / wc));
+        CU(cudaMalloc(&sc.d_twh, sizeof(double2) * hr)); CU(cudaMalloc(&sc.d_tww, sizeof(double2) * wc));
+        CU(cudaMemcpy(sc.d_twh, th.data(), sizeof(double2) * hr, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(sc.d_tww, tw.data(), sizeof(double2) * wc, cudaMemcpyHostToDevice));
+    }
+    KcfClassDev kd{ hr, wc, sc.d_wy, sc.d_wx, sc.d_yf, sc.norm, sc.d_twh, sc.d_tww };
     CU(cudaMemcpy(c->d_classes + c->classes.size(), &kd, sizeof(kd), cudaMemcpyHostToDevice));
     c->classes.push_back(sc);
     *out = (int)c->classes.size() - 1;
@@ -242,7 +255,9 @@ void mot_ctx_destroy(mot_ctx_t *c)
     for (auto p : c->frame_owned) if (p) cudaFree(p);
     cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
     cudaFree(c->d_tab_rsqrt); cudaFree(c->d_tab_rcp); cudaFree(c->d_tab_bin); cudaFree(c->kal.x); cudaFree(c->kal.P);
-    for (auto &sc : c->classes) { cudaFree(sc.d_wy); cudaFree(sc.d_wx); cudaFree(sc.d_yf); }
+    for (auto &sc : c->classes) { cudaFree(sc.d_wy); cudaFree(sc.d_wx); cudaFree(sc.d_yf); cudaFree(sc.d_twh); cudaFree(sc.d_tww); }
+    for (auto &m : c->meta_h) { if (m.model_ptr) cudaFree(m.model_ptr); if (m.alpha_ptr) cudaFree(m.alpha_ptr); }
+    c->d_scratch.release();
     c->d_slots.release(); c->d_frames.release(); c->d_TD.release(); c->d_assign.release(); c->d_boxes.release(); c->d_trk.release();
     c->d_det.release(); c->d_meta_stage.release(); c->d_gray.release(); c->d_dist.release(); c->d_work.release(); c->d_cost.release();
     c->h_slots.release(); c->h_frames.release(); c->h_TD.release(); c->h_assign.release(); c->h_boxes.release(); c->h_trk.release();
@@ -295,9 +310,8 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
         for (int i = 0; i < n; ++i) {
             const int rows = boxes[i].b - boxes[i].t + 1, cols = boxes[i].r - boxes[i].l + 1;          // kcf.cpp:148-149
             const int hr = rows / KCF_CELL, wc = cols / KCF_CELL;
-            if (hr < 2 || wc < 2) return fail(MOT_ERR_SHAPE, "window %dx%d px is smaller than 2x2 cells", rows, cols);
-            if (kcf_fast_smem_bytes(hr, wc) == 0)
-                return fail(MOT_ERR_SHAPE, "window %dx%d px = %dx%d cells: this build has fused kernels for 8/16/32-cell sides only", rows, cols, hr, wc);
+            if (hr < 2 || wc < 2) return fail(MOT_ERR_SHAPE, "window %dx%d px is smaller than 2x2 cells (8x8 px)", rows, cols);
+            if (rows > c->H || cols > c->W) return fail(MOT_ERR_SHAPE, "window %dx%d px is larger than the %dx%d frame", rows, cols, c->H, c->W);
         }
         long max_model = 0, max_alpha = 0;
         for (int i = 0; i < n; ++i) {
@@ -307,11 +321,16 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
             m.pos = boxes[i]; m.scale_horiz = 1.0f; m.scale_vert = 1.0f; m.first_update = 1;          // kcf.cpp:200-209
             int cls = 0; const int rc = get_class(c, m.hr, m.wc, &cls); if (rc) return rc;
             m.size_class = cls;
+            const long S_ = (long)m.wc * (m.hr / 2 + 1);
+            if (!c->classes[cls].fast) {
+                // sizes without a fused kernel own their model / alpha (they can exceed the fixed slot stride)
+                CU(cudaMalloc(&m.model_ptr, sizeof(float2) * KCF_CHAN * S_)); CU(cudaMalloc(&m.alpha_ptr, sizeof(float) * S_));
+                CU(cudaMemsetAsync(m.model_ptr, 0, sizeof(float2) * KCF_CHAN * S_, c->stream)); CU(cudaMemsetAsync(m.alpha_ptr, 0, sizeof(float) * S_, c->stream));
+            }
             const int slot = c->free_slots.back(); c->free_slots.pop_back();
             c->used[slot] = 1; c->meta_h[slot] = m; c->classes[cls].live++;
             c->h_slots.p[i] = slot; c->h_meta_stage.p[i] = m; handles_out[i] = slot;
-            const long S = (long)m.wc * (m.hr / 2 + 1);
-            max_model = std::max(max_model, KCF_CHAN * S); max_alpha = std::max(max_alpha, S);
+            if (c->classes[cls].fast) { max_model = std::max(max_model, KCF_CHAN * S_); max_alpha = std::max(max_alpha, S_); }
         }
         CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_meta_stage.p, c->h_meta_stage.p, sizeof(KcfMeta) * n, cudaMemcpyHostToDevice, c->stream));
@@ -344,7 +363,11 @@ int mot_tracker_delete_batch(mot_ctx_t *c, int n, const int *handles)
         const int s = handles[i];
         if (s < 0 || s >= c->max_tracks || !c->used[s]) return fail(MOT_ERR_ARG, "delete of invalid handle %d", s);
         c->used[s] = 0;
-        if (c->kind == MOT_TRACKER_KCF) c->classes[c->meta_h[s].size_class].live--;
+        if (c->kind == MOT_TRACKER_KCF) {
+            KcfMeta &m = c->meta_h[s];
+            c->classes[m.size_class].live--;
+            if (m.model_ptr || m.alpha_ptr) { cudaStreamSynchronize(c->stream); cudaFree(m.model_ptr); cudaFree(m.alpha_ptr); m.model_ptr = nullptr; m.alpha_ptr = nullptr; }
+        }
         c->free_slots.push_back(s);
     }
     return 0;
@@ -365,10 +388,19 @@ static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, c
 
 static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
 {
-    const int rc = kcf_launch_fast(mode, hr, wc, L, c->stream);
-    if (rc == -1000) return fail(MOT_ERR_SHAPE, "no fused kernel for %dx%d cells", hr, wc);
-    if (rc) return fail(MOT_ERR_CUDA, "KCF launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-    c->launches += 1;
+    if (kcf_fast_smem_bytes(hr, wc) != 0) {
+        const int rc = kcf_launch_fast(mode, hr, wc, L, c->stream);
+        if (rc) return fail(MOT_ERR_CUDA, "KCF launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+        return 0;
+    }
+    // any other size: unfused pipeline with per-job scratch, processed in chunks of at most ~1 GB of scratch
+    const size_t per_job = kcf_generic_scratch_bytes(hr, wc);
+    size_t jobs = std::min<size_t>((size_t)L.n_jobs, std::max<size_t>(1, ((size_t)1 << 30) / per_job));
+    CU(c->d_scratch.ensure(jobs * per_job));
+    const int rc = kcf_launch_generic(mode, hr, wc, L, c->d_scratch.p, c->d_scratch.n, c->stream);
+    if (rc < 0) return fail(MOT_ERR_CUDA, "KCF (any-size path) launch failed: %s", cudaGetErrorString((cudaError_t)(-rc)));
+    c->launches += rc;
     return 0;
 }
 
@@ -398,6 +430,7 @@ static int kcf_batch_host(mot_ctx_t *c, int mode, int n, const int *handles, con
         const int cls = c->meta_h[c->h_slots.p[a]].size_class;
         int b = a; while (b < n && c->meta_h[c->h_slots.p[b]].size_class == cls) ++b;
         KcfLaunch L; fill_launch(c, L, b - a, c->d_slots.p + a, c->d_frames.p + a, c->d_boxes.p + a, clamp);
+        if (c->dumps && (long)c->classes[cls].hr * c->classes[cls].wc > DUMP_NB_MAX) return fail(MOT_ERR_SHAPE, "stage dumps are limited to %ld cells", DUMP_NB_MAX);
         if (c->dumps) { c->dump_hr = c->classes[cls].hr; c->dump_wc = c->classes[cls].wc; c->dump_rows = c->meta_h[c->h_slots.p[a]].rows; c->dump_cols = c->meta_h[c->h_slots.p[a]].cols; if (b - a != 1 || n != 1) return fail(MOT_ERR_ARG, "stage dumps need a batch of exactly one job"); }
         const int rc = kcf_run(c, mode, c->classes[cls].hr, c->classes[cls].wc, L); if (rc) return rc;
         a = b;
@@ -501,6 +534,7 @@ static int kcf_gray(mot_ctx_t *c, int mode, int handle, const float *gray_host, 
     CU(cudaMemcpyAsync(c->d_boxes.p, c->h_boxes.p, sizeof(mot_bbox_t), cudaMemcpyHostToDevice, c->stream));
     KcfLaunch L; fill_launch(c, L, 1, c->d_slots.p, nullptr, c->d_boxes.p, 0);
     L.gray = c->d_gray.p; L.gray_stride = (long)npx;
+    if (c->dumps && (long)m.hr * m.wc > DUMP_NB_MAX) return fail(MOT_ERR_SHAPE, "stage dumps are limited to %ld cells", DUMP_NB_MAX);
     if (c->dumps) { c->dump_hr = m.hr; c->dump_wc = m.wc; c->dump_rows = m.rows; c->dump_cols = m.cols; }
     const int rc = kcf_run(c, mode, m.hr, m.wc, L); if (rc) return rc;
     if (mode == KCF_MODE_PREDICT) CU(cudaMemcpyAsync(c->h_boxes.p, c->d_boxes.p, sizeof(mot_bbox_t), cudaMemcpyDeviceToHost, c->stream));
@@ -633,11 +667,11 @@ int mot_debug_enable_dumps(mot_ctx_t *c, int enable)
     if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
     CU(cudaSetDevice(c->device));
     if (enable && !c->dump.gray) {
-        const long px = 16L * NB_MAX + 64L * 64, cell = NB_MAX, spec = NB_MAX;
+        const long cell = DUMP_NB_MAX, px = 16L * cell + 12L * 2 * cell + 64, spec = cell;     // sized for windows up to DUMP_NB_MAX cells
         KcfDump &d = c->dump;
         d.stride_px = px; d.stride_cell = cell; d.stride_spec = spec;
         CU(cudaMalloc(&d.gray, sizeof(float) * px)); CU(cudaMalloc(&d.m0, sizeof(float) * px)); CU(cudaMalloc(&d.bin, sizeof(int) * px));
-        CU(cudaMalloc(&d.r1, sizeof(float) * cell * 18)); CU(cudaMalloc(&d.nrm, sizeof(float) * (cell + 4 * 64 + 8)));
+        CU(cudaMalloc(&d.r1, sizeof(float) * cell * 18)); CU(cudaMalloc(&d.nrm, sizeof(float) * (3 * cell + 8)));
         CU(cudaMalloc(&d.feat, sizeof(float) * cell * KCF_CHAN)); CU(cudaMalloc(&d.spec, sizeof(float2) * spec * KCF_CHAN));
         CU(cudaMalloc(&d.zf, sizeof(float2) * spec)); CU(cudaMalloc(&d.resp, sizeof(float) * cell)); CU(cudaMalloc(&d.kf, sizeof(float) * spec));
         CU(cudaMalloc(&d.peak, sizeof(int) * 2)); CU(cudaMalloc(&d.margin, sizeof(float) * 2));
@@ -684,12 +718,12 @@ long mot_debug_state(mot_ctx_t *c, int handle, int which, void *host_out, long m
         const long S = (long)m.wc * (m.hr / 2 + 1);
         if (which == 0) {
             const long bytes = 8 * KCF_CHAN * S; if (bytes > max_bytes) return fail(MOT_ERR_ARG, "buffer too small");
-            e = cudaMemcpy(host_out, c->d_model + (long)handle * c->model_stride, bytes, cudaMemcpyDeviceToHost);
+            e = cudaMemcpy(host_out, m.model_ptr ? m.model_ptr : c->d_model + (long)handle * c->model_stride, bytes, cudaMemcpyDeviceToHost);
             return e == cudaSuccess ? bytes : fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
         }
         if (which == 1) {
             const long bytes = 4 * S; if (bytes > max_bytes) return fail(MOT_ERR_ARG, "buffer too small");
-            e = cudaMemcpy(host_out, c->d_alpha + (long)handle * c->alpha_stride, bytes, cudaMemcpyDeviceToHost);
+            e = cudaMemcpy(host_out, m.alpha_ptr ? m.alpha_ptr : c->d_alpha + (long)handle * c->alpha_stride, bytes, cudaMemcpyDeviceToHost);
             return e == cudaSuccess ? bytes : fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
         }
         return fail(MOT_ERR_ARG, "unknown state %d for a KCF context", which);

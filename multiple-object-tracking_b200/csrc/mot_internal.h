@@ -19,6 +19,8 @@ struct KcfMeta {
     float scale_horiz, scale_vert;    // kcf.cpp:470-472
     int first_update;                 // kcf.cpp:209
     int size_class;                   // index into the per-size constant tables
+    float2 *model_ptr;                // any-size tracks own their model / alpha (null: slot arena, see KcfLaunch)
+    float *alpha_ptr;
 };
 
 // Per-size constants shared by every track of the same window (kcf.cpp:203-207 are size-only).
@@ -27,6 +29,7 @@ struct KcfClassDev {
     const float *wy, *wx;             // hann_f(hr), hann_f(wc): cos_win = wy * wx^T (kcf.cpp:124-130)
     const float *yf_re;               // Re(fft2(labels)), S floats (only the real part is ever used, kcf.cpp:373)
     float norm;                       // feature_norm_ratio = 1/(wc*hr*31) (kcf.cpp:197)
+    const double2 *tw_hr, *tw_wc;     // exp(-2 pi i t / n) for n = hr, wc (any-size DFT path)
 };
 
 struct FhogTablesDev {
@@ -76,5 +79,11 @@ enum { KCF_MODE_PREDICT = 0, KCF_MODE_UPDATE = 1 };
 // returns 0 when (hr, wc) has a register-FFT instantiation
 int kcf_launch_fast(int mode, int hr, int wc, const KcfLaunch &p, cudaStream_t s);
 size_t kcf_fast_smem_bytes(int hr, int wc);
+
+// Any window size (hr, wc >= 2): unfused multi-kernel pipeline with per-job scratch in global memory.
+// rows_max / cols_max bound the template sizes of the jobs (4*hr+3 / 4*wc+3).  Returns the number of kernels launched
+// (> 0) or a negative cudaError.
+size_t kcf_generic_scratch_bytes(int hr, int wc);
+int kcf_launch_generic(int mode, int hr, int wc, const KcfLaunch &p, void *scratch, size_t scratch_bytes, cudaStream_t s);
 
 }  // namespace mot

@@ -18,7 +18,8 @@ def one_box(l, t, rows, cols, typ=1):
     return b
 
 
-@pytest.mark.parametrize("rows,cols", [(128, 128), (64, 64), (64, 128), (130, 67), (35, 34)])
+@pytest.mark.parametrize("rows,cols", [(128, 128), (64, 64), (64, 128), (130, 67), (35, 34),
+                                       (120, 160), (100, 60), (37, 53), (150, 91), (8, 8)])   # second row: sizes without a fused kernel (any-size path)
 def test_stagewise_vs_oracle(oracle, rows, cols):
     require_gpu()
     M = mot()
@@ -133,10 +134,10 @@ def test_mixed_sizes_batch_and_gray_entry(oracle):
     W, H = 1280, 720
     sc = Scene(31, W, H, 12, tsize=40, win=64)
     frame = sc.render()
-    sizes = [(128, 128), (64, 64), (64, 128), (128, 64), (32, 32), (128, 128), (64, 64), (35, 130)]
+    sizes = [(128, 128), (64, 64), (64, 128), (128, 64), (32, 32), (128, 128), (64, 64), (35, 130), (120, 100), (51, 77), (120, 100)]
     b = boxes_array(len(sizes))
     for i, (r, c) in enumerate(sizes):
-        b[i] = one_box(60 + 140 * i, 100 + 30 * (i % 3), r, c, typ=i % 3)[0]
+        b[i] = one_box(40 + 100 * i, 100 + 30 * (i % 3), r, c, typ=i % 3)[0]
     ctx = M.Context(W, H, max_tracks=32, n_frame_slots=2, kind=M.TRACKER_KCF)
     ctx.upload(1, frame)
     h = ctx.new(b)
@@ -169,5 +170,30 @@ def test_unsupported_shape_fails_loudly():
     M = mot()
     ctx = M.Context(640, 480, max_tracks=4, kind=M.TRACKER_KCF)
     with pytest.raises(M.MotError):
-        ctx.new(one_box(10, 10, 120, 160))       # 30x40 cells: no fused kernel in this build
+        ctx.new(one_box(10, 10, 7, 40))          # fewer than 2 cells along one side
+    with pytest.raises(M.MotError):
+        ctx.new(one_box(0, 0, 500, 100))         # taller than the frame
     ctx.close()
+
+
+def test_config1_mixed_radix_window_sequence(oracle):
+    """BASELINE config 1, mixed-radix variant: a 120x160-px window = 30x40 cells, any-size path."""
+    require_gpu()
+    M = mot()
+    W, H = 640, 480
+    sc = Scene(0x5EED0101, W, H, 1, tsize=51, win=128, vmax=2.0)
+    sc.pos[:] = [[320.0, 240.0]]
+    frame = sc.render()
+    b = one_box(240, 180, 120, 160)
+    ctx = M.Context(W, H, max_tracks=2, n_frame_slots=1, kind=M.TRACKER_KCF)
+    ctx.upload(0, frame)
+    h = ctx.new(b); ob = box_of(b[0]); oh = oracle.kcf_new(ob)
+    ctx.update(h, [0], b); oracle.kcf_update(oh, crop_gray(oracle, frame, ob, 120, 160), ob)
+    for f in range(25):
+        sc.step(); frame = sc.render(); ctx.upload(0, frame)
+        out = ctx.predict(h, [0], b, clamp=1)
+        oracle.kcf_predict(oh, crop_gray(oracle, frame, ob, 120, 160), ob)
+        assert tuple(int(out[0][k]) for k in "ltbr") == ob.tup(), "frame %d" % f
+        b = out.copy()
+        ctx.update(h, [0], b); oracle.kcf_update(oh, crop_gray(oracle, frame, ob, 120, 160), ob)
+    oracle.kcf_delete(oh); ctx.close()

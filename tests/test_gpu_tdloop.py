@@ -38,6 +38,34 @@ def test_frame_loop_trace(oracle, tracker, mode):
     td.close(); ref.close(); ctx.close()
 
 
+def test_frame_loop_with_detections_of_any_size(oracle):
+    """Detections whose sizes change from frame to frame: templates of arbitrary size (any-size path) and the
+    reference's scrambled resize on every update whose box differs from the template."""
+    require_gpu()
+    M = mot()
+    W, H = 1280, 720
+    sc = Scene(77, W, H, 8, tsize=40, win=64)
+    ctx = M.Context(W, H, max_tracks=128, n_frame_slots=1, kind=M.TRACKER_KCF)
+    td = ctx.td(0, cap=64, cost_mode=0)
+    ref = oracle.td_new("kcf", W, H, 64, 0)
+    rng = np.random.default_rng(8)
+    grow = rng.integers(-6, 30, size=(8, 2))
+    for f in range(14):
+        sc.step()
+        frame = sc.render()
+        dets = sc.windows(jitter=1)
+        jig = rng.integers(-2, 3, size=(8, 2))
+        dets["r"] = np.clip(dets["r"] + grow[:, 0] + jig[:, 0], dets["l"] + 16, W - 1)
+        dets["b"] = np.clip(dets["b"] + grow[:, 1] + jig[:, 1], dets["t"] + 16, H - 1)
+        td.step(frame, dets); ref.step(frame, dets)
+        a, b = td.tracks(), ref.tracks()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (f, k)
+        pa, aa = td.last(); pb, ab = ref.last()
+        assert np.array_equal(pa, pb) and np.array_equal(aa, ab), f
+    td.close(); ref.close(); ctx.close()
+
+
 def test_multi_stream_lockstep_equals_single(oracle):
     require_gpu()
     M = mot()
