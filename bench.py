@@ -73,7 +73,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -237,10 +237,8 @@ def run_b200(args):
     total_ms = evs[0].elapsed_time(evs[-1])
     t_pred = sum(evs[2 * k].elapsed_time(evs[2 * k + 1]) for k in range(args.steps)) / args.steps
     t_upd = sum(evs[2 * k + 1].elapsed_time(evs[2 * k + 2]) for k in range(args.steps)) / args.steps
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    from mot_b200.shard import max_over_ranks
+    total_ms = max_over_ranks(total_ms, dev)              # device time of the step = max over ranks
     value = world * n * args.steps / (total_ms * 1e-3)
 
     # ---- sanity: the trackers are still on their targets (the timed work was real) ------------------------------------
@@ -276,10 +274,7 @@ def run_b200(args):
             e2e_step(2 + k)
         ctx2.sync()
         dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(dt, dev)
         e2e = {"value": world * n * ke / dt, "unit": "track-updates/s", "h2d_bytes_per_step": NS * H * W * 3 + 2 * n * (24 + 8),
                "d2h_bytes_per_step": n * 24, "steps": ke, "ms_per_step": 1e3 * dt / ke}
         ctx2.close()
@@ -294,13 +289,20 @@ def run_b200(args):
         dom = "update" if t_upd >= t_pred else "predict"
         bytes_dom = (B_UPDATE if dom == "update" else B_PREDICT) * n
         achieved = bytes_dom / (max(t_upd, t_pred) * 1e-3) / 1e9
+        traffic = None
+        try:            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("jobs_per_launch") == n:
+                traffic = tj[dom]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "kcf_fused_kernel<32,32,%s>" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                     "ms_predict": t_pred, "ms_update": t_upd, "algorithmic_bytes_per_track": {"predict": B_PREDICT, "update": B_UPDATE},
                     "step_frac": (B_PAIR * n / ((t_pred + t_upd) * 1e-3) / 1e9) / peak}
         cb = None
         if world == 1 and not args.no_cpu:
-            cb, _ = cpu_reference(os.cpu_count() or 1, 16, 2, 8)
+            cb, _ = cpu_reference(os.cpu_count() or 1, 32, 2, 24)
         line = {"metric": "KCF track-updates/sec", "value": value, "unit": "track-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
