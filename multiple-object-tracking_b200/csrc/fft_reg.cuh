@@ -55,4 +55,24 @@ template <int N, int DIR> __device__ __forceinline__ void fft_dif(float2 (&a)[N]
     }
 }
 
+// N-point FFT shared by a pair of adjacent lanes (lane parity `half`): lane 0 holds points 0..N/2-1, lane 1 holds points
+// N/2..N-1.  The first radix-2 (DIF) stage crosses the pair through warp shuffles; each lane then transforms its N/2
+// points on its own.  On return lane `half` holds X[2m + half] in a[brev<N/2>(m)].  `mask` = lanes taking part.
+template <int N, int DIR> __device__ __forceinline__ void fft_pair(float2 (&a)[N / 2], int half, unsigned mask)
+{
+    constexpr int H = N / 2;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float ox = __shfl_xor_sync(mask, a[i].x, 1), oy = __shfl_xor_sync(mask, a[i].y, 1);
+        const float2 sum = make_float2(a[i].x + ox, a[i].y + oy);                       // lane 0: u + v
+        const float2 dif = cmul_tw<DIR>(make_float2(ox - a[i].x, oy - a[i].y), i, N);   // lane 1: (u - v) w^i, u = partner's point
+        a[i] = half ? dif : sum;
+    }
+    fft_dif<H, DIR>(a);
+}
+
+// position of packed bin k in row j of the spectrum buffer: an XOR swizzle that keeps (a) the column-wise writers of the
+// row pass, (b) the pair-wise readers of the column pass (rows j and j + WC/2 in the same instruction) off each other's banks
+template <int HK, int WC> __device__ __forceinline__ int fpos(int k, int j) { return k ^ (j & (HK - 1)) ^ ((j >= WC / 2) ? (HK >> 1) : 0); }
+
 }  // namespace mot

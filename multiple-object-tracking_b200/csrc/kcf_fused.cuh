@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             for (int i = 0; i < HR; ++i) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j * HR + i] = (i & 1) ? z[i >> 1].y : z[i >> 1].x;
         }
         fft_dif<HK, -1>(z);
-        const int sw = j & (HK - 1);
+        const int sw = (j & (HK - 1)) ^ ((j >= WC / 2) ? (HK >> 1) : 0);   // see fpos()
         float2 *const dst = F2 + (c * WC + j) * HK;
         {
             const float2 z0 = z[0];
@@ -459,99 +459,89 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     __syncthreads();
 
     // ------------------------------------------------------------------ P5: complex FFT along the WC columns + spectral work
-    // Tasks (channel c, packed bin k).  Bins k >= 1 are ordinary columns; bin 0 carries two real-input columns (DC and
-    // Nyquist) that are separated after the transform.  The two kinds are kept in different warps (no divergence):
-    // threads [0, 31*(HK-1)) take k >= 1, the warp(s) from K0_BASE on take k = 0.
-    float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column products [31][WC]
+    // Tasks (channel c, packed bin k), each run by a PAIR of adjacent lanes that hold half of the WC points each (the
+    // first radix-2 stage goes through warp shuffles), so the transform fits the 64-register budget of a 1024-thread CTA.
+    // Lane `half` of a pair ends up with the output rows j' = 2m + half.  Bins k >= 1 are ordinary columns; bin 0 carries
+    // two real-input columns (DC and Nyquist) that are separated after the transform: the DC column is finished here, the
+    // Nyquist column is parked (unmultiplied) in FN and finished, one element per thread, in P5b.  The two kinds of task
+    // live in different warps (no divergence): tasks [0, 31*(HK-1)) have k >= 1, tasks from K0_BASE on have k = 0.
+    float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column [31][WC]
     float2 *const model = p.model + (long)slot * p.model_stride;
     const bool first = (MODE == KCF_MODE_UPDATE) && meta->first_update != 0;
     const float fac = first ? 1.0f : p.factor;                         // kcf.cpp:443
     const float omf = __fsub_rn(1.0f, fac);
-    constexpr int N_K1 = KCF_CHAN * (HK - 1);
-    constexpr int K0_BASE = (N_K1 + 31) & ~31;
-    static_assert(K0_BASE + KCF_CHAN <= NT, "P5 task layout");
-    if (tid < N_K1 || (tid >= K0_BASE && tid < K0_BASE + KCF_CHAN)) {
-        const bool k0 = tid >= K0_BASE;
-        const int c = k0 ? tid - K0_BASE : tid / (HK - 1);
-        const int k = k0 ? 0 : tid - c * (HK - 1) + 1;
-        const float2 *const mrow = model + c * S + k;                  // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186): + j*SK
-        constexpr int CH = 8, C0 = 4;                                  // model values in flight per thread (k >= 1 / k = 0 tasks)
-        float2 mpre[CH];
+    const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
+    {
+        constexpr int HW = WC / 2;
+        constexpr int N_K1 = KCF_CHAN * (HK - 1);
+        constexpr int K0_BASE = (N_K1 + 15) & ~15;                     // 16 pair-tasks per warp
+        static_assert(2 * (K0_BASE + KCF_CHAN) <= NT, "P5 task layout");
+        const int task = tid >> 1, half = tid & 1;
+        const bool active = task < N_K1 || (task >= K0_BASE && task < K0_BASE + KCF_CHAN);
+        const unsigned msk = __ballot_sync(0xFFFFFFFFu, active);
+        if (active) {
+            const bool k0 = task >= K0_BASE;
+            const int c = k0 ? task - K0_BASE : task / (HK - 1);
+            const int k = k0 ? 0 : task - c * (HK - 1) + 1;
+            float2 *const mrow = model + c * S + half * SK + k;        // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186): row j' = 2m + half
+            constexpr int CH = (HW < 4) ? HW : 4;                      // model values in flight per thread
+            float2 mpre[CH];
 #pragma unroll
-        for (int q = 0; q < CH; ++q) mpre[q] = make_float2(0.f, 0.f);
-        const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
-        if (need_model) {
+            for (int q = 0; q < CH; ++q) mpre[q] = need_model ? mrow[q * 2 * SK] : make_float2(0.f, 0.f);   // hides behind the FFT
+            float2 a[HW];
 #pragma unroll
-            for (int q = 0; q < CH; ++q) if (!k0 || q < C0) mpre[q] = mrow[q * SK];   // first chunk: its latency hides behind the FFT below
-        }
-        float2 a[WC];
+            for (int i = 0; i < HW; ++i) { const int j = half * HW + i; a[i] = F2[(c * WC + j) * HK + fpos<HK, WC>(k, j)]; }
+            fft_pair<WC, -1>(a, half, msk);
 #pragma unroll
-        for (int j = 0; j < WC; ++j) a[j] = F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))];
-        fft_dif<WC, -1>(a);
-        if (!k0) {
-#pragma unroll
-            for (int jb = 0; jb < WC; jb += CH) {
+            for (int mb = 0; mb < HW; mb += CH) {
                 float2 mv[CH];
 #pragma unroll
                 for (int q = 0; q < CH; ++q) mv[q] = mpre[q];
-                if (need_model && jb + CH < WC) {
+                if (need_model && mb + CH < HW) {
 #pragma unroll
-                    for (int q = 0; q < CH; ++q) mpre[q] = mrow[(jb + CH + q) * SK];
+                    for (int q = 0; q < CH; ++q) mpre[q] = mrow[(mb + CH + q) * 2 * SK];
                 }
 #pragma unroll
                 for (int q = 0; q < CH; ++q) {
-                    const int j = jb + q;
-                    const float2 v = a[brev<WC>(j)];
-                    if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + c * S + j * SK + k] = v;
+                    const int m = mb + q, jp = 2 * m + half;
+                    float2 v = a[brev<HW>(m)];
+                    if (k0) {
+                        // slot 0 = FFT(DC_j + i Nyq_j): X[j'] and X[-j'] (same parity -> same lane) give the two columns
+                        const float2 ya = a[brev<HW>((HW - m) % HW)], yb = a[brev<HW>(HW - 1 - m)];
+                        const float2 y = half ? yb : ya;
+                        const float2 v1 = make_float2(0.5f * (v.x + y.x), 0.5f * (v.y - y.y));   // DC column
+                        FN[c * WC + jp] = make_float2(0.5f * (v.y + y.y), 0.5f * (y.x - v.x));   // Nyquist column, finished in P5b
+                        v = v1;
+                    }
+                    if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + c * S + jp * SK + k] = v;
                     float2 o;
                     if (MODE == KCF_MODE_PREDICT) {
                         o = make_float2(v.x * mv[q].x + v.y * mv[q].y, v.y * mv[q].x - v.x * mv[q].y);     // xf * conj(model), kcf.cpp:306-345
                     } else {
                         o = make_float2(v.x * v.x + v.y * v.y, 0.f);                                         // |xf|^2, kcf.cpp:269-293
                         // model = (1-f) model + f xf, kcf.cpp:380-395 (f = 1 on the first update: the old model drops out)
-                        model[c * S + j * SK + k] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, mv[q].x), __fmul_rn(fac, v.x)),
-                                                                              __fadd_rn(__fmul_rn(omf, mv[q].y), __fmul_rn(fac, v.y)));
+                        mrow[m * 2 * SK] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, mv[q].x), __fmul_rn(fac, v.x)),
+                                                                   __fadd_rn(__fmul_rn(omf, mv[q].y), __fmul_rn(fac, v.y)));
                     }
-                    F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))] = o;
+                    F2[(c * WC + jp) * HK + fpos<HK, WC>(k, jp)] = o;
                 }
             }
+        }
+    }
+    __syncthreads();
+    // ---- P5b: the Nyquist column (k = HR/2), one element per thread
+    for (int e = tid; e < KCF_CHAN * WC; e += NT) {
+        const int c = e / WC, jp = e - c * WC;
+        const float2 v = FN[e];
+        const int sp1 = c * S + jp * SK + HK;
+        if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp1] = v;
+        if (MODE == KCF_MODE_PREDICT) {
+            const float2 m1 = model[sp1];
+            FN[e] = make_float2(v.x * m1.x + v.y * m1.y, v.y * m1.x - v.x * m1.y);
         } else {
-            // slot 0 = FFT(DC_j + i Nyq_j): separate the DC column (k = 0) and the Nyquist column (k = HR/2)
-#pragma unroll
-            for (int jb = 0; jb < WC; jb += C0) {
-                float2 mv[C0], mn[C0];
-#pragma unroll
-                for (int q = 0; q < C0; ++q) mv[q] = mpre[q];
-                if (need_model) {
-#pragma unroll
-                    for (int q = 0; q < C0; ++q) mn[q] = mrow[(jb + q) * SK + HK];
-                    if (jb + C0 < WC) {
-#pragma unroll
-                        for (int q = 0; q < C0; ++q) mpre[q] = mrow[(jb + C0 + q) * SK];
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < C0; ++q) {
-                    const int j = jb + q;
-                    const float2 x = a[brev<WC>(j)], y = a[brev<WC>((WC - j) % WC)];
-                    const float2 v0 = make_float2(0.5f * (x.x + y.x), 0.5f * (x.y - y.y));
-                    const float2 v1 = make_float2(0.5f * (x.y + y.y), 0.5f * (y.x - x.x));
-                    const int sp0 = c * S + j * SK, sp1 = sp0 + HK;
-                    if (DUMP && p.dump.spec) { p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp0] = v0; p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp1] = v1; }
-                    float2 o0, o1;
-                    if (MODE == KCF_MODE_PREDICT) {
-                        o0 = make_float2(v0.x * mv[q].x + v0.y * mv[q].y, v0.y * mv[q].x - v0.x * mv[q].y);
-                        o1 = make_float2(v1.x * mn[q].x + v1.y * mn[q].y, v1.y * mn[q].x - v1.x * mn[q].y);
-                    } else {
-                        o0 = make_float2(v0.x * v0.x + v0.y * v0.y, 0.f);
-                        o1 = make_float2(v1.x * v1.x + v1.y * v1.y, 0.f);
-                        model[sp0] = first ? v0 : make_float2(__fadd_rn(__fmul_rn(omf, mv[q].x), __fmul_rn(fac, v0.x)), __fadd_rn(__fmul_rn(omf, mv[q].y), __fmul_rn(fac, v0.y)));
-                        model[sp1] = first ? v1 : make_float2(__fadd_rn(__fmul_rn(omf, mn[q].x), __fmul_rn(fac, v1.x)), __fadd_rn(__fmul_rn(omf, mn[q].y), __fmul_rn(fac, v1.y)));
-                    }
-                    F2[(c * WC + j) * HK + (0 ^ (j & (HK - 1)))] = o0;
-                    FN[c * WC + j] = o1;
-                }
-            }
+            FN[e] = make_float2(v.x * v.x + v.y * v.y, 0.f);
+            if (first) model[sp1] = v;
+            else { const float2 m1 = model[sp1]; model[sp1] = make_float2(__fadd_rn(__fmul_rn(omf, m1.x), __fmul_rn(fac, v.x)), __fadd_rn(__fmul_rn(omf, m1.y), __fmul_rn(fac, v.y))); }
         }
     }
     __syncthreads();
@@ -564,7 +554,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < KCF_CHAN; ++c) {
-            const float2 v = (k < HK) ? F2[(c * WC + j) * HK + (k ^ (j & (HK - 1)))] : FN[c * WC + j];
+            const float2 v = (k < HK) ? F2[(c * WC + j) * HK + fpos<HK, WC>(k, j)] : FN[c * WC + j];
             if (c == 0) acc = v; else { acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); }
         }
         if (MODE == KCF_MODE_PREDICT) {
@@ -594,14 +584,20 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 
     // ------------------------------------------------------------------ P7: response = c2r(zf), first-max argmax, box shift
     float *const resp = reinterpret_cast<float *>(zf_s + S);           // [WC][HR]
-    if (tid < SK) {
-        // inverse complex FFT along the WC columns for half-spectrum row k = tid
-        float2 a[WC];
+    {
+        // inverse complex FFT along the WC columns of every half-spectrum bin k, one lane pair per bin
+        constexpr int HW = WC / 2;
+        const int kk = tid >> 1, half = tid & 1;
+        const bool active = kk < SK;
+        const unsigned msk = __ballot_sync(0xFFFFFFFFu, active);
+        if (active) {
+            float2 a[HW];
 #pragma unroll
-        for (int j = 0; j < WC; ++j) a[j] = zf_s[j * SK + tid];
-        fft_dif<WC, +1>(a);
+            for (int i = 0; i < HW; ++i) a[i] = zf_s[(half * HW + i) * SK + kk];
+            fft_pair<WC, +1>(a, half, msk);
 #pragma unroll
-        for (int j = 0; j < WC; ++j) zf_s[j * SK + tid] = a[brev<WC>(j)];
+            for (int m = 0; m < HW; ++m) zf_s[(2 * m + half) * SK + kk] = a[brev<HW>(m)];
+        }
     }
     __syncthreads();
     if (tid < WC) {

@@ -8,7 +8,7 @@ namespace mot {
 
 constexpr int KCF_CHAN = 31;          // trackers/kcf.cpp:157 f_chan = 32 - 1
 constexpr int KCF_CELL = 4;           // trackers/kcf.cpp:488
-constexpr int KCF_THREADS = 512;      // one CTA per track job
+constexpr int KCF_THREADS = 1024;     // one CTA per track job, 32 warps, 64 registers per thread
 constexpr int NB_MAX = 1152;          // cells per window the fused kernel can hold in shared memory (32x32 = 1024 named shape)
 
 // Per-track persistent state (one per slot), trackers/kcf.cpp:27-76 minus everything derivable.
