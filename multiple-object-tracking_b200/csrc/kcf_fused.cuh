@@ -33,7 +33,7 @@ template <int HR, int WC> struct Geo {
     static constexpr int S = WC * SK;
     static constexpr int H0 = 4 * HR, W0 = 4 * WC;
     static constexpr int RMAX = 4 * HR + 3, CMAX = 4 * WC + 3;
-    static constexpr int GS = RMAX;                      // gray column stride (odd -> conflict-free in both directions)
+    static constexpr int GS = RMAX + 2;                  // gray column stride incl. a 1-pixel replicated apron (odd -> conflict-free both ways)
     static constexpr int RS = HR + 1;                    // histogram / normaliser column stride
     // (M/16, bin) per pixel with a 2..5-pixel zero border, de-interleaved along y: [x+2][(y+2)&3][(y+2)>>2]
     static constexpr int PC = 4 * (HR + 2);                // column pitch of the padded layout
@@ -41,7 +41,7 @@ template <int HR, int WC> struct Geo {
     static constexpr int RAW_PITCH = 432;                  // bytes per staged frame row: 3*(4*32+3) + 2*15 alignment slack, 16-byte multiple
     static constexpr int RAW_FLOATS = RMAX * RAW_PITCH / 4;
     static constexpr int F_MIN = 31 * NB;
-    static constexpr int F_A = CMAX * GS > PADM + PADM / 4 ? CMAX * GS : PADM + PADM / 4;
+    static constexpr int F_A = (CMAX + 2) * GS > PADM + PADM / 4 ? (CMAX + 2) * GS : PADM + PADM / 4;
     static constexpr int F_FLOATS = ((F_MIN > F_A ? F_MIN : F_A) + 3) & ~3;
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
@@ -166,15 +166,16 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 
     if (p.gray != nullptr) {
         const float *src = p.gray + (long)job * p.gray_stride;
-        for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; F[x * GS + y] = src[idx]; }
+        for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; F[(x + 1) * GS + y + 1] = src[idx]; }
     } else if (staged) {
-        mbar_wait(&mbar2, 0);
+        if (tid < 32) mbar_wait(&mbar2, 0);        // one warp polls, the others sleep at the barrier
+        __syncthreads();
         // staged bytes -> gray: one warp per row, lanes along x (3-byte pixels: conflict-free shared loads)
         const int warp = tid >> 5, lane = tid & 31;
         for (int y = warp; y < rows; y += NT / 32) {
             const unsigned char *rrow = raw + y * G::RAW_PITCH - a0;
 #pragma unroll 4
-            for (int x = lane; x < cols; x += 32) F[x * GS + y] = bgr_gray(rrow + clampi(l + x, 0, Wm) * 3);
+            for (int x = lane; x < cols; x += 32) F[(x + 1) * GS + y + 1] = bgr_gray(rrow + clampi(l + x, 0, Wm) * 3);
         }
     } else if (identity) {
         // unaligned frames: plain loads.  Equal sizes: bilinearInterpolationGray is an exact copy (top/drawlib.c:610-633, xs = ys = 1)
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         for (int y = warp; y < rows; y += NT / 32) {
             const uint8_t *r0 = frame + (long)clampi(t + y, 0, Hm) * p.frame_stride;
 #pragma unroll 4
-            for (int x = lane; x < cols; x += 32) F[x * GS + y] = bgr_gray(r0 + clampi(l + x, 0, Wm) * 3);
+            for (int x = lane; x < cols; x += 32) F[(x + 1) * GS + y + 1] = bgr_gray(r0 + clampi(l + x, 0, Wm) * 3);
         }
     } else {
         // the reference resamples a column-major crop as if it were row-major height x width; reproduced through
@@ -206,65 +207,51 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             const float l1 = __fadd_rn(__fmul_rn(ifx, c[2]), __fmul_rn(fx, c[3]));
             const float o = __fadd_rn(__fmul_rn(ify, l0), __fmul_rn(fy, l1));
             const int dc = k / rows, dr = k - dc * rows;                         // column-major template element
-            F[dc * GS + dr] = o;
+            F[(dc + 1) * GS + dr + 1] = o;
         }
     }
-    if (fetch && !staged) mbar_wait(&mbar2, 0);                // speculative rows must have landed before the region is reused
-    if (lut_smem) mbar_wait(&mbar, 0);
+    if (tid < 32) {
+        if (fetch && !staged) mbar_wait(&mbar2, 0);            // speculative rows must have landed before the region is reused
+        if (lut_smem) mbar_wait(&mbar, 0);
+    }
+    __syncthreads();
+    // replicated 1-pixel apron: grad1's one-sided border differences become plain central differences (factor 1)
+    for (int k = tid; k < 2 * (rows + cols); k += NT) {
+        if (k < 2 * rows) { const int y = k >> 1, right = k & 1; float *q = F + (right ? cols : 1) * GS + y + 1; q[right ? GS : -GS] = *q; }
+        else { const int k2 = k - 2 * rows, x = k2 >> 1, bot = k2 & 1; float *q = F + (x + 1) * GS + (bot ? rows : 1); q[bot ? 1 : -1] = *q; }
+    }
     __syncthreads();
     if (DUMP && p.dump.gray) {
         float *d = p.dump.gray + (long)job * p.dump.stride_px;
-        for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; d[idx] = F[x * GS + y]; }
+        for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; d[idx] = F[(x + 1) * GS + y + 1]; }
     }
 
     // ------------------------------------------------------------------ P1: gradient magnitude + orientation bin
     // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin)
     float m0r[G::PIX_PER_THREAD];
     unsigned char bnr[G::PIX_PER_THREAD];
+    {
+        const LutConsts lk = make_lut_consts(p.tab);
+        auto p1_pixels = [&](const float *rs, const float *rc, const uint32_t *bn) {
 #pragma unroll
-    for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
-        const int idx = tid + q * NT;
-        m0r[q] = 0.f; bnr[q] = 0;
-        if (idx < H0 * W0) {
-            const int x = idx / H0, y = idx - x * H0;
-            const float *g = F + x * GS + y;
-            // grad1: one-sided difference (x1) on the border, central difference (x0.5) inside -- as clamped neighbours
-            const int xm = x > 0 ? -GS : 0, xp = x < cols - 1 ? GS : 0, ym = y > 0 ? -1 : 0, yp = y < rows - 1 ? 1 : 0;
-            const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f, ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
-            const float gx = __fmul_rn(__fsub_rn(g[xp], g[xm]), rx);
-            const float gy = __fmul_rn(__fsub_rn(g[yp], g[ym]), ry);
-            const float m2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
-            // RCPSQRT (rsqrtps) from the harvested table: exponent parity + top mantissa bits, exact 2^-q scaling
-            float m;
-            {
-                const uint32_t u = __float_as_uint(m2);
-                if (u < 0x00800000u) m = 1e10f;                       // rsqrtps(+0 / denormal) = +inf -> MIN(.,1e10f)
-                else {
-                    const int e = (int)(u >> 23) - 127;
-                    const uint32_t key = (u & 0x7FFFFFu) >> (23 - p.tab.rsqrt_bits);
-                    const uint32_t T = __float_as_uint(rs_tab[((e & 1) << p.tab.rsqrt_bits) + key]);
-                    m = __uint_as_float(T - ((uint32_t)(e >> 1) << 23));
-                    m = (m < 1e10f) ? m : 1e10f;
+            for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
+                const int idx = tid + q * NT;
+                m0r[q] = 0.f; bnr[q] = 0;
+                if (idx < H0 * W0) {
+                    const int x = idx / H0, y = idx - x * H0;
+                    const float *g = F + (x + 1) * GS + y + 1;
+                    // grad1: one-sided difference (x1) on the border, central difference (x0.5) inside; the apron makes both one form
+                    const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f, ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
+                    const float gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), rx);
+                    const float gy = __fmul_rn(__fsub_rn(g[1], g[-1]), ry);
+                    int bb;
+                    m0r[q] = grad_pixel_k(gx, gy, rs, rc, bn, lk, &bb);
+                    bnr[q] = (unsigned char)bb;
                 }
             }
-            // RCP (rcpps) from the harvested table
-            float M;
-            {
-                const uint32_t u = __float_as_uint(m);
-                const int e = (int)(u >> 23) - 127;
-                const uint32_t U = __float_as_uint(rc_tab[(u & 0x7FFFFFu) >> (23 - p.tab.rcp_bits)]);
-                M = __uint_as_float(U - ((uint32_t)e << 23));
-            }
-            float gn = __fmul_rn(__fmul_rn(gx, m), 10000.0f);
-            gn = __uint_as_float(__float_as_uint(gn) ^ (__float_as_uint(gy) & 0x80000000u));
-            int ai = __float2int_rz(gn) + 10010;
-            ai = clampi(ai, 0, 20019);
-            const uint32_t ent = bn_tab[(gy < 0.f ? p.tab.bin_nseg : 0) + (ai >> p.tab.bin_shift)];
-            int bb = (int)(ent & 0xFFu) - ((uint32_t)ai >= (ent >> 8) ? 1 : 0);
-            if (bb >= 18) bb = 0;
-            m0r[q] = __fmul_rn(M, 0.0625f);                           // M0 = M * (1/bin^2), gradientMex.cpp:143
-            bnr[q] = (unsigned char)bb;
-        }
+        };
+        if (lut_smem) p1_pixels(R1, R1 + n_rs, reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc);   // shared-memory tables (LDS)
+        else p1_pixels(p.tab.rsqrt_tab, p.tab.rcp_tab, p.tab.bin_tab);                                   // oversized tables stay in global memory
     }
     __syncthreads();
     // (M0, bin) overwrite the gray patch in a zero-bordered layout de-interleaved along y, [x+2][(y+2)&3][(y+2)>>2], so
