@@ -57,6 +57,9 @@ template <class T> struct PinBuf {
 struct mot_ctx_s {
     int device = 0, W = 0, H = 0, max_tracks = 0, n_frames = 0, kind = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // frame uploads run here so that they overlap with kernels of the compute stream
+    std::vector<cudaEvent_t> slot_uploaded;   // per frame slot: recorded after its last upload
+    std::vector<char> slot_pending;           // an upload of this slot has not been waited for by the compute stream yet
     long launches = 0;
     // frames
     std::vector<uint8_t *> frame_owned;
@@ -187,6 +190,22 @@ static int get_class(mot_ctx_t *c, int hr, int wc, int *out)
     return 0;
 }
 
+// The compute stream waits for the uploads of the frame slots a launch is going to read (all pending ones when the slots
+// are only known on the device).  Uploads of OTHER slots (the next frames) keep streaming underneath the kernels.
+static int wait_frames(mot_ctx_t *c, int n, const int *frame_slots)
+{
+    if (frame_slots) {
+        for (int i = 0; i < n; ++i) {
+            const int s = frame_slots[i];
+            if (s >= 0 && s < c->n_frames && c->slot_pending[s]) { CU(cudaStreamWaitEvent(c->stream, c->slot_uploaded[s], 0)); c->slot_pending[s] = 0; }
+        }
+    } else {
+        for (int s = 0; s < c->n_frames; ++s)
+            if (c->slot_pending[s]) { CU(cudaStreamWaitEvent(c->stream, c->slot_uploaded[s], 0)); c->slot_pending[s] = 0; }
+    }
+    return 0;
+}
+
 static int sync_frame_ptrs(mot_ctx_t *c)
 {
     if (!c->frame_ptr_dirty) return 0;
@@ -215,9 +234,12 @@ int mot_ctx_create(mot_ctx_t **out, int device, int frame_w, int frame_h, int ma
     mot_ctx_t *c = new mot_ctx_t();
     c->device = device; c->W = frame_w; c->H = frame_h; c->max_tracks = max_tracks; c->n_frames = n_frame_slots; c->kind = tracker_kind;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     c->frame_owned.assign(n_frame_slots, nullptr);
     c->frame_ptr_h.assign(n_frame_slots, nullptr);
+    c->slot_uploaded.assign(n_frame_slots, nullptr); c->slot_pending.assign(n_frame_slots, 0);
+    for (auto &e : c->slot_uploaded) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->frame_stride = frame_w * 3;
     CU(cudaMalloc(&c->d_frame_ptr, sizeof(void *) * n_frame_slots));
     c->used.assign(max_tracks, 0);
@@ -264,12 +286,13 @@ void mot_ctx_destroy(mot_ctx_t *c)
     c->h_det.release(); c->h_meta_stage.release(); c->h_dist.release(); c->h_cost.release();
     cudaFree(c->dump.gray); cudaFree(c->dump.m0); cudaFree(c->dump.bin); cudaFree(c->dump.r1); cudaFree(c->dump.nrm); cudaFree(c->dump.feat);
     cudaFree(c->dump.spec); cudaFree(c->dump.zf); cudaFree(c->dump.resp); cudaFree(c->dump.kf); cudaFree(c->dump.peak); cudaFree(c->dump.margin);
+    cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); for (auto e : c->slot_uploaded) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
 int mot_ctx_set_stream(mot_ctx_t *c, void *s) { if (!c) return fail(MOT_ERR_ARG, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
-int mot_sync(mot_ctx_t *c) { if (!c) return fail(MOT_ERR_ARG, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+int mot_sync(mot_ctx_t *c) { if (!c) return fail(MOT_ERR_ARG, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->copy_stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
 long mot_launch_count(mot_ctx_t *c) { return c ? c->launches : 0; }
 int mot_ctx_kind(mot_ctx_t *c) { return c ? c->kind : MOT_ERR_ARG; }
 
@@ -281,7 +304,13 @@ int mot_frame_upload(mot_ctx_t *c, int slot, const uint8_t *host_bgr, int stride
     if (!c->frame_owned[slot]) CU(cudaMalloc(&c->frame_owned[slot], (size_t)c->W * 3 * c->H));
     if (c->frame_ptr_h[slot] != c->frame_owned[slot]) { c->frame_ptr_h[slot] = c->frame_owned[slot]; c->frame_ptr_dirty = true; }
     if (c->frame_stride != c->W * 3) return fail(MOT_ERR_ARG, "mixing bound device frames of another stride with uploaded frames");
-    CU(cudaMemcpy2DAsync(c->frame_owned[slot], (size_t)c->W * 3, host_bgr, (size_t)stride_bytes, (size_t)c->W * 3, c->H, cudaMemcpyHostToDevice, c->stream));
+    // On the copy stream: the upload of the next frame overlaps with kernels still running on the compute stream.  The next
+    // launch waits for it (frames_ready); the caller must not overwrite a slot that enqueued, unfinished work still reads
+    // (the host-array calls synchronise before returning, so alternating two slots per stream is always safe).
+    if (stride_bytes == c->W * 3) CU(cudaMemcpyAsync(c->frame_owned[slot], host_bgr, (size_t)c->W * 3 * c->H, cudaMemcpyHostToDevice, c->copy_stream));
+    else CU(cudaMemcpy2DAsync(c->frame_owned[slot], (size_t)c->W * 3, host_bgr, (size_t)stride_bytes, (size_t)c->W * 3, c->H, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->slot_uploaded[slot], c->copy_stream));
+    c->slot_pending[slot] = 1;
     return 0;
 }
 
@@ -412,6 +441,7 @@ static int kcf_batch_host(mot_ctx_t *c, int mode, int n, const int *handles, con
     if (!handles || !frame_slots || !boxes) return fail(MOT_ERR_ARG, "null array");
     CU(cudaSetDevice(c->device));
     { const int rc = sync_frame_ptrs(c); if (rc) return rc; }
+    { const int rc = wait_frames(c, n, frame_slots); if (rc) return rc; }
     std::vector<int> order(n);
     for (int i = 0; i < n; ++i) {
         const int s = handles[i];
@@ -451,6 +481,7 @@ static int kcf_batch_dev(mot_ctx_t *c, int mode, int n, const int *d_handles, co
     if (n == 0) return 0;
     CU(cudaSetDevice(c->device));
     { const int rc = sync_frame_ptrs(c); if (rc) return rc; }
+    { const int rc = wait_frames(c, 0, nullptr); if (rc) return rc; }
     int cls = -1;
     for (size_t i = 0; i < c->classes.size(); ++i) if (c->classes[i].live > 0) { if (cls >= 0) return fail(MOT_ERR_SHAPE, "device-array batches need all live trackers to share one window size; use the host-array call"); cls = (int)i; }
     if (cls < 0) return fail(MOT_ERR_ARG, "no live trackers");
