@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Secondary benchmarks of the association / Kalman side of the path (BASELINE configs 2 and 5).
+
+  config 2: Kalman tracker + Hungarian association, 64 tracks x 64 detections per frame, one 1080p stream
+            -> frames/s through the batched frame loop (mot_td_step) and through the oracle's loop on one host core
+  config 5: N independent 512x512 association problems (cost matrix + Munkres), device-resident
+            -> matrices/s on the GPU vs assignmentoptimal (oracle) on the host cores; assignments compared bit-exactly
+
+    python bench_assoc.py [--matrices 256] [--dim 512] [--cpu-matrices 8]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "multiple-object-tracking_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import numpy as np
+
+
+def config5(args):
+    import torch
+    import mot_b200 as M
+    import oraclelib
+    from synth import random_boxes, jittered_detections
+    n, dim = args.matrices, args.dim
+    rng = np.random.default_rng(0x5EED0500)
+    trk = np.zeros((n, dim), M.BBOX_DTYPE); det = np.zeros((n, dim), M.BBOX_DTYPE)
+    for m in range(n):
+        trk[m] = random_boxes(rng, dim, 1920, 1080)
+        det[m] = random_boxes(rng, dim, 1920, 1080)          # independent boxes: the hard case, no greedy shortcut
+    ctx = M.Context(1920, 1080, max_tracks=4, kind=M.TRACKER_KALMAN)
+    dev = torch.device("cuda", 0)
+    d_T = torch.full((n,), dim, dtype=torch.int32, device=dev); d_D = d_T.clone()
+    d_trk = torch.from_numpy(trk.view(np.uint8).reshape(n, dim * 24)).to(dev); d_det = torch.from_numpy(det.view(np.uint8).reshape(n, dim * 24)).to(dev)
+    d_dist = torch.zeros((n, dim * dim), dtype=torch.float64, device=dev)
+    d_assign = torch.zeros((n, dim), dtype=torch.int32, device=dev); d_cost = torch.zeros(n, dtype=torch.float64, device=dev)
+    stream = torch.cuda.Stream(); ctx.set_stream(stream.cuda_stream)
+    out = {}
+    for mode, name in ((M.COST_IOU_CLAMPED, "iou_clamped"), (M.COST_REF_CENTROID, "ref_centroid")):
+        def run():
+            rc = M.lib().mot_associate_batch_dev(ctx.h, n, d_T.data_ptr(), d_D.data_ptr(), d_trk.data_ptr(), dim, d_det.data_ptr(), dim, mode,
+                                                 d_dist.data_ptr(), dim * dim, d_assign.data_ptr(), dim, d_cost.data_ptr(), dim)
+            assert rc == 0, M.lib().mot_last_error()
+        with torch.cuda.stream(stream):
+            run(); stream.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream); run(); e1.record(stream); stream.synchronize()
+        ms = e0.elapsed_time(e1)
+        assign = d_assign.cpu().numpy(); dist = d_dist.cpu().numpy()
+        orc = oraclelib.Oracle(oraclelib.best())
+        ncpu = min(args.cpu_matrices, n)
+        t0 = time.perf_counter()
+        same = True
+        for m in range(ncpu):
+            a, _ = orc.assign(dist[m].reshape(dim, dim).T)
+            same &= bool(np.array_equal(a, assign[m]))
+        cpu_s = (time.perf_counter() - t0) / ncpu
+        out[name] = {"gpu_matrices_per_s": n / (ms * 1e-3), "gpu_ms_total": ms, "cpu_s_per_matrix_one_core": cpu_s,
+                     "speedup_vs_one_core": cpu_s * n / (ms * 1e-3), "bit_exact_on_checked": same, "checked": ncpu}
+    ctx.close()
+    return {"config": "C5: %d x (%dx%d) association problems, device resident" % (n, dim, dim), **out}
+
+
+def config2(args):
+    import mot_b200 as M
+    import oraclelib
+    from synth import Scene
+    W, H, frames = 1920, 1080, 300
+    sc = Scene(0x5EED0200, W, H, 64, tsize=48, win=96)
+    dets = []
+    for f in range(frames):
+        sc.step(); dets.append(sc.windows(jitter=2))
+    out = {}
+    for mode, name in ((0, "ref_centroid"), (1, "iou_clamped")):
+        ctx = M.Context(W, H, max_tracks=256, kind=M.TRACKER_KALMAN)
+        td = ctx.td(0, cap=128, cost_mode=mode)
+        td.step(None, dets[0])
+        t0 = time.perf_counter()
+        for f in range(1, frames):
+            td.step(None, dets[f])
+        g = (frames - 1) / (time.perf_counter() - t0)
+        orc = oraclelib.Oracle(oraclelib.best())
+        ref = orc.td_new("kal", W, H, 128, mode)
+        ref.step(None, dets[0])
+        t0 = time.perf_counter()
+        for f in range(1, frames):
+            ref.step(None, dets[f])
+        c = (frames - 1) / (time.perf_counter() - t0)
+        same = all(np.array_equal(td.tracks()[k], ref.tracks()[k]) for k in ("tid", "boxes", "age"))
+        out[name] = {"gpu_frames_per_s_host_loop": g, "cpu_frames_per_s_one_core": c, "identical_final_track_table": bool(same)}
+        td.close(); ref.close(); ctx.close()
+    # the same loop over 64 independent streams stepped in lock step: one predict / associate / update launch per frame for all
+    ns, fr2 = 64, 60
+    scs = [Scene(0x5EED0200 + 7 * s_, W, H, 64, tsize=48, win=96) for s_ in range(ns)]
+    dd = []
+    for f in range(fr2):
+        row = []
+        for sc_ in scs:
+            sc_.step(); row.append(sc_.windows(jitter=2))
+        dd.append(row)
+    ctx = M.Context(W, H, max_tracks=64 * 128, kind=M.TRACKER_KALMAN)
+    tds = [ctx.td(0, cap=128, cost_mode=0) for _ in range(ns)]
+    M.step_multi(tds, None, dd[0])
+    t0 = time.perf_counter()
+    for f in range(1, fr2):
+        M.step_multi(tds, None, dd[f])
+    out["lockstep_64_streams"] = {"gpu_stream_frames_per_s": ns * (fr2 - 1) / (time.perf_counter() - t0)}
+    for t in tds:
+        t.close()
+    ctx.close()
+    return {"config": "C2: Kalman + Hungarian, 64 tracks x 64 detections, one 1080p stream, %d frames (host-array frame loop, one sync per stage)" % frames, **out}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--matrices", type=int, default=148)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--cpu-matrices", type=int, default=2)
+    args = ap.parse_args()
+    print(json.dumps(config2(args)))
+    print(json.dumps(config5(args)))
