@@ -106,24 +106,50 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 
     __shared__ __align__(8) uint64_t mbar, mbar2;     // SSE tables / staged frame rows
     const int tid = threadIdx.x;
-    const int job = blockIdx.x;
-    if (job >= p.n_jobs) return;
     if (tid == 0) { mbar_init(&mbar, 1); mbar_init(&mbar2, 1); }
     __syncthreads();
-    // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
-    // The SSE tables and the frame rows of the ROI are pulled into shared memory by the bulk-copy engine
-    // (cp.async.bulk on an mbarrier), issued before anything else so that the per-track metadata loads overlap with
-    // them; rows start on arbitrary byte offsets, so each row is fetched as the enclosing 16-byte-aligned span.
     const bool lut_smem = lut_floats > 0;
     const int n_rs = 2 << p.tab.rsqrt_bits, n_rc = 1 << p.tab.rcp_bits, n_bn = (2 * p.tab.bin_nseg + 3) & ~3;
+    unsigned char *const raw = reinterpret_cast<unsigned char *>(R1 + ((lut_floats + 3) & ~3));
+    const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
+
+    // Fetch the frame rows of job `jb`'s crop into the staging area with the bulk-copy engine (cp.async.bulk on mbar2).
+    // Rows start on arbitrary byte offsets, so each row is fetched as the enclosing 16-byte-aligned span; that needs a
+    // 16-byte aligned frame base and stride (true for every common frame width).  Whether the crop has the template size
+    // (the only case that uses the staged rows) is known only when the metadata arrives: a crop that fits the staging area
+    // is fetched speculatively.  Executed by warp 1; exactly one arrival on mbar2 per job, with or without bytes.
+    auto issue_roi = [&](int jb) {
+        const mot_bbox_t bx = p.boxes[jb];
+        int l = bx.l, t = bx.t, r = bx.r, b = bx.b;
+        if (t > b) { const int q = t; t = b; b = q; }
+        if (l > r) { const int q = l; l = r; r = q; }
+        const int rows_s = b - t + 1, cols_s = r - l + 1;
+        const uint8_t *frame = (p.gray == nullptr) ? p.frame_ptr[p.frames[jb]] : nullptr;
+        const bool fetch = (p.gray == nullptr) && rows_s <= G::RMAX && cols_s <= G::CMAX && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0;
+        const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols_s - 1, 0, Wm);
+        const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;
+        if (tid == 32) mbar_expect_tx(&mbar2, fetch ? (uint32_t)rows_s * (uint32_t)(a1 - a0) : 0u);
+        __syncwarp();
+        if (fetch)
+            for (int y = tid - 32; y < rows_s; y += 32)
+                bulk_g2s(raw + y * G::RAW_PITCH, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar2);
+    };
+
+    // Persistent CTA: jobs blockIdx.x, blockIdx.x + gridDim.x, ...; the crop of the NEXT job streams into shared memory
+    // while the spectral phases of the current one run (the staging area is free from P5 on).
+    uint32_t phase = 0;
+    if (tid >= 32 && tid < 64 && (int)blockIdx.x < p.n_jobs) issue_roi(blockIdx.x);
+    for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, phase ^= 1u) {
+    __syncthreads();                                   // the previous job is done with every shared-memory region
+    // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
     const float *rs_tab = p.tab.rsqrt_tab, *rc_tab = p.tab.rcp_tab;
     const uint32_t *bn_tab = p.tab.bin_tab;
     if (lut_smem) { rs_tab = R1; rc_tab = R1 + n_rs; bn_tab = reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc; }
-    unsigned char *const raw = reinterpret_cast<unsigned char *>(R1 + ((lut_floats + 3) & ~3));
-    if (lut_smem && tid < 3) {
-        if (tid == 0) { mbar_expect_tx(&mbar, (uint32_t)(n_rs + n_rc + n_bn) * 4u); bulk_g2s(R1, p.tab.rsqrt_tab, n_rs * 4, &mbar); }
-        if (tid == 1) bulk_g2s(R1 + n_rs, p.tab.rcp_tab, n_rc * 4, &mbar);
-        if (tid == 2) bulk_g2s(R1 + n_rs + n_rc, p.tab.bin_tab, n_bn * 4, &mbar);
+    if (tid < 3) {
+        // SSE tables -> shared memory (one arrival on mbar per job)
+        if (tid == 0) { mbar_expect_tx(&mbar, lut_smem ? (uint32_t)(n_rs + n_rc + n_bn) * 4u : 0u); if (lut_smem) bulk_g2s(R1, p.tab.rsqrt_tab, n_rs * 4, &mbar); }
+        if (tid == 1 && lut_smem) bulk_g2s(R1 + n_rs, p.tab.rcp_tab, n_rc * 4, &mbar);
+        if (tid == 2 && lut_smem) bulk_g2s(R1 + n_rs + n_rc, p.tab.bin_tab, n_bn * 4, &mbar);
     }
 
     const int slot = p.slots[job];
@@ -133,19 +159,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     if (t > b) { const int q = t; t = b; b = q; }              // top/drawlib.c:203-215
     if (l > r) { const int q = l; l = r; r = q; }
     const int rows_s = b - t + 1, cols_s = r - l + 1;
-    const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
-    // bulk staging needs 16-byte aligned rows: frame base and stride multiples of 16 (true for every common frame width).
-    // Whether the crop has the template size (the only case that uses the staged rows) is known only after the metadata
-    // arrives; a crop that fits the staging area is fetched speculatively.
     const bool fetch = (p.gray == nullptr) && rows_s <= G::RMAX && cols_s <= G::CMAX && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0;
     const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols_s - 1, 0, Wm);
-    const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;      // aligned byte span of a frame row
-    if (fetch && tid >= 32 && tid < 64) {
-        if (tid == 32) mbar_expect_tx(&mbar2, (uint32_t)rows_s * (uint32_t)(a1 - a0));
-        __syncwarp();
-        for (int y = tid - 32; y < rows_s; y += 32)
-            bulk_g2s(raw + y * G::RAW_PITCH, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar2);
-    }
+    const int a0 = (x_lo * 3) & ~15;                           // aligned start of the staged byte span of a frame row
 
     KcfMeta *const meta = p.meta + slot;
     const KcfClassDev cls = p.classes[meta->size_class];
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         const float *src = p.gray + (long)job * p.gray_stride;
         for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; F[(x + 1) * GS + y + 1] = src[idx]; }
     } else if (staged) {
-        if (tid < 32) mbar_wait(&mbar2, 0);        // one warp polls, the others sleep at the barrier
+        if (tid < 32) mbar_wait(&mbar2, phase);    // one warp polls, the others sleep at the barrier
         __syncthreads();
         // staged bytes -> gray: one warp per row, lanes along x (3-byte pixels: conflict-free shared loads)
         const int warp = tid >> 5, lane = tid & 31;
@@ -211,8 +227,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         }
     }
     if (tid < 32) {
-        if (fetch && !staged) mbar_wait(&mbar2, 0);            // speculative rows must have landed before the region is reused
-        if (lut_smem) mbar_wait(&mbar, 0);
+        if (!staged) mbar_wait(&mbar2, phase);                 // (speculative) rows must have landed before the region is reused
+        mbar_wait(&mbar, phase);
     }
     __syncthreads();
     // replicated 1-pixel apron: grad1's one-sided border differences become plain central differences (factor 1)
@@ -444,6 +460,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         }
     }
     __syncthreads();
+    // The histograms are consumed: the staging area is free again -> start streaming the next job's crop underneath P5..P7
+    if (tid >= 32 && tid < 64 && job + (int)gridDim.x < p.n_jobs) issue_roi(job + gridDim.x);
 
     // ------------------------------------------------------------------ P5: complex FFT along the WC columns + spectral work
     // Tasks (channel c, packed bin k), each run by a PAIR of adjacent lanes that hold half of the WC points each (the
@@ -565,7 +583,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             meta->scale_vert = __fdiv_rn((float)(box.b - box.t + 1), (float)rows);
             meta->first_update = 0;
         }
-        return;
+        continue;                                      // next job (uniform: MODE is a template parameter)
     }
     __syncthreads();
 
@@ -643,6 +661,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         }
         p.boxes[job] = pos;
     }
+    }   // persistent job loop
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -658,8 +677,13 @@ template <int HR, int WC> int kcf_launch_size(int mode, const KcfLaunch &p, cuda
     else                          fn = dump ? (const void *)kcf_fused_kernel<HR, WC, KCF_MODE_UPDATE, true> : (const void *)kcf_fused_kernel<HR, WC, KCF_MODE_UPDATE, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
+    // persistent CTAs: one per SM (207 KB of shared memory each), looping over the jobs
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = p.n_jobs < sms ? p.n_jobs : sms;
     void *args[2] = { (void *)&p, (void *)&lut_floats };
-    e = cudaLaunchKernel(fn, dim3((unsigned)p.n_jobs), dim3(KCF_THREADS), args, bytes, s);
+    e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(KCF_THREADS), args, bytes, s);
     return (int)e;
 }
 
