@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
                 }
             }
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
+            __syncwarp();                                         // every lane has read the old word
             if (lane == 0) s.Zc[c * nWr + w] = word;
         }
         after_step5 = true;

@@ -68,6 +68,7 @@ template <int N, int DIR> __device__ __forceinline__ void fft_pair(float2 (&a)[N
         const float2 dif = cmul_tw<DIR>(make_float2(ox - a[i].x, oy - a[i].y), i, N);   // lane 1: (u - v) w^i, u = partner's point
         a[i] = half ? dif : sum;
     }
+    __syncwarp(mask);       // callers transform shared-memory columns in place: the pair's loads precede either lane's stores
     fft_dif<H, DIR>(a);
 }
 
