@@ -56,12 +56,25 @@ struct MunkresSmem {
     double *mat;            // optional shared-memory copy of the working matrix
     uint32_t *Zc;           // [nC][nWr] zero bitmap, column-major: bit r of word (c, r>>5)
     uint32_t *covR, *covC;  // cover bit masks
+    uint32_t *cand, *candAll; // columns that may hold an UNCOVERED zero (superset) / that hold any zero
     int *starOfRow, *starOfCol, *primeOfRow;
     double *redd;           // [16] reduction scratch
     int *ctrl;              // [4]: 0 = control word, 1 = aug row, 2 = aug col
 };
 
 __device__ __forceinline__ bool tst(const uint32_t *w, int i) { return (w[i >> 5] >> (i & 31)) & 1u; }
+
+// next column >= from that is uncovered and flagged as a candidate, or n if none; executed uniformly by a warp
+__device__ __forceinline__ int next_candidate(const uint32_t *cov, const uint32_t *cand, int from, int n)
+{
+    while (from < n) {
+        const int w = from >> 5;
+        uint32_t bits = ~cov[w] & cand[w] & (0xFFFFFFFFu << (from & 31));
+        if (bits) { const int i = (w << 5) + __ffs(bits) - 1; return i < n ? i : n; }
+        from = (w + 1) << 5;
+    }
+    return n;
+}
 
 // next index >= from whose bit in `mask` is CLEAR (i.e. next uncovered), or n if none; executed uniformly by a warp
 __device__ __forceinline__ int next_clear(const uint32_t *mask, int from, int n)
@@ -91,15 +104,18 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
     const int minDim = nR <= nC ? nR : nC;
     const int nWr = (nR + 31) >> 5, nWc = (nC + 31) >> 5;
     const int md = p.max_dim, mdW = (md + 31) >> 5;
+    const int zs = nWr | 1;                                 // odd row stride of the zero bitmap
 
     MunkresSmem s;
     {
         unsigned char *q = smem_raw;
         s.mat = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)smem_mat_doubles;
         s.redd = reinterpret_cast<double *>(q); q += sizeof(double) * 16;
-        s.Zc = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * (size_t)md * mdW;
+        s.Zc = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * (size_t)md * (mdW | 1);
         s.covR = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
         s.covC = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
+        s.cand = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
+        s.candAll = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
         s.starOfRow = reinterpret_cast<int *>(q); q += sizeof(int) * md;
         s.starOfCol = reinterpret_cast<int *>(q); q += sizeof(int) * md;
         s.primeOfRow = reinterpret_cast<int *>(q); q += sizeof(int) * md;
@@ -134,8 +150,22 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
         const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
         const bool z = (r < nR) && (fabs(d[r + (long)nR * c]) < DBL_EPSILON);
         const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
-        if (lane == 0) s.Zc[c * nWr + w] = word;
+        if (lane == 0) s.Zc[c * zs + w] = word;
     }
+    __syncthreads();
+    // Column filters for step 3: candAll = columns with a zero, cand = columns with a zero in an uncovered row.  While step 3
+    // runs, rows only get covered, so `cand` computed before it stays a superset; it is refreshed after step 5 (new zeros) and
+    // reset to candAll after step 4 (all rows uncovered).  Pure acceleration: the sweep still checks every column it visits.
+    auto refresh_candidates = [&]() {
+        for (int cb = warp * 32; cb < nC; cb += NT) {
+            const int c = cb + lane;
+            uint32_t any = 0, unc = 0;
+            if (c < nC) for (int w = 0; w < nWr; ++w) { const uint32_t z = s.Zc[c * zs + w]; any |= z; unc |= z & ~s.covR[w]; }
+            const uint32_t wa = __ballot_sync(0xFFFFFFFFu, any != 0), wu = __ballot_sync(0xFFFFFFFFu, unc != 0);
+            if (lane == 0) { s.candAll[cb >> 5] = wa; s.cand[cb >> 5] = wu; }
+        }
+    };
+    refresh_candidates();
     __syncthreads();
 
     // greedy initial stars (hungarian.cpp:91-101 / :126-140) -- sequential by nature, one warp
@@ -144,7 +174,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
             for (int r = 0; r < nR; ++r) {
                 for (int cb = 0; cb < nC; cb += 32) {
                     const int c = cb + lane;
-                    const bool ok = (c < nC) && ((s.Zc[c * nWr + (r >> 5)] >> (r & 31)) & 1u) && !tst(s.covC, c);
+                    const bool ok = (c < nC) && ((s.Zc[c * zs + (r >> 5)] >> (r & 31)) & 1u) && !tst(s.covC, c);
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
                     if (bal) {
                         const int cs = cb + __ffs(bal) - 1;
@@ -156,7 +186,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
             }
         } else {
             for (int c = 0; c < nC; ++c) {
-                const uint32_t mw = (lane < nWr) ? (s.Zc[c * nWr + lane] & ~s.covR[lane]) : 0u;
+                const uint32_t mw = (lane < nWr) ? (s.Zc[c * zs + lane] & ~s.covR[lane]) : 0u;
                 const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mw != 0);
                 if (bal) {
                     const int fl = __ffs(bal) - 1;
@@ -191,10 +221,10 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
                 bool zerosFound = true;
                 while (zerosFound && aug_r < 0) {
                     zerosFound = false;
-                    for (int c = next_clear(s.covC, 0, nC); c < nC; c = next_clear(s.covC, c + 1, nC)) {
-                        const uint32_t mw = (lane < nWr) ? (s.Zc[c * nWr + lane] & ~s.covR[lane]) : 0u;
+                    for (int c = next_candidate(s.covC, s.cand, 0, nC); c < nC; c = next_candidate(s.covC, s.cand, c + 1, nC)) {
+                        const uint32_t mw = (lane < nWr) ? (s.Zc[c * zs + lane] & ~s.covR[lane]) : 0u;
                         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mw != 0);
-                        if (!bal) continue;
+                        if (!bal) { if (lane == 0) s.cand[c >> 5] &= ~(1u << (c & 31)); __syncwarp(); continue; }   // stays empty until step 4 / 5
                         const int fl = __ffs(bal) - 1;
                         const int r = (fl << 5) + __ffs(__shfl_sync(0xFFFFFFFFu, mw, fl)) - 1;
                         const int sc = s.starOfRow[r];
@@ -218,7 +248,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
                 }
                 __syncwarp();
                 for (int i = lane; i < nR; i += 32) s.primeOfRow[i] = -1;
-                if (lane < mdW) s.covR[lane] = 0;
+                if (lane < mdW) { s.covR[lane] = 0; s.cand[lane] = s.candAll[lane]; }      // all rows uncovered again
                 // step 2a (hungarian.cpp:193-210): cover every column that holds a star
                 for (int w = lane; w < nWc; w += 32) {
                     uint32_t bits = 0;
@@ -254,7 +284,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
             const bool cc = tst(s.covC, c);
             const uint32_t crw = s.covR[w];
             if (cc && crw == 0) continue;                         // covered column, no covered row in this word: untouched
-            const uint32_t old = s.Zc[c * nWr + w];
+            const uint32_t old = s.Zc[c * zs + w];
             bool z = (old >> lane) & 1u;
             if (r < nR) {
                 const bool rc = (crw >> lane) & 1u;
@@ -268,9 +298,11 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
             }
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
             __syncwarp();                                         // every lane has read the old word
-            if (lane == 0) s.Zc[c * nWr + w] = word;
+            if (lane == 0) s.Zc[c * zs + w] = word;
         }
         after_step5 = true;
+        __syncthreads();
+        refresh_candidates();                                     // new zeros appeared, old ones vanished
         __syncthreads();
     }
 
@@ -288,7 +320,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
 static size_t munkres_smem(int md, int mat_doubles)
 {
     const int mdW = (md + 31) >> 5;
-    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * 16 + sizeof(uint32_t) * ((size_t)md * mdW + 2 * mdW) +
+    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * 16 + sizeof(uint32_t) * ((size_t)md * (mdW | 1) + 4 * mdW) +
            sizeof(int) * (3 * (size_t)md + 4);
 }
 
