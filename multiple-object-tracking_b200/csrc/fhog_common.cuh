@@ -59,29 +59,27 @@ __device__ __forceinline__ float grad_pixel(float gx, float gy, const float *rs_
 }
 
 // ---- the same pixel step with the table indexing folded into a few integer ops (used by the fused kernels) ---------------
-struct LutConsts { int sh_rs; uint32_t mask_rs, flip_rs; int sh_rc; int bin_shift, bin_nseg; };
+struct LutConsts { int sh_rs; uint32_t mask_rs, flip_rs; int sh_rc; int bin_shift, bin_nseg; float rcp_cap; };
 
 __device__ __forceinline__ LutConsts make_lut_consts(const FhogTablesDev &t)
 {
     LutConsts k;
     k.sh_rs = 23 - t.rsqrt_bits; k.mask_rs = (2u << t.rsqrt_bits) - 1u; k.flip_rs = 1u << t.rsqrt_bits;   // [exponent LSB | top mantissa bits], parity of (e - 127)
-    k.sh_rc = 23 - t.rcp_bits; k.bin_shift = t.bin_shift; k.bin_nseg = t.bin_nseg;
+    k.sh_rc = 23 - t.rcp_bits; k.bin_shift = t.bin_shift; k.bin_nseg = t.bin_nseg; k.rcp_cap = t.rcp_cap;
     return k;
 }
 
-__device__ __forceinline__ float grad_pixel_k(float gx, float gy, const float *rs_tab, const float *rc_tab, const uint32_t *bn_tab,
-                                              const LutConsts &k, int *bin_out)
+__device__ __forceinline__ float grad_pixel_k(float gx, float gy, const float2 *rsrc_tab, const uint32_t *bn_tab, const LutConsts &k, int *bin_out)
 {
     const float m2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
-    // rsqrtps: table[parity(e)][top mantissa bits] * 2^-(e >> 1), e = unbiased exponent; (e >> 1) = ((biased + 1) >> 1) - 64
+    // rsqrtps: table[parity(e)][top mantissa bits] * 2^-q, q = e >> 1 = ((biased + 1) >> 1) - 64 (e = unbiased exponent).
+    // rcpps of that value: rcp(T * 2^-q) = rcp(T) * 2^q exactly, and rcp(T) sits next to T in the fused table.
     const uint32_t u = __float_as_uint(m2);
-    const uint32_t T = __float_as_uint(rs_tab[((u >> k.sh_rs) & k.mask_rs) ^ k.flip_rs]);
-    float m = __uint_as_float(T + (64u << 23) - (((u + 0x00800000u) >> 24) << 23));
-    m = (u < 0x00800000u) ? 1e10f : fminf(m, 1e10f);              // rsqrtps(+0 / denormal) = +inf; MIN(., 1e10f)
-    // rcpps: table[top mantissa bits] * 2^-e
-    const uint32_t v = __float_as_uint(m);
-    const uint32_t U = __float_as_uint(rc_tab[(v & 0x7FFFFFu) >> k.sh_rc]);
-    const float M = __uint_as_float(U + (127u << 23) - (v & 0x7F800000u));
+    const float2 tr = rsrc_tab[((u >> k.sh_rs) & k.mask_rs) ^ k.flip_rs];
+    const uint32_t qs = (((u + 0x00800000u) >> 24) - 64u) << 23;
+    float m = __uint_as_float(__float_as_uint(tr.x) - qs);
+    float M = __uint_as_float(__float_as_uint(tr.y) + qs);
+    if (u < 0x00800000u || !(m < 1e10f)) { m = 1e10f; M = k.rcp_cap; }     // rsqrtps(+0 / denormal) = +inf; MIN(., 1e10f)
     float gn = __fmul_rn(__fmul_rn(gx, m), 10000.0f);
     gn = __uint_as_float(__float_as_uint(gn) ^ (__float_as_uint(gy) & 0x80000000u));
     int ai = __float2int_rz(gn) + 10010;

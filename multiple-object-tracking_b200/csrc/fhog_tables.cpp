@@ -121,6 +121,9 @@ void build(FhogTables &t)
                 if (emu_bin(t, i - 10010, s) != want) { t.error = "orientation-bin table self-check failed"; return; }
             }
     }
+    t.rsrc_tab.resize(2 * t.rsqrt_tab.size());
+    for (size_t i = 0; i < t.rsqrt_tab.size(); ++i) { t.rsrc_tab[2 * i] = t.rsqrt_tab[i]; t.rsrc_tab[2 * i + 1] = emu_rcp(t, t.rsqrt_tab[i]); }
+    t.rcp_cap = emu_rcp(t, 1e10f);
     t.ok = true;
 }
 

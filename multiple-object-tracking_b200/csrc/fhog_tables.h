@@ -24,6 +24,10 @@ struct FhogTables {
     // rcp: value for x in [1,2): index = mantissa >> (23 - rcp_bits)
     int rcp_bits = 0;
     std::vector<float> rcp_tab;
+    // fused form for the kernels: rsrc_tab[2i] = rsqrt_tab[i], rsrc_tab[2i+1] = rcp(rsqrt_tab[i]) (both lookups share one index);
+    // rcp_cap = rcp(1e10f), the value taken when MIN(RCPSQRT(M2), 1e10f) saturates (zero gradient)
+    std::vector<float> rsrc_tab;
+    float rcp_cap = 0.f;
     // orientation bin: segment = (idx + 10010) >> bin_shift, entry[sign * nseg + segment] = (thr << 8) | base,
     // bin = base - (idx + 10010 >= thr), then 18 wraps to 0.  idx = (int)(Gx * m * 10000) in [-10010, 10010).
     int bin_shift = 0, bin_nseg = 0;

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     if (tid == 0) { mbar_init(&mbar, 1); mbar_init(&mbar2, 1); }
     __syncthreads();
     const bool lut_smem = lut_floats > 0;
-    const int n_rs = 2 << p.tab.rsqrt_bits, n_rc = 1 << p.tab.rcp_bits, n_bn = (2 * p.tab.bin_nseg + 3) & ~3;
+    const int n_rs = 2 * (2 << p.tab.rsqrt_bits), n_bn = (2 * p.tab.bin_nseg + 3) & ~3;      // floats of the fused {rsqrt, rcp} table; bin entries
     unsigned char *const raw = reinterpret_cast<unsigned char *>(R1 + ((lut_floats + 3) & ~3));
     const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
 
@@ -142,14 +142,10 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, phase ^= 1u) {
     __syncthreads();                                   // the previous job is done with every shared-memory region
     // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
-    const float *rs_tab = p.tab.rsqrt_tab, *rc_tab = p.tab.rcp_tab;
-    const uint32_t *bn_tab = p.tab.bin_tab;
-    if (lut_smem) { rs_tab = R1; rc_tab = R1 + n_rs; bn_tab = reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc; }
     if (tid < 3) {
         // SSE tables -> shared memory (one arrival on mbar per job)
-        if (tid == 0) { mbar_expect_tx(&mbar, lut_smem ? (uint32_t)(n_rs + n_rc + n_bn) * 4u : 0u); if (lut_smem) bulk_g2s(R1, p.tab.rsqrt_tab, n_rs * 4, &mbar); }
-        if (tid == 1 && lut_smem) bulk_g2s(R1 + n_rs, p.tab.rcp_tab, n_rc * 4, &mbar);
-        if (tid == 2 && lut_smem) bulk_g2s(R1 + n_rs + n_rc, p.tab.bin_tab, n_bn * 4, &mbar);
+        if (tid == 0) { mbar_expect_tx(&mbar, lut_smem ? (uint32_t)(n_rs + n_bn) * 4u : 0u); if (lut_smem) bulk_g2s(R1, p.tab.rsrc_tab, n_rs * 4, &mbar); }
+        if (tid == 1 && lut_smem) bulk_g2s(R1 + n_rs, p.tab.bin_tab, n_bn * 4, &mbar);
     }
 
     const int slot = p.slots[job];
@@ -248,7 +244,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     unsigned char bnr[G::PIX_PER_THREAD];
     {
         const LutConsts lk = make_lut_consts(p.tab);
-        auto p1_pixels = [&](const float *rs, const float *rc, const uint32_t *bn) {
+        auto p1_pixels = [&](const float2 *rsrc, const uint32_t *bn) {
 #pragma unroll
             for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
                 const int idx = tid + q * NT;
@@ -261,13 +257,13 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                     const float gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), rx);
                     const float gy = __fmul_rn(__fsub_rn(g[1], g[-1]), ry);
                     int bb;
-                    m0r[q] = grad_pixel_k(gx, gy, rs, rc, bn, lk, &bb);
+                    m0r[q] = grad_pixel_k(gx, gy, rsrc, bn, lk, &bb);
                     bnr[q] = (unsigned char)bb;
                 }
             }
         };
-        if (lut_smem) p1_pixels(R1, R1 + n_rs, reinterpret_cast<const uint32_t *>(R1) + n_rs + n_rc);   // shared-memory tables (LDS)
-        else p1_pixels(p.tab.rsqrt_tab, p.tab.rcp_tab, p.tab.bin_tab);                                   // oversized tables stay in global memory
+        if (lut_smem) p1_pixels(reinterpret_cast<const float2 *>(R1), reinterpret_cast<const uint32_t *>(R1) + n_rs);   // shared-memory tables (LDS)
+        else p1_pixels(p.tab.rsrc_tab, p.tab.bin_tab);                                                                // oversized tables stay in global memory
     }
     __syncthreads();
     // (M0, bin) overwrite the gray patch in a zero-bordered layout de-interleaved along y, [x+2][(y+2)&3][(y+2)>>2], so
@@ -668,7 +664,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 template <int HR, int WC> int kcf_launch_size(int mode, const KcfLaunch &p, cudaStream_t s)
 {
     const FhogTablesDev &t = p.tab;
-    int lut_floats = (2 << t.rsqrt_bits) + (1 << t.rcp_bits) + ((2 * t.bin_nseg + 3) & ~3);
+    int lut_floats = 2 * (2 << t.rsqrt_bits) + ((2 * t.bin_nseg + 3) & ~3);      // fused {rsqrt, rcp} table + bin step table
     if (lut_floats > 8192) lut_floats = 0;                                      // too large: read the tables from global memory
     const size_t bytes = smem_bytes<HR, WC>(lut_floats);
     const bool dump = p.dump.gray != nullptr;

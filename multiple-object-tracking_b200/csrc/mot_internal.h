@@ -36,6 +36,8 @@ struct FhogTablesDev {
     const float *rsqrt_tab; int rsqrt_bits;
     const float *rcp_tab; int rcp_bits;
     const uint32_t *bin_tab; int bin_shift, bin_nseg;
+    const float2 *rsrc_tab;           // {rsqrt_tab[i], rcp(rsqrt_tab[i])}: one look-up serves RCPSQRT and RCP
+    float rcp_cap;                    // rcp(1e10f)
 };
 
 // Optional stage dumps (all may be null).  Index = job * stride of that stage.
