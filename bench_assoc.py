@@ -113,6 +113,28 @@ def config2(args):
     for t in tds:
         t.close()
     ctx.close()
+    # device-resident loop (mot_tdd_*): detections resident too, five launches per frame, one sync at the very end
+    import torch
+    for ns2, key in ((1, "device_resident_1_stream"), (64, "device_resident_64_streams")):
+        ctx = M.Context(W, H, max_tracks=ns2 * 128, kind=M.TRACKER_KALMAN)
+        loop = M.DeviceLoop(ctx, ns2, cap=128, max_det=64, cost_mode=0)
+        dev = torch.device("cuda", 0)
+        dd_dev = []
+        for f in range(fr2):
+            buf = np.zeros((ns2, 64), M.BBOX_DTYPE)
+            for s_ in range(ns2):
+                buf[s_, :len(dd[f][s_])] = dd[f][s_]
+            dd_dev.append(torch.from_numpy(buf.view(np.uint8).reshape(ns2, 64 * 24)).to(dev))
+        nd_dev = torch.full((ns2,), 64, dtype=torch.int32, device=dev)
+        loop.step_dev(dd_dev[0].data_ptr(), nd_dev.data_ptr()); ctx.sync()
+        reps = 5
+        t0 = time.perf_counter()
+        for rep in range(reps):
+            for f in range(1, fr2):
+                loop.step_dev(dd_dev[f].data_ptr(), nd_dev.data_ptr())
+        ctx.sync()
+        out[key] = {"gpu_stream_frames_per_s": ns2 * reps * (fr2 - 1) / (time.perf_counter() - t0)}
+        loop.close(); ctx.close()
     return {"config": "C2: Kalman + Hungarian, 64 tracks x 64 detections, one 1080p stream, %d frames (host-array frame loop, one sync per stage)" % frames, **out}
 
 

@@ -131,6 +131,21 @@ int mot_td_ntracks(mot_td_t *td);
 void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *vis, int *invis);
 int mot_td_last(mot_td_t *td, mot_bbox_t *predicted, int *assigned_trackers);
 
+/* ---- the same frame loop with the track tables resident on the DEVICE (Kalman kind): five launches per frame for all
+ *      streams, no host synchronisation (replaces top/td.cpp:343-644 including the bookkeeping,
+ *      the stable compaction of lost tracks :585-609 and the spawn order :612-644) --------------------------------- */
+typedef struct mot_tdd_s mot_tdd_t;
+/* n_streams independent streams, at most cap tracks (reference: 256, top/td.cpp:12) and max_det detections
+ * (reference: 128, top/cnntype.h:46) each, both <= 1024.  The context must be a Kalman context with >= n_streams*cap slots. */
+int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *ctx, int n_streams, int cap, int max_det, int cost_mode);
+void mot_tdd_destroy(mot_tdd_t *tdd);
+/* detections already on the device: d_dets[n_streams][max_det], d_ndet[n_streams]; asynchronous on the context stream */
+int mot_tdd_step_dev(mot_tdd_t *tdd, const mot_bbox_t *d_dets, const int *d_ndet);
+/* detections in host arrays (dets[s] points at ndet[s] boxes); staged, uploaded and stepped; asynchronous */
+int mot_tdd_step(mot_tdd_t *tdd, const mot_bbox_t *const *dets, const int *ndet);
+/* snapshot of stream s (synchronises); returns the number of live tracks or a negative error */
+int mot_tdd_read(mot_tdd_t *tdd, int stream, uint32_t *tid, mot_bbox_t *boxes, int *age, int *vis, int *invis);
+
 /* ---- test hooks: stage dumps of the fused KCF kernel ------------------------------------------------------- */
 /* Stages: 0 gray | 1 m0 | 2 bin(int) | 3 r1 | 4 norm | 5 feat(xf_tm) | 6 spec(xf_fq, float pairs) | 7 zf | 8 response |
  *         9 kf | 10 peak(int x2) | 11 margin(float x2).  Enable before a predict/update of ONE track, then fetch. */

@@ -53,6 +53,7 @@ __global__ void kalman_predict_kernel(KalmanState st, int n, const int *slots, m
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int s = slots[i];
+    if (s < 0) return;                         // inactive entry of a device-resident track table
     double x[6], P[6][6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) x[k] = st.x[(long)k * st.cap + s];
@@ -100,6 +101,7 @@ __global__ void kalman_update_kernel(KalmanState st, int n, const int *slots, co
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int s = slots[i];
+    if (s < 0) return;
     double x[6], P[6][6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) x[k] = st.x[(long)k * st.cap + s];

@@ -1,10 +1,8 @@
 // mot_capi.cu -- the C ABI declared in include/mot_b200.h: context, frames, tracker slots, batched launches.
 // Host-side only bookkeeping; every numeric step of the hot path runs in the CUDA kernels of this directory.
 // There is deliberately NO CPU fallback: a missing device, a failed launch or an unsupported shape is an error.
-#include "mot_internal.h"
+#include "mot_ctx.h"
 #include "fhog_tables.h"
-#include "kalman.h"
-#include "assoc.h"
 
 #include <algorithm>
 #include <cmath>
@@ -18,83 +16,14 @@
 using namespace mot;
 
 static thread_local std::string g_err;
-static int fail(int code, const char *fmt, ...)
+int mot_fail(int code, const char *fmt, ...)
 {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
     g_err = buf;
     return code;
 }
-#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(MOT_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
-
-namespace {
-
-struct SizeClass { int hr, wc, live; bool fast; float *d_wy, *d_wx, *d_yf; double2 *d_twh, *d_tww; float norm; };
-
-template <class T> struct DevBuf {
-    T *p = nullptr; size_t n = 0;
-    cudaError_t ensure(size_t want) {
-        if (want <= n) return cudaSuccess;
-        if (p) cudaFree(p);
-        n = std::max(want, n * 2);
-        return cudaMalloc(&p, sizeof(T) * n);
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-};
-template <class T> struct PinBuf {
-    T *p = nullptr; size_t n = 0;
-    cudaError_t ensure(size_t want) {
-        if (want <= n) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        n = std::max(want, n * 2);
-        return cudaMallocHost(&p, sizeof(T) * n);
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
-};
-
-}  // namespace
-
-struct mot_ctx_s {
-    int device = 0, W = 0, H = 0, max_tracks = 0, n_frames = 0, kind = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t copy_stream = nullptr;   // frame uploads run here so that they overlap with kernels of the compute stream
-    std::vector<cudaEvent_t> slot_uploaded;   // per frame slot: recorded after its last upload
-    std::vector<char> slot_pending;           // an upload of this slot has not been waited for by the compute stream yet
-    long launches = 0;
-    // frames
-    std::vector<uint8_t *> frame_owned;
-    std::vector<const uint8_t *> frame_ptr_h;
-    const uint8_t **d_frame_ptr = nullptr;
-    bool frame_ptr_dirty = true;
-    int frame_stride = 0;
-    // track slots
-    std::vector<int> free_slots;
-    std::vector<char> used;
-    std::vector<KcfMeta> meta_h;          // host mirror of the immutable part (rows, cols, hr, wc, size_class)
-    KcfMeta *d_meta = nullptr;
-    float2 *d_model = nullptr; long model_stride = 0;
-    float *d_alpha = nullptr; long alpha_stride = 0;
-    std::vector<SizeClass> classes;
-    KcfClassDev *d_classes = nullptr;
-    FhogTablesDev tab{};
-    float *d_tab_rsqrt = nullptr, *d_tab_rcp = nullptr, *d_tab_rsrc = nullptr; uint32_t *d_tab_bin = nullptr;
-    KalmanState kal{};
-    // staging
-    DevBuf<int> d_slots, d_frames, d_TD, d_assign;
-    DevBuf<mot_bbox_t> d_boxes, d_trk, d_det;
-    DevBuf<KcfMeta> d_meta_stage;
-    DevBuf<float> d_gray;
-    DevBuf<char> d_scratch;               // per-job intermediates of the any-size KCF path
-    DevBuf<double> d_dist, d_work, d_cost;
-    PinBuf<int> h_slots, h_frames, h_TD, h_assign;
-    PinBuf<mot_bbox_t> h_boxes, h_trk, h_det;
-    PinBuf<KcfMeta> h_meta_stage;
-    PinBuf<double> h_dist, h_cost;
-    // dumps
-    bool dumps = false;
-    KcfDump dump{};
-    int dump_hr = 0, dump_wc = 0, dump_rows = 0, dump_cols = 0;
-};
+#define fail mot_fail
 
 static constexpr int MAX_CLASSES = 1024;
 static constexpr long DUMP_NB_MAX = 4096;       // stage dumps (test hook) are available for windows up to 64x64 cells

@@ -1,0 +1,222 @@
+// td_device.cu -- the frame loop of the reference with the track table RESIDENT ON THE DEVICE (Kalman tracker kind).
+//
+// One iteration of pthread_mtcnn_trkn (top/td.cpp:343-644) for S independent streams is five launches and no host
+// synchronisation: kalman_predict (+clamp, :344-384) -> cost matrices + Munkres (:386-470) -> td_scatter (:472-547,
+// :550-556 bookkeeping) -> kalman_update (:539, :581) -> td_lifecycle (delete lost with stable compaction :585-609, spawn
+// per unassigned detection in ascending order :612-644).  The bookkeeping, the order of the track table and the ids are
+// the reference's, per stream; host/td_loop.cpp is the same loop with the table on the host.
+// Stream s owns the Kalman slots [s*cap, (s+1)*cap).
+#include "mot_ctx.h"
+
+namespace mot {
+
+struct TddState {
+    int S, cap, max_det;
+    int *ntracks; uint32_t *tracker_id;          // [S]
+    uint32_t *tid; int *slot, *age, *vis, *invis; mot_bbox_t *bbox;      // [S][cap]; slot = -1 beyond ntracks
+    int *assign;                                 // [S][md] rows of the cost matrix -> column
+    int *assigned_detected;                      // [S][max_det]
+    int md;
+};
+
+// scatter of the assignment + bookkeeping of assigned / unassigned tracks (top/td.cpp:472-502, 512-556)
+__global__ void td_scatter_kernel(TddState st, const mot_bbox_t *dets, const int *ndet)
+{
+    const int s = blockIdx.x, T = st.ntracks[s], D = ndet[s];
+    __shared__ int at[1024];
+    for (int i = threadIdx.x; i < T; i += blockDim.x) at[i] = -1;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) st.assigned_detected[(long)s * st.max_det + j] = -1;
+    __syncthreads();
+    if (T && D) {
+        const int *a = st.assign + (long)s * st.md;
+        if (T < D) { for (int i = threadIdx.x; i < T; i += blockDim.x) { const int j = a[i]; at[i] = j; if (j >= 0) st.assigned_detected[(long)s * st.max_det + j] = i; } }
+        else       { for (int j = threadIdx.x; j < D; j += blockDim.x) { const int i = a[j]; if (i >= 0) at[i] = j; st.assigned_detected[(long)s * st.max_det + j] = i; } }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const long o = (long)s * st.cap + i;
+        const int j = at[i];
+        if (j >= 0) { st.bbox[o] = dets[(long)s * st.max_det + j]; st.vis[o]++; st.age[o]++; st.invis[o] = 0; }     // :541-546
+        else        { st.age[o]++; st.invis[o]++; }                                                               // :555-556
+    }
+}
+
+// delete lost tracks with stable compaction (top/td.cpp:585-609), then spawn (top/td.cpp:612-644)
+__global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox_t *dets, const int *ndet)
+{
+    const int s = blockIdx.x, T = st.ntracks[s], D = ndet[s], cap = st.cap, tid = threadIdx.x, NTH = blockDim.x;
+    extern __shared__ int sm[];
+    int *pos = sm;                    // [cap] new position of a kept track / [max_det] rank of a spawning detection
+    int *freeid = sm + 1024;          // [cap] free local slot ids in ascending order
+    __shared__ int total, nfree;
+    // ---- keep flags + exclusive scan (a single thread: tables are a few hundred entries) -------------------------------
+    if (tid == 0) {
+        int n = 0;
+        for (int i = 0; i < T; ++i) {
+            const long o = (long)s * cap + i;
+            const bool lost = ((st.age[o] < 10) && (st.vis[o] * 5 < 3 * st.age[o])) || (st.invis[o] >= 20);    // :587-590
+            pos[i] = lost ? -1 : n;
+            if (!lost) ++n;
+        }
+        total = n;
+    }
+    __syncthreads();
+    // stable compaction through registers
+    uint32_t r_tid[4]; int r_slot[4], r_age[4], r_vis[4], r_inv[4]; mot_bbox_t r_box[4]; int r_pos[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = tid + q * NTH; r_pos[q] = -1;
+        if (i < T) { const long o = (long)s * cap + i; r_pos[q] = pos[i]; r_tid[q] = st.tid[o]; r_slot[q] = st.slot[o]; r_age[q] = st.age[o]; r_vis[q] = st.vis[o]; r_inv[q] = st.invis[o]; r_box[q] = st.bbox[o]; }
+    }
+    __syncthreads();
+    const int n2 = total;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (r_pos[q] >= 0) { const long o = (long)s * cap + r_pos[q]; st.tid[o] = r_tid[q]; st.slot[o] = r_slot[q]; st.age[o] = r_age[q]; st.vis[o] = r_vis[q]; st.invis[o] = r_inv[q]; st.bbox[o] = r_box[q]; }
+    }
+    for (int i = n2 + tid; i < T; i += NTH) st.slot[(long)s * cap + i] = -1;
+    __syncthreads();
+    // ---- free local slot ids (ascending) + ranks of the spawning detections ------------------------------------------------
+    if (tid == 0) {
+        // cap <= 1024 -> 32-word bitmap on the stack
+        uint32_t used[32];
+        for (int w = 0; w < 32; ++w) used[w] = 0;
+        for (int i = 0; i < n2; ++i) { const int ls = st.slot[(long)s * cap + i] - s * cap; used[ls >> 5] |= 1u << (ls & 31); }
+        int nf = 0;
+        for (int ls = 0; ls < cap; ++ls) if (!((used[ls >> 5] >> (ls & 31)) & 1u)) freeid[nf++] = ls;
+        nfree = nf;
+        int rk = 0;
+        for (int j = 0; j < D; ++j) { const bool un = st.assigned_detected[(long)s * st.max_det + j] < 0; pos[j] = (un && n2 + rk < cap) ? rk : -1; if (un && n2 + rk < cap) ++rk; }
+        total = rk;
+    }
+    __syncthreads();
+    const int spawned = total;
+    const uint32_t id0 = st.tracker_id[s];
+    for (int j = tid; j < D; j += NTH) {
+        const int rk = pos[j];
+        if (rk < 0) continue;
+        const long o = (long)s * cap + n2 + rk;
+        const mot_bbox_t b = dets[(long)s * st.max_det + j];
+        const int sl = s * cap + freeid[rk];
+        st.tid[o] = id0 + (uint32_t)rk; st.slot[o] = sl; st.age[o] = 0; st.vis[o] = 0; st.invis[o] = 0; st.bbox[o] = b;      // :618-627
+        // tracker_new, trackers/kalman.cpp:147-163: x0 = [l,t,r,b,0,0], P0 = 1e4 I
+        const double x0[6] = { (double)b.l, (double)b.t, (double)b.r, (double)b.b, 0.0, 0.0 };
+        for (int k = 0; k < 6; ++k) kal.x[(long)k * kal.cap + sl] = x0[k];
+        for (int c = 0; c < 6; ++c) for (int r = 0; r < 6; ++r) kal.P[(long)(c * 6 + r) * kal.cap + sl] = (r == c) ? 1e4 : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) { st.ntracks[s] = n2 + spawned; st.tracker_id[s] = id0 + (uint32_t)spawned; }
+}
+
+}  // namespace mot
+
+using namespace mot;
+
+struct mot_tdd_s {
+    mot_ctx_t *ctx;
+    TddState st;
+    int cost_mode;
+    double *d_dist, *d_cost;
+    DevBuf<mot_bbox_t> d_dets; DevBuf<int> d_ndet;
+    PinBuf<mot_bbox_t> h_dets; PinBuf<int> h_ndet;
+};
+
+extern "C" {
+
+int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int max_det, int cost_mode)
+{
+    if (!out || !c || n_streams <= 0 || cap <= 0 || cap > 1024 || max_det <= 0 || max_det > 1024) return mot_fail(MOT_ERR_ARG, "mot_tdd_create: bad argument (cap and max_det must be in 1..1024)");
+    if (c->kind != MOT_TRACKER_KALMAN) return mot_fail(MOT_ERR_KIND, "the device-resident frame loop is available for Kalman contexts");
+    if ((long)n_streams * cap > c->max_tracks) return mot_fail(MOT_ERR_CAPACITY, "context has %d track slots, %d streams x %d are needed", c->max_tracks, n_streams, cap);
+    for (char u : c->used) if (u) return mot_fail(MOT_ERR_ARG, "the context already holds host-managed trackers");
+    CU(cudaSetDevice(c->device));
+    mot_tdd_t *t = new mot_tdd_s();
+    t->ctx = c; t->cost_mode = cost_mode;
+    TddState &st = t->st;
+    st.S = n_streams; st.cap = cap; st.max_det = max_det; st.md = cap > max_det ? cap : max_det;
+    const size_t n = (size_t)n_streams * cap;
+    CU(cudaMalloc(&st.ntracks, sizeof(int) * n_streams)); CU(cudaMalloc(&st.tracker_id, sizeof(uint32_t) * n_streams));
+    CU(cudaMalloc(&st.tid, sizeof(uint32_t) * n)); CU(cudaMalloc(&st.slot, sizeof(int) * n)); CU(cudaMalloc(&st.age, sizeof(int) * n));
+    CU(cudaMalloc(&st.vis, sizeof(int) * n)); CU(cudaMalloc(&st.invis, sizeof(int) * n)); CU(cudaMalloc(&st.bbox, sizeof(mot_bbox_t) * n));
+    CU(cudaMalloc(&st.assign, sizeof(int) * (size_t)n_streams * st.md)); CU(cudaMalloc(&st.assigned_detected, sizeof(int) * (size_t)n_streams * max_det));
+    CU(cudaMalloc(&t->d_dist, sizeof(double) * (size_t)n_streams * st.md * st.md)); CU(cudaMalloc(&t->d_cost, sizeof(double) * n_streams));
+    CU(cudaMemsetAsync(st.ntracks, 0, sizeof(int) * n_streams, c->stream)); CU(cudaMemsetAsync(st.tracker_id, 0, sizeof(uint32_t) * n_streams, c->stream));
+    CU(cudaMemsetAsync(st.slot, 0xFF, sizeof(int) * n, c->stream));
+    CU(cudaMemsetAsync(st.age, 0, sizeof(int) * n, c->stream)); CU(cudaMemsetAsync(st.vis, 0, sizeof(int) * n, c->stream)); CU(cudaMemsetAsync(st.invis, 0, sizeof(int) * n, c->stream));
+    CU(cudaMemsetAsync(st.bbox, 0, sizeof(mot_bbox_t) * n, c->stream)); CU(cudaMemsetAsync(st.tid, 0, sizeof(uint32_t) * n, c->stream));
+    for (long i = 0; i < (long)n_streams * cap; ++i) c->used[i] = 1;        // these slots now belong to the device-side tables
+    c->free_slots.erase(std::remove_if(c->free_slots.begin(), c->free_slots.end(), [&](int s) { return s < n_streams * cap; }), c->free_slots.end());
+    *out = t;
+    return 0;
+}
+
+void mot_tdd_destroy(mot_tdd_t *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->stream);
+    TddState &st = t->st;
+    cudaFree(st.ntracks); cudaFree(st.tracker_id); cudaFree(st.tid); cudaFree(st.slot); cudaFree(st.age); cudaFree(st.vis); cudaFree(st.invis);
+    cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost);
+    t->d_dets.release(); t->d_ndet.release(); t->h_dets.release(); t->h_ndet.release();
+    for (long i = 0; i < (long)st.S * st.cap; ++i) { t->ctx->used[i] = 0; t->ctx->free_slots.push_back((int)i); }
+    delete t;
+}
+
+/* detections: device arrays dets[S][max_det], ndet[S]; everything is enqueued on the context stream, nothing synchronises */
+int mot_tdd_step_dev(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet)
+{
+    if (!t || !d_dets || !d_ndet) return mot_fail(MOT_ERR_ARG, "mot_tdd_step_dev: null argument");
+    mot_ctx_t *c = t->ctx; TddState &st = t->st;
+    CU(cudaSetDevice(c->device));
+    const int n = st.S * st.cap;
+    int rc = kalman_predict(c->kal, n, st.slot, st.bbox, 1, c->W, c->H, c->stream);
+    if (rc) return mot_fail(MOT_ERR_CUDA, "kalman_predict launch failed (%d)", rc);
+    rc = mot_associate_batch_dev(c, st.S, st.ntracks, d_ndet, st.bbox, st.cap, d_dets, st.max_det, t->cost_mode,
+                                 t->d_dist, (long)st.md * st.md, st.assign, st.md, t->d_cost, st.md);
+    if (rc) return rc;
+    td_scatter_kernel<<<st.S, 256, 0, c->stream>>>(st, d_dets, d_ndet);
+    rc = kalman_update(c->kal, n, st.slot, st.bbox, c->stream);
+    if (rc) return mot_fail(MOT_ERR_CUDA, "kalman_update launch failed (%d)", rc);
+    td_lifecycle_kernel<<<st.S, 256, sizeof(int) * 2048, c->stream>>>(st, c->kal, d_dets, d_ndet);
+    CU(cudaGetLastError());
+    c->launches += 4;           // predict, scatter, update, lifecycle (+2 counted by the association call)
+    return 0;
+}
+
+/* host-array convenience: detections of every stream are staged and uploaded, then mot_tdd_step_dev; asynchronous */
+int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
+{
+    if (!t || !dets || !ndet) return mot_fail(MOT_ERR_ARG, "mot_tdd_step: null argument");
+    mot_ctx_t *c = t->ctx; TddState &st = t->st;
+    CU(cudaSetDevice(c->device));
+    CU(t->h_dets.ensure((size_t)st.S * st.max_det)); CU(t->d_dets.ensure((size_t)st.S * st.max_det)); CU(t->h_ndet.ensure(st.S)); CU(t->d_ndet.ensure(st.S));
+    CU(cudaStreamSynchronize(c->stream));        // the staging buffers of the previous step have been consumed
+    for (int s = 0; s < st.S; ++s) {
+        if (ndet[s] < 0 || ndet[s] > st.max_det) return mot_fail(MOT_ERR_ARG, "stream %d has %d detections (max %d)", s, ndet[s], st.max_det);
+        t->h_ndet.p[s] = ndet[s];
+        if (ndet[s]) memcpy(t->h_dets.p + (size_t)s * st.max_det, dets[s], sizeof(mot_bbox_t) * ndet[s]);
+    }
+    CU(cudaMemcpyAsync(t->d_dets.p, t->h_dets.p, sizeof(mot_bbox_t) * (size_t)st.S * st.max_det, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(t->d_ndet.p, t->h_ndet.p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream));
+    return mot_tdd_step_dev(t, t->d_dets.p, t->d_ndet.p);
+}
+
+/* snapshot of one stream's track table (synchronises); returns the number of tracks */
+int mot_tdd_read(mot_tdd_t *t, int s, uint32_t *tid, mot_bbox_t *boxes, int *age, int *vis, int *invis)
+{
+    if (!t || s < 0 || s >= t->st.S) return mot_fail(MOT_ERR_ARG, "mot_tdd_read: bad argument");
+    mot_ctx_t *c = t->ctx; TddState &st = t->st;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    int n = 0;
+    CU(cudaMemcpy(&n, st.ntracks + s, sizeof(int), cudaMemcpyDeviceToHost));
+    const long o = (long)s * st.cap;
+    if (tid) CU(cudaMemcpy(tid, st.tid + o, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    if (boxes) CU(cudaMemcpy(boxes, st.bbox + o, sizeof(mot_bbox_t) * n, cudaMemcpyDeviceToHost));
+    if (age) CU(cudaMemcpy(age, st.age + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (vis) CU(cudaMemcpy(vis, st.vis + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (invis) CU(cudaMemcpy(invis, st.invis + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+}  // extern "C"

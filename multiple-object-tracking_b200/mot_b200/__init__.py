@@ -24,6 +24,7 @@ EXPORTS = [
     "mot_predict_batch", "mot_update_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
     "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_get", "mot_td_last",
+    "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_read",
     "mot_debug_enable_dumps", "mot_debug_fetch", "mot_debug_state", "mot_debug_tables",
 ]
 
@@ -82,6 +83,11 @@ def lib():
             "mot_td_ntracks": [C.c_void_p],
             "mot_td_get": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
             "mot_td_last": [C.c_void_p, C.c_void_p, C.c_void_p],
+            "mot_tdd_create": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int],
+            "mot_tdd_destroy": [C.c_void_p],
+            "mot_tdd_step_dev": [C.c_void_p, C.c_void_p, C.c_void_p],
+            "mot_tdd_step": [C.c_void_p, C.c_void_p, C.c_void_p],
+            "mot_tdd_read": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         }.items():
             getattr(L, name).argtypes = types
         _lib = L
@@ -240,6 +246,38 @@ class Context:
 
     def td(self, frame_slot=0, cap=256, cost_mode=COST_REF_CENTROID):
         return TdLoop(self, frame_slot, cap, cost_mode)
+
+
+class DeviceLoop:
+    """mot_tdd_*: the frame loop with the track tables resident on the device (Kalman contexts)."""
+
+    def __init__(self, ctx, n_streams, cap=256, max_det=128, cost_mode=COST_REF_CENTROID):
+        self.ctx, self.n, self.cap = ctx, n_streams, cap
+        h = C.c_void_p()
+        _chk(lib().mot_tdd_create(C.byref(h), ctx.h, n_streams, cap, max_det, cost_mode))
+        self.h = h
+
+    def step(self, dets):
+        dl = [_boxes(d) for d in dets]
+        arr = (C.c_void_p * self.n)(*[d.ctypes.data if len(d) else None for d in dl])
+        nd = np.array([len(d) for d in dl], np.int32)
+        _chk(lib().mot_tdd_step(self.h, arr, _p(nd)))
+
+    def step_dev(self, d_dets, d_ndet):
+        _chk(lib().mot_tdd_step_dev(self.h, C.c_void_p(d_dets), C.c_void_p(d_ndet)))
+
+    def tracks(self, s):
+        tid = np.zeros(self.cap, np.uint32); boxes = np.zeros(self.cap, BBOX_DTYPE)
+        age = np.zeros(self.cap, np.int32); vis = np.zeros(self.cap, np.int32); inv = np.zeros(self.cap, np.int32)
+        n = lib().mot_tdd_read(self.h, s, _p(tid), _p(boxes), _p(age), _p(vis), _p(inv))
+        if n < 0:
+            _chk(n)
+        return dict(tid=tid[:n], boxes=boxes[:n], age=age[:n], vis=vis[:n], inv=inv[:n])
+
+    def close(self):
+        if self.h:
+            lib().mot_tdd_destroy(self.h)
+            self.h = None
 
 
 class TdLoop:

@@ -90,3 +90,42 @@ def test_multi_stream_lockstep_equals_single(oracle):
     for r in refs:
         r.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_device_resident_loop_trace(oracle, mode):
+    """mot_tdd_*: track tables, bookkeeping, stable compaction and spawn on the device; five launches per frame, no host
+    sync.  Trace-identical to the oracle's loop for several streams at once, through births, misses and deaths."""
+    require_gpu()
+    M = mot()
+    W, H, ns, cap = 1280, 720, 5, 48
+    scs = [Scene(400 + 3 * s + mode, W, H, 20, tsize=40, win=64) for s in range(ns)]
+    ctx = M.Context(W, H, max_tracks=ns * cap, kind=M.TRACKER_KALMAN)
+    loop = M.DeviceLoop(ctx, ns, cap=cap, max_det=64, cost_mode=mode)
+    refs = [oracle.td_new("kal", W, H, cap, mode) for _ in range(ns)]
+    drng = np.random.default_rng(17)
+    for f in range(70):
+        dets = []
+        for s, sc in enumerate(scs):
+            sc.step()
+            d = sc.windows(jitter=2)
+            keep = drng.random(len(d)) > (0.5 if 20 <= f < 45 and s % 2 == 0 else 0.1)     # a long drought kills tracks on even streams
+            d = np.ascontiguousarray(d[keep])
+            if f % 5 == 2:
+                fp = d[:2].copy(); fp["l"] = (fp["l"] + 333) % (W - 80); fp["r"] = fp["l"] + 63
+                d = np.ascontiguousarray(np.concatenate([d, fp]))
+            if f == 30 and s == 1:
+                d = d[:0]                                                           # a frame without detections
+            dets.append(d)
+        loop.step(dets)
+        for s in range(ns):
+            refs[s].step(None, dets[s])
+        if f % 3 == 0 or f > 60:
+            for s in range(ns):
+                a, b = loop.tracks(s), refs[s].tracks()
+                for k in a:
+                    assert np.array_equal(a[k], b[k]), (f, s, k)
+    loop.close()
+    for r in refs:
+        r.close()
+    ctx.close()
