@@ -277,9 +277,10 @@ def run_b200(args):
             hb = ctx2.predict(h2, fs2[k & 1], hb, clamp=1)
             ctx2.update(h2, fs2[k & 1], hb)
 
-        upload(0)
+        upload(0); upload(1)                 # both slot sets exist (the first upload of a slot allocates it)
         ctx2.sync()
         t0 = time.perf_counter(); upload(1); ctx2.sync(); h2d_s = time.perf_counter() - t0      # PCIe alone, for context
+        upload(0)
         for k in range(2):
             e2e_step(k)
         ctx2.sync(); barrier()

@@ -73,6 +73,8 @@ def main():
             key = "pre/other"
             if line and line[0] == "fft_reg.cuh":
                 key = "fft_reg"
+            elif line and line[0] == "fhog_common.cuh":
+                key = "P0" if line[1] < 22 else "P1"                     # bgr_gray / grad_pixel_k
             elif line and line[0] == "kcf_fused.cuh":
                 for ln, nm in marks:
                     if line[1] >= ln:
