@@ -149,3 +149,38 @@ def test_many_tracks_one_launch_equals_per_track_oracle(oracle):
         assert tuple(int(out[i][k]) for k in "ltbr") == want, i
         oracle.kcf_delete(oh)
     ctx.close()
+
+
+def test_reference_plugin_signatures_through_the_shim(oracle):
+    """host/tracker_shim.cpp: the reference's own per-object entry points (tracker_new/predict/update/delete with a HOST gray
+    patch, assignmentoptimal with a host matrix) running on the GPU, compared call by call with the oracle."""
+    require_gpu()
+    import ctypes as C
+    M = mot()
+    L = M.lib()
+    L.mot_shim_tracker_new.restype = C.c_void_p
+    for kind in (M.TRACKER_KCF, M.TRACKER_KALMAN):
+        assert L.mot_shim_configure(kind, 640, 480, 16) == 0, L.mot_last_error()
+        rng = np.random.default_rng(4)
+        img = (rng.random((60, 80)).repeat(8, 0).repeat(8, 1) * 200).astype(np.float32)
+        b = BBox(96, 64, 64 + 63, 96 + 63, 1, 1.0); ob = BBox.from_buffer_copy(b)
+        h = C.c_void_p(L.mot_shim_tracker_new(C.byref(b)))
+        assert h.value
+        oh = oracle.kcf_new(ob) if kind == M.TRACKER_KCF else oracle.kal_new(ob)
+        for step in range(4):
+            g = np.asfortranarray(img[b.t:b.b + 1, b.l:b.r + 1])
+            og = np.asfortranarray(img[ob.t:ob.b + 1, ob.l:ob.r + 1])
+            L.mot_shim_tracker_update(h, g.ctypes.data_as(C.c_void_p), C.byref(b))
+            (oracle.kcf_update(oh, og, ob) if kind == M.TRACKER_KCF else oracle.kal_update(oh, ob))
+            img = np.roll(img, (4, -4), (0, 1))
+            g = np.asfortranarray(img[b.t:b.b + 1, b.l:b.r + 1]); og = np.asfortranarray(img[ob.t:ob.b + 1, ob.l:ob.r + 1])
+            L.mot_shim_tracker_predict(h, g.ctypes.data_as(C.c_void_p), C.byref(b))
+            (oracle.kcf_predict(oh, og, ob) if kind == M.TRACKER_KCF else oracle.kal_predict(oh, ob))
+            assert b.tup() == ob.tup(), (kind, step)
+        L.mot_shim_tracker_delete(h)
+        (oracle.kcf_delete(oh) if kind == M.TRACKER_KCF else oracle.kal_delete(oh))
+    d = np.asfortranarray(np.round(rng.random((23, 31)), 2))
+    a = np.full(23, -5, np.int32); cost = C.c_double()
+    L.mot_shim_assignmentoptimal(a.ctypes.data_as(C.c_void_p), C.byref(cost), d.ctypes.data_as(C.c_void_p), 23, 31)
+    a_or, c_or = oracle.assign(d)
+    assert np.array_equal(a, a_or) and cost.value == c_or
