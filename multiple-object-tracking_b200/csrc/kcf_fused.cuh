@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             const int c = k0 ? task - K0_BASE : task / (HK - 1);
             const int k = k0 ? 0 : task - c * (HK - 1) + 1;
             float2 *const mrow = model + c * S + half * SK + k;        // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186): row j' = 2m + half
-            constexpr int CH = (HW < 4) ? HW : 4;                      // model values in flight per thread
+            constexpr int CH = (HW < 2) ? HW : 2;                      // model values in flight per thread (double-buffered)
             float2 mpre[CH];
 #pragma unroll
             for (int q = 0; q < CH; ++q) mpre[q] = need_model ? mrow[q * 2 * SK] : make_float2(0.f, 0.f);   // hides behind the FFT

@@ -28,6 +28,18 @@ int mot_fail(int code, const char *fmt, ...)
 static constexpr int MAX_CLASSES = 1024;
 static constexpr long DUMP_NB_MAX = 4096;       // stage dumps (test hook) are available for windows up to 64x64 cells
 
+// Small host arrays (slots, frame indices, boxes) reach the device through this kernel reading the pinned staging
+// buffers directly (zero-copy over PCIe) instead of through cudaMemcpyAsync: H2D copies of every stream share one copy
+// engine, so a 256 KB memcpy would queue behind the 400 MB of next-frame uploads and serialise the pipeline.
+__global__ void stage_in_kernel(int *d_slots, const int *h_slots, int *d_frames, const int *h_frames, mot_bbox_t *d_boxes, const mot_bbox_t *h_boxes, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d_slots[i] = h_slots[i];
+    if (d_frames) d_frames[i] = h_frames[i];
+    d_boxes[i] = h_boxes[i];
+}
+
 __global__ void meta_scatter_kernel(KcfMeta *meta, const KcfMeta *src, const int *slots, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,9 +397,9 @@ static int kcf_batch_host(mot_ctx_t *c, int mode, int n, const int *handles, con
     CU(c->h_slots.ensure(n)); CU(c->h_frames.ensure(n)); CU(c->h_boxes.ensure(n));
     CU(c->d_slots.ensure(n)); CU(c->d_frames.ensure(n)); CU(c->d_boxes.ensure(n));
     for (int i = 0; i < n; ++i) { c->h_slots.p[i] = handles[order[i]]; c->h_frames.p[i] = frame_slots[order[i]]; c->h_boxes.p[i] = boxes[order[i]]; }
-    CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_frames.p, c->h_frames.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_boxes.p, c->h_boxes.p, sizeof(mot_bbox_t) * n, cudaMemcpyHostToDevice, c->stream));
+    stage_in_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_slots.p, c->h_slots.p, c->d_frames.p, c->h_frames.p, c->d_boxes.p, c->h_boxes.p, n);
+    CU(cudaGetLastError());
+    c->launches += 1;
     for (int a = 0; a < n;) {
         const int cls = c->meta_h[c->h_slots.p[a]].size_class;
         int b = a; while (b < n && c->meta_h[c->h_slots.p[b]].size_class == cls) ++b;
