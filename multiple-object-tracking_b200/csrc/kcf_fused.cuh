@@ -184,10 +184,19 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         __syncthreads();
         // staged bytes -> gray: one warp per row, lanes along x (3-byte pixels: conflict-free shared loads)
         const int warp = tid >> 5, lane = tid & 31;
-        for (int y = warp; y < rows; y += NT / 32) {
-            const unsigned char *rrow = raw + y * G::RAW_PITCH - a0;
+        if (l >= 0 && l + cols - 1 <= Wm) {
+            // crop inside the frame horizontally (the common case): no per-pixel clamping
+            for (int y = warp; y < rows; y += NT / 32) {
+                const unsigned char *rrow = raw + y * G::RAW_PITCH + (l * 3 - a0);
 #pragma unroll 4
-            for (int x = lane; x < cols; x += 32) F[(x + 1) * GS + y + 1] = bgr_gray(rrow + clampi(l + x, 0, Wm) * 3);
+                for (int x = lane; x < cols; x += 32) F[(x + 1) * GS + y + 1] = bgr_gray(rrow + x * 3);
+            }
+        } else {
+            for (int y = warp; y < rows; y += NT / 32) {
+                const unsigned char *rrow = raw + y * G::RAW_PITCH - a0;
+#pragma unroll 4
+                for (int x = lane; x < cols; x += 32) F[(x + 1) * GS + y + 1] = bgr_gray(rrow + clampi(l + x, 0, Wm) * 3);
+            }
         }
     } else if (identity) {
         // unaligned frames: plain loads.  Equal sizes: bilinearInterpolationGray is an exact copy (top/drawlib.c:610-633, xs = ys = 1)
