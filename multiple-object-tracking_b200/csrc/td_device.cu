@@ -119,6 +119,10 @@ struct mot_tdd_s {
     double *d_dist, *d_cost;
     DevBuf<mot_bbox_t> d_dets; DevBuf<int> d_ndet;
     PinBuf<mot_bbox_t> h_dets; PinBuf<int> h_ndet;
+    // The host-array step is launch-latency bound (two copies + six kernels for a few hundred tracks): its fixed sequence is
+    // captured once into a CUDA graph and replayed.
+    cudaGraphExec_t graph = nullptr;
+    cudaStream_t graph_stream = nullptr;
 };
 
 extern "C" {
@@ -157,6 +161,7 @@ void mot_tdd_destroy(mot_tdd_t *t)
     TddState &st = t->st;
     cudaFree(st.ntracks); cudaFree(st.tracker_id); cudaFree(st.tid); cudaFree(st.slot); cudaFree(st.age); cudaFree(st.vis); cudaFree(st.invis);
     cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost);
+    if (t->graph) cudaGraphExecDestroy(t->graph);
     t->d_dets.release(); t->d_ndet.release(); t->h_dets.release(); t->h_ndet.release();
     for (long i = 0; i < (long)st.S * st.cap; ++i) { t->ctx->used[i] = 0; t->ctx->free_slots.push_back((int)i); }
     delete t;
@@ -196,9 +201,26 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
         t->h_ndet.p[s] = ndet[s];
         if (ndet[s]) memcpy(t->h_dets.p + (size_t)s * st.max_det, dets[s], sizeof(mot_bbox_t) * ndet[s]);
     }
-    CU(cudaMemcpyAsync(t->d_dets.p, t->h_dets.p, sizeof(mot_bbox_t) * (size_t)st.S * st.max_det, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(t->d_ndet.p, t->h_ndet.p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream));
-    return mot_tdd_step_dev(t, t->d_dets.p, t->d_ndet.p);
+    if (t->graph && t->graph_stream == c->stream) { CU(cudaGraphLaunch(t->graph, c->stream)); c->launches += 6; return 0; }
+    if (t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
+    // first call (or the stream changed): make every lazy allocation happen outside the capture, then record the sequence
+    CU(c->d_work.ensure((size_t)st.S * st.md * st.md));
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e1 = cudaMemcpyAsync(t->d_dets.p, t->h_dets.p, sizeof(mot_bbox_t) * (size_t)st.S * st.max_det, cudaMemcpyHostToDevice, c->stream);
+    cudaError_t e2 = cudaMemcpyAsync(t->d_ndet.p, t->h_ndet.p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream);
+    const long l0 = c->launches;
+    const int rc = (e1 == cudaSuccess && e2 == cudaSuccess) ? mot_tdd_step_dev(t, t->d_dets.p, t->d_ndet.p) : MOT_ERR_CUDA;
+    c->launches = l0;
+    const cudaError_t e3 = cudaStreamEndCapture(c->stream, &g);
+    if (rc || e3 != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); return rc ? rc : mot_fail(MOT_ERR_CUDA, "graph capture of the frame loop failed: %s", cudaGetErrorString(e3)); }
+    const cudaError_t e4 = cudaGraphInstantiate(&t->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e4 != cudaSuccess) { t->graph = nullptr; return mot_fail(MOT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e4)); }
+    t->graph_stream = c->stream;
+    CU(cudaGraphLaunch(t->graph, c->stream));
+    c->launches += 6;
+    return 0;
 }
 
 /* snapshot of one stream's track table (synchronises); returns the number of tracks */
