@@ -147,7 +147,7 @@ def config2(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--matrices", type=int, default=148)
+    ap.add_argument("--matrices", type=int, default=1024)
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--cpu-matrices", type=int, default=2)
     args = ap.parse_args()

@@ -57,6 +57,7 @@ struct MunkresSmem {
     uint32_t *Zc;           // [nC][nWr] zero bitmap, column-major: bit r of word (c, r>>5)
     uint32_t *covR, *covC;  // cover bit masks
     uint32_t *cand, *candAll; // columns that may hold an UNCOVERED zero (superset) / that hold any zero
+    uint32_t *Zr;           // [nR][nWc] row-major copy of the zero bitmap for the greedy start (null when it does not fit)
     int *starOfRow, *starOfCol, *primeOfRow;
     double *redd;           // [16] reduction scratch
     int *ctrl;              // [4]: 0 = control word, 1 = aug row, 2 = aug col
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
         s.covC = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
         s.cand = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
         s.candAll = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
+        s.Zr = (md <= 512) ? reinterpret_cast<uint32_t *>(q) : nullptr; q += (md <= 512) ? sizeof(uint32_t) * (size_t)md * mdW : 0;
         s.starOfRow = reinterpret_cast<int *>(q); q += sizeof(int) * md;
         s.starOfCol = reinterpret_cast<int *>(q); q += sizeof(int) * md;
         s.primeOfRow = reinterpret_cast<int *>(q); q += sizeof(int) * md;
@@ -166,11 +168,32 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
         }
     };
     refresh_candidates();
+    if (s.Zr && nR <= nC) {
+        // row-major copy of the bitmap: row r, word w = columns 32w..32w+31
+        for (int task = warp; task < nR * nWc; task += NW) {
+            const int r = task / nWc, w = task - r * nWc, c = (w << 5) + lane;
+            const bool z = (c < nC) && ((s.Zc[c * zs + (r >> 5)] >> (r & 31)) & 1u);
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
+            if (lane == 0) s.Zr[r * nWc + w] = word;
+        }
+    }
     __syncthreads();
 
     // greedy initial stars (hungarian.cpp:91-101 / :126-140) -- sequential by nature, one warp
     if (warp == 0) {
-        if (nR <= nC) {
+        if (nR <= nC && s.Zr) {
+            // first uncovered zero column of each row, rows ascending (hungarian.cpp:91-101): one ballot per row
+            for (int r = 0; r < nR; ++r) {
+                const uint32_t mw = (lane < nWc) ? (s.Zr[r * nWc + lane] & ~s.covC[lane]) : 0u;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mw != 0);
+                if (bal) {
+                    const int fl = __ffs(bal) - 1;
+                    const int cs = (fl << 5) + __ffs(__shfl_sync(0xFFFFFFFFu, mw, fl)) - 1;
+                    if (lane == 0) { s.starOfRow[r] = cs; s.starOfCol[cs] = r; s.covC[cs >> 5] |= 1u << (cs & 31); }
+                    __syncwarp();
+                }
+            }
+        } else if (nR <= nC) {
             for (int r = 0; r < nR; ++r) {
                 for (int cb = 0; cb < nC; cb += 32) {
                     const int c = cb + lane;
@@ -306,13 +329,25 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
         __syncthreads();
     }
 
-    // buildassignmentvector + computeassignmentcost (hungarian.cpp:161-189); rows summed in ascending order
+    // buildassignmentvector + computeassignmentcost (hungarian.cpp:161-189); rows summed in ascending order.  The per-row costs
+    // are fetched in parallel into shared memory (the zero bitmap is dead by now), then added up by one thread in row order.
     const bool fail = s.ctrl[0] == CTRL_FAIL;
-    for (int r = tid; r < nR; r += NT) assign[r] = fail ? -1 : s.starOfRow[r];
+    double *const rowcost = reinterpret_cast<double *>(s.Zc);      // md*(mdW|1) words >= nR doubles for every md >= 1? guarded below
+    const bool stage = (size_t)nR * sizeof(double) <= sizeof(uint32_t) * (size_t)md * (mdW | 1);
+    __syncthreads();
+    for (int r = tid; r < nR; r += NT) {
+        const int c = s.starOfRow[r];
+        assign[r] = fail ? -1 : c;
+        if (stage) rowcost[r] = (!fail && c >= 0) ? distIn[r + (long)nR * c] : 0.0;
+    }
+    __syncthreads();
     if (tid == 0) {
         double cst = 0.0;
-        if (!fail) for (int r = 0; r < nR; ++r) { const int c = s.starOfRow[r]; if (c >= 0) cst = __dadd_rn(cst, distIn[r + (long)nR * c]); }
-        else cst = nan("");
+        if (fail) cst = nan("");
+        else for (int r = 0; r < nR; ++r) {
+            const int c = s.starOfRow[r];
+            if (c >= 0) cst = __dadd_rn(cst, stage ? rowcost[r] : distIn[r + (long)nR * c]);
+        }
         p.cost[m] = cst;
     }
 }
@@ -320,7 +355,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
 static size_t munkres_smem(int md, int mat_doubles)
 {
     const int mdW = (md + 31) >> 5;
-    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * 16 + sizeof(uint32_t) * ((size_t)md * (mdW | 1) + 4 * mdW) +
+    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * 16 + sizeof(uint32_t) * ((size_t)md * (mdW | 1) + 4 * mdW + (md <= 512 ? (size_t)md * mdW : 0)) +
            sizeof(int) * (3 * (size_t)md + 4);
 }
 

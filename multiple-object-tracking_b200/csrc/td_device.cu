@@ -48,16 +48,17 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
     extern __shared__ int sm[];
     int *pos = sm;                    // [cap] new position of a kept track / [max_det] rank of a spawning detection
     int *freeid = sm + 1024;          // [cap] free local slot ids in ascending order
-    __shared__ int total, nfree;
-    // ---- keep flags + exclusive scan (a single thread: tables are a few hundred entries) -------------------------------
+    __shared__ int total;
+    // ---- keep flags in parallel, exclusive scan by one thread on shared memory (tables are a few hundred entries) ----------
+    for (int i = tid; i < T; i += NTH) {
+        const long o = (long)s * cap + i;
+        const bool lost = ((st.age[o] < 10) && (st.vis[o] * 5 < 3 * st.age[o])) || (st.invis[o] >= 20);        // :587-590
+        pos[i] = lost ? -1 : 0;
+    }
+    __syncthreads();
     if (tid == 0) {
         int n = 0;
-        for (int i = 0; i < T; ++i) {
-            const long o = (long)s * cap + i;
-            const bool lost = ((st.age[o] < 10) && (st.vis[o] * 5 < 3 * st.age[o])) || (st.invis[o] >= 20);    // :587-590
-            pos[i] = lost ? -1 : n;
-            if (!lost) ++n;
-        }
+        for (int i = 0; i < T; ++i) if (pos[i] == 0) pos[i] = n++;
         total = n;
     }
     __syncthreads();
@@ -77,16 +78,18 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
     for (int i = n2 + tid; i < T; i += NTH) st.slot[(long)s * cap + i] = -1;
     __syncthreads();
     // ---- free local slot ids (ascending) + ranks of the spawning detections ------------------------------------------------
+    __shared__ uint32_t used[32];                       // cap <= 1024
+    if (tid < 32) used[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n2; i += NTH) { const int ls = st.slot[(long)s * cap + i] - s * cap; atomicOr(&used[ls >> 5], 1u << (ls & 31)); }
+    for (int j = tid; j < D; j += NTH) pos[j] = st.assigned_detected[(long)s * st.max_det + j] < 0 ? 1 : 0;
+    __syncthreads();
     if (tid == 0) {
-        // cap <= 1024 -> 32-word bitmap on the stack
-        uint32_t used[32];
-        for (int w = 0; w < 32; ++w) used[w] = 0;
-        for (int i = 0; i < n2; ++i) { const int ls = st.slot[(long)s * cap + i] - s * cap; used[ls >> 5] |= 1u << (ls & 31); }
         int nf = 0;
         for (int ls = 0; ls < cap; ++ls) if (!((used[ls >> 5] >> (ls & 31)) & 1u)) freeid[nf++] = ls;
-        nfree = nf;
+        (void)nf;
         int rk = 0;
-        for (int j = 0; j < D; ++j) { const bool un = st.assigned_detected[(long)s * st.max_det + j] < 0; pos[j] = (un && n2 + rk < cap) ? rk : -1; if (un && n2 + rk < cap) ++rk; }
+        for (int j = 0; j < D; ++j) { const bool ok = pos[j] && n2 + rk < cap; pos[j] = ok ? rk : -1; if (ok) ++rk; }
         total = rk;
     }
     __syncthreads();
