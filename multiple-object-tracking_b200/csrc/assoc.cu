@@ -17,7 +17,7 @@
 
 namespace mot {
 
-constexpr int MUNKRES_THREADS = 512;
+constexpr int MUNKRES_THREADS = 1024;
 
 __device__ __forceinline__ double cost_cell(const mot_bbox_t &t, const mot_bbox_t &d, int mode, double screen_dis)
 {
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
     {
         unsigned char *q = smem_raw;
         s.mat = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)smem_mat_doubles;
-        s.redd = reinterpret_cast<double *>(q); q += sizeof(double) * 16;
+        s.redd = reinterpret_cast<double *>(q); q += sizeof(double) * 32;
         s.Zc = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * (size_t)md * (mdW | 1);
         s.covR = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
         s.covC = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
@@ -287,12 +287,24 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
         if (ctrl != CTRL_STEP5) break;
         if (++guard > guard_max) { if (tid == 0) s.ctrl[0] = CTRL_FAIL; __syncthreads(); break; }
 
-        // step 5 (hungarian.cpp:337-368), whole CTA.  h = smallest uncovered element
+        // step 5 (hungarian.cpp:337-368), whole CTA.  h = smallest uncovered element.  Both passes walk (column, 32-row word)
+        // tasks four at a time per warp so that four independent global loads are in flight (the passes are latency-bound).
+        constexpr int U = 8;
+        const int nTask = nC * nWr;
         double h = DBL_MAX;
-        for (int task = warp; task < nC * nWr; task += NW) {
-            const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
-            if (tst(s.covC, c)) continue;
-            if (r < nR && !tst(s.covR, r)) { const double v = d[r + (long)nR * c]; if (v < h) h = v; }
+        for (int t0 = warp; t0 < nTask; t0 += NW * U) {
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int task = t0 + u * NW;
+                v[u] = DBL_MAX;
+                if (task < nTask) {
+                    const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
+                    if (!tst(s.covC, c) && r < nR && !tst(s.covR, r)) v[u] = d[r + (long)nR * c];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (v[u] < h) h = v[u];
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_xor_sync(0xFFFFFFFFu, h, off); if (o < h) h = o; }
@@ -302,26 +314,41 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
 #pragma unroll
         for (int w = 1; w < NW; ++w) { const double o = s.redd[w]; if (o < h) h = o; }
         // add h to covered rows, then subtract h from uncovered columns; refresh the zero bits of touched cells
-        for (int task = warp; task < nC * nWr; task += NW) {
-            const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
-            const bool cc = tst(s.covC, c);
-            const uint32_t crw = s.covR[w];
-            if (cc && crw == 0) continue;                         // covered column, no covered row in this word: untouched
-            const uint32_t old = s.Zc[c * zs + w];
-            bool z = (old >> lane) & 1u;
-            if (r < nR) {
-                const bool rc = (crw >> lane) & 1u;
-                if (rc || !cc) {
-                    double v = d[r + (long)nR * c];
-                    if (rc) v = __dadd_rn(v, h);
-                    if (!cc) v = __dsub_rn(v, h);
-                    d[r + (long)nR * c] = v;
-                    z = fabs(v) < DBL_EPSILON;
+        for (int t0 = warp; t0 < nTask; t0 += NW * U) {
+            double v[U]; bool touch[U], live[U], rcv[U], ccv[U]; long off[U]; int zi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int task = t0 + u * NW;
+                touch[u] = false; live[u] = false; rcv[u] = false; ccv[u] = true; off[u] = 0; zi[u] = 0; v[u] = 0.0;
+                if (task < nTask) {
+                    const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
+                    const bool cc = tst(s.covC, c);
+                    const uint32_t crw = s.covR[w];
+                    live[u] = !(cc && crw == 0);                  // covered column, no covered row in this word: untouched
+                    zi[u] = c * zs + w; ccv[u] = cc;
+                    if (live[u] && r < nR) {
+                        rcv[u] = (crw >> lane) & 1u;
+                        touch[u] = rcv[u] || !cc;
+                        off[u] = r + (long)nR * c;
+                        if (touch[u]) v[u] = d[off[u]];
+                    }
                 }
             }
-            const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
-            __syncwarp();                                         // every lane has read the old word
-            if (lane == 0) s.Zc[c * zs + w] = word;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!live[u]) continue;                            // warp-uniform (depends on the task only)
+                bool z = (s.Zc[zi[u]] >> lane) & 1u;
+                if (touch[u]) {
+                    double x = v[u];
+                    if (rcv[u]) x = __dadd_rn(x, h);
+                    if (!ccv[u]) x = __dsub_rn(x, h);
+                    d[off[u]] = x;
+                    z = fabs(x) < DBL_EPSILON;
+                }
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
+                __syncwarp();                                     // every lane has read the old word
+                if (lane == 0) s.Zc[zi[u]] = word;
+            }
         }
         after_step5 = true;
         __syncthreads();
@@ -355,7 +382,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
 static size_t munkres_smem(int md, int mat_doubles)
 {
     const int mdW = (md + 31) >> 5;
-    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * 16 + sizeof(uint32_t) * ((size_t)md * (mdW | 1) + 4 * mdW + (md <= 512 ? (size_t)md * mdW : 0)) +
+    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * 32 + sizeof(uint32_t) * ((size_t)md * (mdW | 1) + 4 * mdW + (md <= 512 ? (size_t)md * mdW : 0)) +
            sizeof(int) * (3 * (size_t)md + 4);
 }
 
