@@ -72,8 +72,14 @@ template <int N, int DIR> __device__ __forceinline__ void fft_pair(float2 (&a)[N
     fft_dif<H, DIR>(a);
 }
 
-// position of packed bin k in row j of the spectrum buffer: an XOR swizzle that keeps (a) the column-wise writers of the
-// row pass, (b) the pair-wise readers of the column pass (rows j and j + WC/2 in the same instruction) off each other's banks
-template <int HK, int WC> __device__ __forceinline__ int fpos(int k, int j) { return k ^ (j & (HK - 1)) ^ ((j >= WC / 2) ? (HK >> 1) : 0); }
+// position of packed bin k in row j of the spectrum buffer: k XOR f(j), with f chosen so that every access pattern of the
+// kernels is bank-conflict free for 64-bit words: (a) the row pass writes rows j = 0..15 / 16..31 at a fixed k (f is a
+// bijection on each half), (b) the column pass reads rows i and i + WC/2 in one instruction (f differs in the top bit),
+// (c) it writes rows 2m and 2m + 1 in one instruction (f differs in the top bit again), (d) the channel sum reads along k.
+template <int HK, int WC> __device__ __forceinline__ int fpos(int k, int j)
+{
+    const int fj = (((j & 1) * (HK >> 1)) | ((j >> 1) & ((HK >> 1) - 1))) ^ ((j >= WC / 2) ? (HK >> 1) : 0);
+    return k ^ fj;
+}
 
 }  // namespace mot

@@ -124,6 +124,11 @@ void build(FhogTables &t)
     t.rsrc_tab.resize(2 * t.rsqrt_tab.size());
     for (size_t i = 0; i < t.rsqrt_tab.size(); ++i) { t.rsrc_tab[2 * i] = t.rsqrt_tab[i]; t.rsrc_tab[2 * i + 1] = emu_rcp(t, t.rsqrt_tab[i]); }
     t.rcp_cap = emu_rcp(t, 1e10f);
+    // the fused kernel carries the orientation bin (0..17) in the five low mantissa bits of M/16; rcpps results are
+    // short-mantissa table values, so those bits are zero -- verified here rather than assumed
+    for (size_t i = 0; i < t.rsqrt_tab.size(); ++i)
+        if (f2u(t.rsrc_tab[2 * i + 1]) & 31u) { t.error = "rcpps returns more than 18 mantissa bits on this CPU; unsupported"; return; }
+    if (f2u(t.rcp_cap) & 31u) { t.error = "rcpps(1e10) has low mantissa bits set; unsupported"; return; }
     t.ok = true;
 }
 

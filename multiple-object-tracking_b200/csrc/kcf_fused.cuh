@@ -37,17 +37,16 @@ template <int HR, int WC> struct Geo {
     static constexpr int RS = HR + 1;                    // histogram / normaliser column stride
     // (M/16, bin) per pixel with a 2..5-pixel zero border, de-interleaved along y: [x+2][(y+2)&3][(y+2)>>2]
     static constexpr int PC = 4 * (HR + 2);                // column pitch of the padded layout
-    static constexpr int PADM = (W0 + 8) * PC;             // floats of M0 (the bins take PADM bytes after it)
+    static constexpr int PADM = (W0 + 8) * PC;             // words of (M0 | bin): the bin rides in the 5 low mantissa bits, which are zero (fhog_tables.cpp)
     static constexpr int RAW_PITCH = 432;                  // bytes per staged frame row: 3*(4*32+3) + 2*15 alignment slack, 16-byte multiple
     static constexpr int RAW_FLOATS = RMAX * RAW_PITCH / 4;
     static constexpr int F_MIN = 31 * NB;
-    static constexpr int F_A = (CMAX + 2) * GS > PADM + PADM / 4 ? (CMAX + 2) * GS : PADM + PADM / 4;
+    static constexpr int F_A = (CMAX + 2) * GS > PADM ? (CMAX + 2) * GS : PADM;
     static constexpr int F_FLOATS = ((F_MIN > F_A ? F_MIN : F_A) + 3) & ~3;
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
     static constexpr int PIX_PER_THREAD = (H0 * W0 + KCF_THREADS - 1) / KCF_THREADS;
     static_assert(3 * CMAX + 30 <= RAW_PITCH, "staged row pitch");
-    static_assert(PADM % 4 == 0, "bin array alignment");
     static_assert((F_FLOATS & 1) == 0, "float2 alignment of the R1 region");
 };
 
@@ -278,15 +277,14 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // (M0, bin) overwrite the gray patch in a zero-bordered layout de-interleaved along y, [x+2][(y+2)&3][(y+2)>>2], so
     // that the cell-parallel gather below reads consecutive words and needs no bounds checks (a zero magnitude adds +0)
     constexpr int PC = G::PC;
-    float *const M0s = F;
-    unsigned char *const Bs = reinterpret_cast<unsigned char *>(F + G::PADM);
+    uint32_t *const MB = reinterpret_cast<uint32_t *>(F);
 #pragma unroll
     for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
         const int idx = tid + q * NT;
         if (idx < H0 * W0) {
             const int x = idx / H0, y = idx - x * H0;
             const int a = (x + 2) * PC + ((y + 2) & 3) * (HR + 2) + ((y + 2) >> 2);
-            M0s[a] = m0r[q]; Bs[a] = bnr[q];
+            MB[a] = __float_as_uint(m0r[q]) | (uint32_t)bnr[q];
             if (DUMP && p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = m0r[q]; p.dump.bin[(long)job * p.dump.stride_px + idx] = bnr[q]; }
         }
     }
@@ -296,7 +294,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         if (k < 8 * (H0 + 8)) { const int cxx = k / (H0 + 8); ys = k - cxx * (H0 + 8); xs = cxx < 2 ? cxx : W0 + cxx; }
         else { const int k2 = k - 8 * (H0 + 8); const int ry = k2 / W0; xs = 2 + (k2 - ry * W0); ys = ry < 2 ? ry : H0 + ry; }
         const int a = xs * PC + (ys & 3) * (HR + 2) + (ys >> 2);
-        M0s[a] = 0.f; Bs[a] = 0;
+        MB[a] = 0u;
     }
     __syncthreads();
 
@@ -330,8 +328,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                 for (int u = 0; u < CPT; ++u) {
                     if (!live[u]) continue;
                     const int a = base[u] + dx * PC + (dy & 3) * (HR + 2) + (dy >> 2);
-                    const float v = __fmul_rn(w, M0s[a]);
-                    float *const hb = h[u] + (int)Bs[a] * (WC * RS);
+                    const uint32_t mb = MB[a];
+                    const float v = __fmul_rn(w, __uint_as_float(mb & ~31u));
+                    float *const hb = h[u] + (int)(mb & 31u) * (WC * RS);
                     *hb = __fadd_rn(*hb, v);
                 }
             }
@@ -441,7 +440,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             for (int i = 0; i < HR; ++i) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j * HR + i] = (i & 1) ? z[i >> 1].y : z[i >> 1].x;
         }
         fft_dif<HK, -1>(z);
-        const int sw = (j & (HK - 1)) ^ ((j >= WC / 2) ? (HK >> 1) : 0);   // see fpos()
+        const int sw = fpos<HK, WC>(0, j);
         float2 *const dst = F2 + (c * WC + j) * HK;
         {
             const float2 z0 = z[0];
