@@ -36,7 +36,8 @@ template <int HR, int WC> struct Geo {
     static constexpr int GS = RMAX + 2;                  // gray column stride incl. a 1-pixel replicated apron (odd -> conflict-free both ways)
     static constexpr int RS = HR + 1;                    // histogram / normaliser column stride
     // (M/16, bin) per pixel with a 2..5-pixel zero border, de-interleaved along y: [x+2][(y+2)&3][(y+2)>>2]
-    static constexpr int PC = 4 * (HR + 2);                // column pitch of the padded layout
+    static constexpr int PS = ((HR + 2 - 8 + 15) / 16) * 16 + 8;   // sub-column pitch: >= HR + 2 and = 8 (mod 16), so that a warp's P1 stores spread over the banks
+    static constexpr int PC = 4 * PS;                      // column pitch of the padded layout
     static constexpr int PADM = (W0 + 8) * PC;             // words of (M0 | bin): the bin rides in the 5 low mantissa bits, which are zero (fhog_tables.cpp)
     static constexpr int RAW_PITCH = 432;                  // bytes per staged frame row: 3*(4*32+3) + 2*15 alignment slack, 16-byte multiple
     static constexpr int RAW_FLOATS = RMAX * RAW_PITCH / 4;
@@ -45,6 +46,7 @@ template <int HR, int WC> struct Geo {
     static constexpr int F_FLOATS = ((F_MIN > F_A ? F_MIN : F_A) + 3) & ~3;
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
+    static constexpr int MQ_FLOATS = 4 * KCF_THREADS;      // P5: two model values (float2) per thread in flight through cp.async
     static constexpr int PIX_PER_THREAD = (H0 * W0 + KCF_THREADS - 1) / KCF_THREADS;
     static_assert(3 * CMAX + 30 <= RAW_PITCH, "staged row pitch");
     static_assert((F_FLOATS & 1) == 0, "float2 alignment of the R1 region");
@@ -61,8 +63,16 @@ __host__ __device__ inline int r1_region_floats(int r1_min, int lut_floats, int 
 template <int HR, int WC> size_t smem_bytes(int lut_floats)
 {
     using G = Geo<HR, WC>;
-    return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS) + G::N_FLOATS + G::NB + HR + WC + 64);
+    return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS) + G::MQ_FLOATS + G::N_FLOATS + G::NB + HR + WC + 64);
 }
+
+// 8-byte asynchronous copy global -> shared (SASS: LDGSTS), completion tracked per thread with commit / wait groups
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -97,7 +107,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     extern __shared__ __align__(16) float smem[];
     float *const F = smem;
     float *const R1 = F + G::F_FLOATS;
-    float *const Ns = R1 + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS);
+    float2 *const MQ = reinterpret_cast<float2 *>(R1 + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS));
+    float *const Ns = reinterpret_cast<float *>(MQ) + G::MQ_FLOATS;
     float *const Es = Ns + G::N_FLOATS;
     float *const wy_s = Es + NB;
     float *const wx_s = wy_s + HR;
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         const int idx = tid + q * NT;
         if (idx < H0 * W0) {
             const int x = idx / H0, y = idx - x * H0;
-            const int a = (x + 2) * PC + ((y + 2) & 3) * (HR + 2) + ((y + 2) >> 2);
+            const int a = (x + 2) * PC + ((y + 2) & 3) * G::PS + ((y + 2) >> 2);
             MB[a] = __float_as_uint(m0r[q]) | (uint32_t)bnr[q];
             if (DUMP && p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = m0r[q]; p.dump.bin[(long)job * p.dump.stride_px + idx] = bnr[q]; }
         }
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         int xs, ys;
         if (k < 8 * (H0 + 8)) { const int cxx = k / (H0 + 8); ys = k - cxx * (H0 + 8); xs = cxx < 2 ? cxx : W0 + cxx; }
         else { const int k2 = k - 8 * (H0 + 8); const int ry = k2 / W0; xs = 2 + (k2 - ry * W0); ys = ry < 2 ? ry : H0 + ry; }
-        const int a = xs * PC + (ys & 3) * (HR + 2) + (ys >> 2);
+        const int a = xs * PC + (ys & 3) * G::PS + (ys >> 2);
         MB[a] = 0u;
     }
     __syncthreads();
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 #pragma unroll
                 for (int u = 0; u < CPT; ++u) {
                     if (!live[u]) continue;
-                    const int a = base[u] + dx * PC + (dy & 3) * (HR + 2) + (dy >> 2);
+                    const int a = base[u] + dx * PC + (dy & 3) * G::PS + (dy >> 2);
                     const uint32_t mb = MB[a];
                     const float v = __fmul_rn(w, __uint_as_float(mb & ~31u));
                     float *const hb = h[u] + (int)(mb & 31u) * (WC * RS);
@@ -493,22 +504,39 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             const int c = k0 ? task - K0_BASE : task / (HK - 1);
             const int k = k0 ? 0 : task - c * (HK - 1) + 1;
             float2 *const mrow = model + c * S + half * SK + k;        // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186): row j' = 2m + half
-            constexpr int CH = (HW < 2) ? HW : 2;                      // model values in flight per thread (double-buffered)
+            // The model column streams in CH values at a time on two paths that alternate chunk by chunk: registers (plain loads)
+            // and a private pair of shared-memory slots (cp.async), so 2 * CH values per thread are in flight without
+            // holding more registers; the first chunk of each path is issued before the transform and hides behind it.
+            constexpr int CH = 2;
+            static_assert(HW % (2 * CH) == 0, "P5 chunking");
+            float2 *const mq = MQ + tid;                               // slots tid, tid + NT
             float2 mpre[CH];
 #pragma unroll
-            for (int q = 0; q < CH; ++q) mpre[q] = need_model ? mrow[q * 2 * SK] : make_float2(0.f, 0.f);   // hides behind the FFT
+            for (int q = 0; q < CH; ++q) mpre[q] = need_model ? mrow[q * 2 * SK] : make_float2(0.f, 0.f);
+            if (need_model) {
+#pragma unroll
+                for (int q = 0; q < CH; ++q) cp_async8(mq + q * NT, mrow + (CH + q) * 2 * SK);
+                cp_async_commit();
+            }
             float2 a[HW];
 #pragma unroll
             for (int i = 0; i < HW; ++i) { const int j = half * HW + i; a[i] = F2[(c * WC + j) * HK + fpos<HK, WC>(k, j)]; }
             fft_pair<WC, -1>(a, half, msk);
 #pragma unroll
             for (int mb = 0; mb < HW; mb += CH) {
+                const bool via_smem = ((mb / CH) & 1) != 0;
                 float2 mv[CH];
+                if (!via_smem) {
 #pragma unroll
-                for (int q = 0; q < CH; ++q) mv[q] = mpre[q];
-                if (need_model && mb + CH < HW) {
+                    for (int q = 0; q < CH; ++q) mv[q] = mpre[q];
+                    if (need_model && mb + 2 * CH < HW) {
 #pragma unroll
-                    for (int q = 0; q < CH; ++q) mpre[q] = mrow[(mb + CH + q) * 2 * SK];
+                        for (int q = 0; q < CH; ++q) mpre[q] = mrow[(mb + 2 * CH + q) * 2 * SK];
+                    }
+                } else {
+                    if (need_model) cp_async_wait_all();
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) mv[q] = need_model ? mq[q * NT] : make_float2(0.f, 0.f);
                 }
 #pragma unroll
                 for (int q = 0; q < CH; ++q) {
@@ -534,23 +562,30 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                     }
                     F2[(c * WC + jp) * HK + fpos<HK, WC>(k, jp)] = o;
                 }
+                if (via_smem && need_model && mb + 2 * CH < HW) {      // slots were read (and their values used) above
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) cp_async8(mq + q * NT, mrow + (mb + 2 * CH + q) * 2 * SK);
+                    cp_async_commit();
+                }
             }
         }
     }
+    // the Nyquist-column model value of P5b: issue the load before the barrier so that its latency overlaps the wait
+    static_assert(KCF_CHAN * WC <= NT, "P5b: one element per thread");
+    float2 m1n = make_float2(0.f, 0.f);
+    if (tid < KCF_CHAN * WC && need_model) m1n = model[(tid / WC) * S + (tid % WC) * SK + HK];
     __syncthreads();
     // ---- P5b: the Nyquist column (k = HR/2), one element per thread
-    for (int e = tid; e < KCF_CHAN * WC; e += NT) {
-        const int c = e / WC, jp = e - c * WC;
+    if (tid < KCF_CHAN * WC) {
+        const int e = tid, c = e / WC, jp = e - c * WC;
         const float2 v = FN[e];
         const int sp1 = c * S + jp * SK + HK;
         if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp1] = v;
         if (MODE == KCF_MODE_PREDICT) {
-            const float2 m1 = model[sp1];
-            FN[e] = make_float2(v.x * m1.x + v.y * m1.y, v.y * m1.x - v.x * m1.y);
+            FN[e] = make_float2(v.x * m1n.x + v.y * m1n.y, v.y * m1n.x - v.x * m1n.y);
         } else {
             FN[e] = make_float2(v.x * v.x + v.y * v.y, 0.f);
-            if (first) model[sp1] = v;
-            else { const float2 m1 = model[sp1]; model[sp1] = make_float2(__fadd_rn(__fmul_rn(omf, m1.x), __fmul_rn(fac, v.x)), __fadd_rn(__fmul_rn(omf, m1.y), __fmul_rn(fac, v.y))); }
+            model[sp1] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, m1n.x), __fmul_rn(fac, v.x)), __fadd_rn(__fmul_rn(omf, m1n.y), __fmul_rn(fac, v.y)));
         }
     }
     __syncthreads();
