@@ -47,6 +47,9 @@ template <int HR, int WC> struct Geo {
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
     static constexpr int MQ_FLOATS = 4 * KCF_THREADS;      // P5: two model values (float2) per thread in flight through cp.async
+    // P5: raw transform of the packed (DC, Nyquist) column, [31][WC] float2; lives on the dead normalisers + energies when they are big enough
+    static constexpr bool ZB_OWN = 2 * KCF_CHAN * WC > N_FLOATS + NB;
+    static constexpr int ZB_FLOATS = ZB_OWN ? 2 * KCF_CHAN * WC : 0;
     static constexpr int PIX_PER_THREAD = (H0 * W0 + KCF_THREADS - 1) / KCF_THREADS;
     static_assert(3 * CMAX + 30 <= RAW_PITCH, "staged row pitch");
     static_assert((F_FLOATS & 1) == 0, "float2 alignment of the R1 region");
@@ -63,7 +66,7 @@ __host__ __device__ inline int r1_region_floats(int r1_min, int lut_floats, int 
 template <int HR, int WC> size_t smem_bytes(int lut_floats)
 {
     using G = Geo<HR, WC>;
-    return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS) + G::MQ_FLOATS + G::N_FLOATS + G::NB + HR + WC + 64);
+    return sizeof(float) * (size_t)(G::F_FLOATS + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS) + G::MQ_FLOATS + G::ZB_FLOATS + G::N_FLOATS + G::NB + HR + WC + 64);
 }
 
 // 8-byte asynchronous copy global -> shared (SASS: LDGSTS), completion tracked per thread with commit / wait groups
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     float *const F = smem;
     float *const R1 = F + G::F_FLOATS;
     float2 *const MQ = reinterpret_cast<float2 *>(R1 + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS));
-    float *const Ns = reinterpret_cast<float *>(MQ) + G::MQ_FLOATS;
+    float *const Ns = reinterpret_cast<float *>(MQ) + G::MQ_FLOATS + G::ZB_FLOATS;
     float *const Es = Ns + G::N_FLOATS;
     float *const wy_s = Es + NB;
     float *const wx_s = wy_s + HR;
@@ -482,10 +485,11 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // Tasks (channel c, packed bin k), each run by a PAIR of adjacent lanes that hold half of the WC points each (the
     // first radix-2 stage goes through warp shuffles), so the transform fits the 64-register budget of a 1024-thread CTA.
     // Lane `half` of a pair ends up with the output rows j' = 2m + half.  Bins k >= 1 are ordinary columns; bin 0 carries
-    // two real-input columns (DC and Nyquist) that are separated after the transform: the DC column is finished here, the
-    // Nyquist column is parked (unmultiplied) in FN and finished, one element per thread, in P5b.  The two kinds of task
+    // two real-input columns (DC and Nyquist): its raw transform is parked in ZB and P5b, one row per thread on all threads,
+    // separates and finishes both columns (so the bin-0 warps are not the stragglers of the phase).  The two kinds of task
     // live in different warps (no divergence): tasks [0, 31*(HK-1)) have k >= 1, tasks from K0_BASE on have k = 0.
     float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column [31][WC]
+    float2 *const ZB = G::ZB_OWN ? MQ + 2 * NT : reinterpret_cast<float2 *>(Ns);   // raw transform of the packed (DC, Nyquist) column [31][WC]
     float2 *const model = p.model + (long)slot * p.model_stride;
     const bool first = (MODE == KCF_MODE_UPDATE) && meta->first_update != 0;
     const float fac = first ? 1.0f : p.factor;                         // kcf.cpp:443
@@ -512,8 +516,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             float2 *const mq = MQ + tid;                               // slots tid, tid + NT
             float2 mpre[CH];
 #pragma unroll
-            for (int q = 0; q < CH; ++q) mpre[q] = need_model ? mrow[q * 2 * SK] : make_float2(0.f, 0.f);
-            if (need_model) {
+            for (int q = 0; q < CH; ++q) mpre[q] = (need_model && !k0) ? mrow[q * 2 * SK] : make_float2(0.f, 0.f);
+            if (need_model && !k0) {
 #pragma unroll
                 for (int q = 0; q < CH; ++q) cp_async8(mq + q * NT, mrow + (CH + q) * 2 * SK);
                 cp_async_commit();
@@ -522,6 +526,11 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 #pragma unroll
             for (int i = 0; i < HW; ++i) { const int j = half * HW + i; a[i] = F2[(c * WC + j) * HK + fpos<HK, WC>(k, j)]; }
             fft_pair<WC, -1>(a, half, msk);
+            if (k0) {
+                // slot 0 = FFT(DC_j + i Nyq_j): parked as it is; P5b separates the two columns with all threads
+#pragma unroll
+                for (int m = 0; m < HW; ++m) ZB[c * WC + 2 * m + half] = a[brev<HW>(m)];
+            } else
 #pragma unroll
             for (int mb = 0; mb < HW; mb += CH) {
                 const bool via_smem = ((mb / CH) & 1) != 0;
@@ -541,15 +550,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 #pragma unroll
                 for (int q = 0; q < CH; ++q) {
                     const int m = mb + q, jp = 2 * m + half;
-                    float2 v = a[brev<HW>(m)];
-                    if (k0) {
-                        // slot 0 = FFT(DC_j + i Nyq_j): X[j'] and X[-j'] (same parity -> same lane) give the two columns
-                        const float2 ya = a[brev<HW>((HW - m) % HW)], yb = a[brev<HW>(HW - 1 - m)];
-                        const float2 y = half ? yb : ya;
-                        const float2 v1 = make_float2(0.5f * (v.x + y.x), 0.5f * (v.y - y.y));   // DC column
-                        FN[c * WC + jp] = make_float2(0.5f * (v.y + y.y), 0.5f * (y.x - v.x));   // Nyquist column, finished in P5b
-                        v = v1;
-                    }
+                    const float2 v = a[brev<HW>(m)];
                     if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + c * S + jp * SK + k] = v;
                     float2 o;
                     if (MODE == KCF_MODE_PREDICT) {
@@ -570,23 +571,34 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             }
         }
     }
-    // the Nyquist-column model value of P5b: issue the load before the barrier so that its latency overlaps the wait
-    static_assert(KCF_CHAN * WC <= NT, "P5b: one element per thread");
-    float2 m1n = make_float2(0.f, 0.f);
-    if (tid < KCF_CHAN * WC && need_model) m1n = model[(tid / WC) * S + (tid % WC) * SK + HK];
+    // the two model values of P5b: issue the loads before the barrier so that their latency overlaps the wait
+    static_assert(KCF_CHAN * WC <= NT, "P5b: one row per thread");
+    float2 m0n = make_float2(0.f, 0.f), m1n = make_float2(0.f, 0.f);
+    if (tid < KCF_CHAN * WC && need_model) {
+        const float2 *mr = model + (tid / WC) * S + (tid % WC) * SK;
+        m0n = mr[0]; m1n = mr[HK];
+    }
     __syncthreads();
-    // ---- P5b: the Nyquist column (k = HR/2), one element per thread
+    // ---- P5b: the DC (k = 0) and Nyquist (k = HR/2) columns, one row j' per thread: Z[j'] and Z[-j'] give both
     if (tid < KCF_CHAN * WC) {
         const int e = tid, c = e / WC, jp = e - c * WC;
-        const float2 v = FN[e];
-        const int sp1 = c * S + jp * SK + HK;
-        if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + sp1] = v;
+        const float2 v = ZB[e], y = ZB[c * WC + ((WC - jp) & (WC - 1))];
+        const float2 dc = make_float2(0.5f * (v.x + y.x), 0.5f * (v.y - y.y));
+        const float2 nq = make_float2(0.5f * (v.y + y.y), 0.5f * (y.x - v.x));
+        const int sp0 = c * S + jp * SK, sp1 = sp0 + HK;
+        if (DUMP && p.dump.spec) { float2 *d = p.dump.spec + (long)job * p.dump.stride_spec * KCF_CHAN; d[sp0] = dc; d[sp1] = nq; }
+        float2 o0, o1;
         if (MODE == KCF_MODE_PREDICT) {
-            FN[e] = make_float2(v.x * m1n.x + v.y * m1n.y, v.y * m1n.x - v.x * m1n.y);
+            o0 = make_float2(dc.x * m0n.x + dc.y * m0n.y, dc.y * m0n.x - dc.x * m0n.y);
+            o1 = make_float2(nq.x * m1n.x + nq.y * m1n.y, nq.y * m1n.x - nq.x * m1n.y);
         } else {
-            FN[e] = make_float2(v.x * v.x + v.y * v.y, 0.f);
-            model[sp1] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, m1n.x), __fmul_rn(fac, v.x)), __fadd_rn(__fmul_rn(omf, m1n.y), __fmul_rn(fac, v.y)));
+            o0 = make_float2(dc.x * dc.x + dc.y * dc.y, 0.f);
+            o1 = make_float2(nq.x * nq.x + nq.y * nq.y, 0.f);
+            model[sp0] = first ? dc : make_float2(__fadd_rn(__fmul_rn(omf, m0n.x), __fmul_rn(fac, dc.x)), __fadd_rn(__fmul_rn(omf, m0n.y), __fmul_rn(fac, dc.y)));
+            model[sp1] = first ? nq : make_float2(__fadd_rn(__fmul_rn(omf, m1n.x), __fmul_rn(fac, nq.x)), __fadd_rn(__fmul_rn(omf, m1n.y), __fmul_rn(fac, nq.y)));
         }
+        F2[(c * WC + jp) * HK + fpos<HK, WC>(0, jp)] = o0;
+        FN[e] = o1;
     }
     __syncthreads();
 
