@@ -130,30 +130,39 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // Rows start on arbitrary byte offsets, so each row is fetched as the enclosing 16-byte-aligned span; that needs a
     // 16-byte aligned frame base and stride (true for every common frame width).  Whether the crop has the template size
     // (the only case that uses the staged rows) is known only when the metadata arrives: a crop that fits the staging area
-    // is fetched speculatively.  Executed by warp 1; exactly one arrival on mbar2 per job, with or without bytes.
-    auto issue_roi = [&](int jb) {
-        const mot_bbox_t bx = p.boxes[jb];
+    // is fetched speculatively.  Executed by the last warp; exactly one arrival on mbar2 per job, with or without bytes.
+    __shared__ mot_bbox_t s_nbox;                     // box and frame of the next job, fetched early (see P0) so that
+    __shared__ const uint8_t *s_nframe;               // issue_roi does not sit on two dependent global loads
+    constexpr int ROI_WARP = NT / 32 - 1;             // the last warp has the lightest P5 (bin-0 tasks)
+    auto issue_roi = [&](const mot_bbox_t bx, const uint8_t *frame_of_job) {
+        const int lane = tid & 31;
         int l = bx.l, t = bx.t, r = bx.r, b = bx.b;
         if (t > b) { const int q = t; t = b; b = q; }
         if (l > r) { const int q = l; l = r; r = q; }
         const int rows_s = b - t + 1, cols_s = r - l + 1;
-        const uint8_t *frame = (p.gray == nullptr) ? p.frame_ptr[p.frames[jb]] : nullptr;
+        const uint8_t *frame = frame_of_job;
         const bool fetch = (p.gray == nullptr) && rows_s <= G::RMAX && cols_s <= G::CMAX && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0;
         const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols_s - 1, 0, Wm);
         const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;
-        if (tid == 32) mbar_expect_tx(&mbar2, fetch ? (uint32_t)rows_s * (uint32_t)(a1 - a0) : 0u);
+        if (lane == 0) mbar_expect_tx(&mbar2, fetch ? (uint32_t)rows_s * (uint32_t)(a1 - a0) : 0u);
         __syncwarp();
         if (fetch)
-            for (int y = tid - 32; y < rows_s; y += 32)
+            for (int y = lane; y < rows_s; y += 32)
                 bulk_g2s(raw + y * G::RAW_PITCH, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar2);
     };
 
     // Persistent CTA: jobs blockIdx.x, blockIdx.x + gridDim.x, ...; the crop of the NEXT job streams into shared memory
     // while the spectral phases of the current one run (the staging area is free from P5 on).
     uint32_t phase = 0;
-    if (tid >= 32 && tid < 64 && (int)blockIdx.x < p.n_jobs) issue_roi(blockIdx.x);
+    if ((tid >> 5) == ROI_WARP && (int)blockIdx.x < p.n_jobs)
+        issue_roi(p.boxes[blockIdx.x], (p.gray == nullptr) ? p.frame_ptr[p.frames[blockIdx.x]] : nullptr);
     for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, phase ^= 1u) {
     __syncthreads();                                   // the previous job is done with every shared-memory region
+    if (tid == 64 && job + (int)gridDim.x < p.n_jobs) {
+        const int jn = job + gridDim.x;
+        s_nbox = p.boxes[jn];
+        s_nframe = (p.gray == nullptr) ? p.frame_ptr[p.frames[jn]] : nullptr;
+    }
     // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
     if (tid < 3) {
         // SSE tables -> shared memory (one arrival on mbar per job)
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     }
     __syncthreads();
     // The histograms are consumed: the staging area is free again -> start streaming the next job's crop underneath P5..P7
-    if (tid >= 32 && tid < 64 && job + (int)gridDim.x < p.n_jobs) issue_roi(job + gridDim.x);
+    if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < p.n_jobs) issue_roi(s_nbox, s_nframe);
 
     // ------------------------------------------------------------------ P5: complex FFT along the WC columns + spectral work
     // Tasks (channel c, packed bin k), each run by a PAIR of adjacent lanes that hold half of the WC points each (the
