@@ -101,6 +101,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Everything a job needs from the per-job / per-track arrays, gathered two jobs ahead by one lane of the staging warp
+// so that no phase sits on a chain of dependent global loads (slot -> meta -> ..., frame index -> frame pointer).
+struct JobDesc {
+    mot_bbox_t box, pos;              // p.boxes[job]; meta->pos
+    const uint8_t *frame;             // p.frame_ptr[p.frames[job]] (null with pre-cropped gray input)
+    int slot, rows, cols, size_class, first_update;
+    float scale_horiz, scale_vert;
+};
+
 template <int HR, int WC, int MODE, bool DUMP>
 __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaunch p, const int lut_floats)
 {
@@ -131,9 +140,18 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // 16-byte aligned frame base and stride (true for every common frame width).  Whether the crop has the template size
     // (the only case that uses the staged rows) is known only when the metadata arrives: a crop that fits the staging area
     // is fetched speculatively.  Executed by the last warp; exactly one arrival on mbar2 per job, with or without bytes.
-    __shared__ mot_bbox_t s_nbox;                     // box and frame of the next job, fetched early (see P0) so that
-    __shared__ const uint8_t *s_nframe;               // issue_roi does not sit on two dependent global loads
+    __shared__ __align__(8) JobDesc s_desc[4];        // ring: job iteration it lives in s_desc[it & 3]
+    __shared__ KcfClassDev s_cls;                     // constants of the current window class (reloaded when the class changes)
+    __shared__ int s_cls_id;
     constexpr int ROI_WARP = NT / 32 - 1;             // the last warp has the lightest P5 (bin-0 tasks)
+    auto fetch_desc = [&](int jb, JobDesc *d) {
+        const int sl = p.slots[jb];
+        const KcfMeta *m = p.meta + sl;
+        d->box = p.boxes[jb];
+        d->frame = (p.gray == nullptr) ? p.frame_ptr[p.frames[jb]] : nullptr;
+        d->slot = sl; d->rows = m->rows; d->cols = m->cols; d->size_class = m->size_class; d->first_update = m->first_update;
+        d->pos = m->pos; d->scale_horiz = m->scale_horiz; d->scale_vert = m->scale_vert;
+    };
     auto issue_roi = [&](const mot_bbox_t bx, const uint8_t *frame_of_job) {
         const int lane = tid & 31;
         int l = bx.l, t = bx.t, r = bx.r, b = bx.b;
@@ -154,15 +172,19 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // Persistent CTA: jobs blockIdx.x, blockIdx.x + gridDim.x, ...; the crop of the NEXT job streams into shared memory
     // while the spectral phases of the current one run (the staging area is free from P5 on).
     uint32_t phase = 0;
-    if ((tid >> 5) == ROI_WARP && (int)blockIdx.x < p.n_jobs)
-        issue_roi(p.boxes[blockIdx.x], (p.gray == nullptr) ? p.frame_ptr[p.frames[blockIdx.x]] : nullptr);
-    for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, phase ^= 1u) {
-    __syncthreads();                                   // the previous job is done with every shared-memory region
-    if (tid == 64 && job + (int)gridDim.x < p.n_jobs) {
-        const int jn = job + gridDim.x;
-        s_nbox = p.boxes[jn];
-        s_nframe = (p.gray == nullptr) ? p.frame_ptr[p.frames[jn]] : nullptr;
+    if (tid == 0) s_cls_id = -1;
+    if ((tid >> 5) == ROI_WARP && (int)blockIdx.x < p.n_jobs) {
+        if ((tid & 31) == 0) {
+            fetch_desc(blockIdx.x, &s_desc[0]);
+            if ((int)(blockIdx.x + gridDim.x) < p.n_jobs) fetch_desc(blockIdx.x + gridDim.x, &s_desc[1]);
+        }
+        __syncwarp();
+        issue_roi(s_desc[0].box, s_desc[0].frame);
     }
+    int it = 0;
+    for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, phase ^= 1u, ++it) {
+    __syncthreads();                                   // the previous job is done with every shared-memory region
+    const JobDesc &jd = s_desc[it & 3];
     // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
     if (tid < 3) {
         // SSE tables -> shared memory (one arrival on mbar per job)
@@ -170,9 +192,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         if (tid == 1 && lut_smem) bulk_g2s(R1 + n_rs, p.tab.bin_tab, n_bn * 4, &mbar);
     }
 
-    const int slot = p.slots[job];
-    mot_bbox_t box = p.boxes[job];
-    const uint8_t *frame = (p.gray == nullptr) ? p.frame_ptr[p.frames[job]] : nullptr;
+    const int slot = jd.slot;
+    mot_bbox_t box = jd.box;
+    const uint8_t *frame = jd.frame;
     int l = box.l, t = box.t, r = box.r, b = box.b;
     if (t > b) { const int q = t; t = b; b = q; }              // top/drawlib.c:203-215
     if (l > r) { const int q = l; l = r; r = q; }
@@ -182,21 +204,27 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     const int a0 = (x_lo * 3) & ~15;                           // aligned start of the staged byte span of a frame row
 
     KcfMeta *const meta = p.meta + slot;
-    const KcfClassDev cls = p.classes[meta->size_class];
-    const int rows = meta->rows, cols = meta->cols;
+    const int rows = jd.rows, cols = jd.cols;
+    const bool first_update = jd.first_update != 0;
+    if (jd.size_class != s_cls_id) {                   // block-uniform; in a launch of one class: the first job only
+        const int sc = jd.size_class;
+        __syncthreads();
+        if (tid == 0) { s_cls = p.classes[sc]; s_cls_id = sc; }
+        __syncthreads();
+        if (tid >= 32 && tid < 32 + HR) wy_s[tid - 32] = s_cls.wy[tid - 32];
+        if (tid >= 64 && tid < 64 + WC) wx_s[tid - 64] = s_cls.wx[tid - 64];
+    }
+    const KcfClassDev &cls = s_cls;
     const bool identity = (p.gray == nullptr) && rows_s == rows && cols_s == cols;
     const bool staged = fetch && identity;
 
     // The model (31*S complex) is not needed before P5, tens of microseconds from now: pull it into L2 now so that P5
     // sees L2 latency instead of HBM latency (there is no shared memory left to stage it in).
-    if (MODE == KCF_MODE_PREDICT || meta->first_update == 0) {
+    if (MODE == KCF_MODE_PREDICT || !first_update) {
         const char *mp = reinterpret_cast<const char *>(p.model + (long)slot * p.model_stride);
         for (int o = tid * 128; o < KCF_CHAN * S * 8; o += NT * 128) prefetch_l2(mp + o);
     }
     if (tid < (S * 4 + 127) / 128) prefetch_l2(reinterpret_cast<const char *>(p.alpha + (long)slot * p.alpha_stride) + tid * 128);
-
-    if (tid >= 32 && tid < 32 + HR) wy_s[tid - 32] = cls.wy[tid - 32];
-    if (tid >= 64 && tid < 64 + WC) wx_s[tid - 64] = cls.wx[tid - 64];
 
     if (p.gray != nullptr) {
         const float *src = p.gray + (long)job * p.gray_stride;
@@ -488,7 +516,11 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     }
     __syncthreads();
     // The histograms are consumed: the staging area is free again -> start streaming the next job's crop underneath P5..P7
-    if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < p.n_jobs) issue_roi(s_nbox, s_nframe);
+    if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < p.n_jobs) {
+        const JobDesc &nd = s_desc[(it + 1) & 3];
+        issue_roi(nd.box, nd.frame);
+        if ((tid & 31) == 0 && job + 2 * (int)gridDim.x < p.n_jobs) fetch_desc(job + 2 * gridDim.x, &s_desc[(it + 2) & 3]);
+    }
 
     // ------------------------------------------------------------------ P5: complex FFT along the WC columns + spectral work
     // Tasks (channel c, packed bin k), each run by a PAIR of adjacent lanes that hold half of the WC points each (the
@@ -500,7 +532,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column [31][WC]
     float2 *const ZB = G::ZB_OWN ? MQ + 2 * NT : reinterpret_cast<float2 *>(Ns);   // raw transform of the packed (DC, Nyquist) column [31][WC]
     float2 *const model = p.model + (long)slot * p.model_stride;
-    const bool first = (MODE == KCF_MODE_UPDATE) && meta->first_update != 0;
+    const bool first = (MODE == KCF_MODE_UPDATE) && first_update;
     const float fac = first ? 1.0f : p.factor;                         // kcf.cpp:443
     const float omf = __fsub_rn(1.0f, fac);
     const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
@@ -707,9 +739,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         if (DUMP && p.dump.peak) { p.dump.peak[2 * job] = vd; p.dump.peak[2 * job + 1] = hd; }
         if (vd > HR / 2) vd -= HR;                                     // kcf.cpp:419-420
         if (hd > WC / 2) hd -= WC;
-        mot_bbox_t pos = meta->pos;
-        const float dv = __fmul_rn((float)(KCF_CELL * (vd - 1)), meta->scale_vert);
-        const float dh = __fmul_rn((float)(KCF_CELL * (hd - 1)), meta->scale_horiz);
+        mot_bbox_t pos = jd.pos;
+        const float dv = __fmul_rn((float)(KCF_CELL * (vd - 1)), jd.scale_vert);
+        const float dh = __fmul_rn((float)(KCF_CELL * (hd - 1)), jd.scale_horiz);
         pos.t = __float2int_rz(__fadd_rn((float)pos.t, dv));           // kcf.cpp:423-426 (float math, truncation)
         pos.b = __float2int_rz(__fadd_rn((float)pos.b, dv));
         pos.l = __float2int_rz(__fadd_rn((float)pos.l, dh));
