@@ -203,7 +203,6 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols_s - 1, 0, Wm);
     const int a0 = (x_lo * 3) & ~15;                           // aligned start of the staged byte span of a frame row
 
-    KcfMeta *const meta = p.meta + slot;
     const int rows = jd.rows, cols = jd.cols;
     const bool first_update = jd.first_update != 0;
     if (jd.size_class != s_cls_id) {                   // block-uniform; in a launch of one class: the first job only
@@ -299,15 +298,14 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 
     // ------------------------------------------------------------------ P1: gradient magnitude + orientation bin
     // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin)
-    float m0r[G::PIX_PER_THREAD];
-    unsigned char bnr[G::PIX_PER_THREAD];
+    uint32_t mbr[G::PIX_PER_THREAD];                   // M/16 with the bin in its five low (zero) mantissa bits
     {
         const LutConsts lk = make_lut_consts(p.tab);
         auto p1_pixels = [&](const float2 *rsrc, const uint32_t *bn) {
 #pragma unroll
             for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
                 const int idx = tid + q * NT;
-                m0r[q] = 0.f; bnr[q] = 0;
+                mbr[q] = 0u;
                 if (idx < H0 * W0) {
                     const int x = idx / H0, y = idx - x * H0;
                     const float *g = F + (x + 1) * GS + y + 1;
@@ -316,8 +314,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                     const float gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), rx);
                     const float gy = __fmul_rn(__fsub_rn(g[1], g[-1]), ry);
                     int bb;
-                    m0r[q] = grad_pixel_k(gx, gy, rsrc, bn, lk, &bb);
-                    bnr[q] = (unsigned char)bb;
+                    const float m0 = grad_pixel_k(gx, gy, rsrc, bn, lk, &bb);
+                    mbr[q] = __float_as_uint(m0) | (uint32_t)bb;
                 }
             }
         };
@@ -335,8 +333,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         if (idx < H0 * W0) {
             const int x = idx / H0, y = idx - x * H0;
             const int a = (x + 2) * PC + ((y + 2) & 3) * G::PS + ((y + 2) >> 2);
-            MB[a] = __float_as_uint(m0r[q]) | (uint32_t)bnr[q];
-            if (DUMP && p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = m0r[q]; p.dump.bin[(long)job * p.dump.stride_px + idx] = bnr[q]; }
+            MB[a] = mbr[q];
+            if (DUMP && p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = __uint_as_float(mbr[q] & ~31u); p.dump.bin[(long)job * p.dump.stride_px + idx] = (unsigned char)(mbr[q] & 31u); }
         }
     }
     // zero border: 8 full columns (x+2 in {0,1,W0+2..W0+7}) and 8 rows of the interior columns (y+2 in {0,1,H0+2..H0+7})
@@ -531,8 +529,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // live in different warps (no divergence): tasks [0, 31*(HK-1)) have k >= 1, tasks from K0_BASE on have k = 0.
     float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column [31][WC]
     float2 *const ZB = G::ZB_OWN ? MQ + 2 * NT : reinterpret_cast<float2 *>(Ns);   // raw transform of the packed (DC, Nyquist) column [31][WC]
-    float2 *const model = p.model + (long)slot * p.model_stride;
-    const bool first = (MODE == KCF_MODE_UPDATE) && first_update;
+    // (job-level values are re-read from the descriptor where they are needed instead of living in registers across the phases)
+    float2 *const model = p.model + (long)jd.slot * p.model_stride;
+    const bool first = (MODE == KCF_MODE_UPDATE) && jd.first_update != 0;
     const float fac = first ? 1.0f : p.factor;                         // kcf.cpp:443
     const float omf = __fsub_rn(1.0f, fac);
     const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
@@ -645,7 +644,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 
     // ------------------------------------------------------------------ P6: sum over the 31 channels (in channel order)
     float2 *const zf_s = FN + KCF_CHAN * WC;                           // [WC][SK]
-    float *const alpha = p.alpha + (long)slot * p.alpha_stride;
+    float *const alpha = p.alpha + (long)jd.slot * p.alpha_stride;
     for (int e = tid; e < S; e += NT) {
         const int j = e / SK, k = e - j * SK;
         float2 acc = make_float2(0.f, 0.f);
@@ -670,10 +669,12 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     if (MODE == KCF_MODE_UPDATE) {
         if (tid == 0) {
             // tracker_update, kcf.cpp:462-476
-            meta->pos = box;
-            meta->scale_horiz = __fdiv_rn((float)(box.r - box.l + 1), (float)cols);
-            meta->scale_vert = __fdiv_rn((float)(box.b - box.t + 1), (float)rows);
-            meta->first_update = 0;
+            KcfMeta *const mt = p.meta + jd.slot;
+            const mot_bbox_t bx = jd.box;
+            mt->pos = bx;
+            mt->scale_horiz = __fdiv_rn((float)(bx.r - bx.l + 1), (float)jd.cols);
+            mt->scale_vert = __fdiv_rn((float)(bx.b - bx.t + 1), (float)jd.rows);
+            mt->first_update = 0;
         }
         continue;                                      // next job (uniform: MODE is a template parameter)
     }
@@ -746,7 +747,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         pos.b = __float2int_rz(__fadd_rn((float)pos.b, dv));
         pos.l = __float2int_rz(__fadd_rn((float)pos.l, dh));
         pos.r = __float2int_rz(__fadd_rn((float)pos.r, dh));
-        meta->pos = pos;
+        (p.meta + jd.slot)->pos = pos;
         if (p.clamp_to_frame) {                                        // top/td.cpp:378-381
             pos.l = clampi(pos.l, 0, p.frame_w - 1); pos.r = clampi(pos.r, 0, p.frame_w - 1);
             pos.t = clampi(pos.t, 0, p.frame_h - 1); pos.b = clampi(pos.b, 0, p.frame_h - 1);
