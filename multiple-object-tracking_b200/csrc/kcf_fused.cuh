@@ -37,7 +37,7 @@ template <int HR, int WC> struct Geo {
     static constexpr int RS = HR + 1;                    // histogram / normaliser column stride
     // (M/16, bin) per pixel with a 2..5-pixel zero border, de-interleaved along y: [x+2][(y+2)&3][(y+2)>>2]
     static constexpr int PS = ((HR + 2 - 8 + 15) / 16) * 16 + 8;   // sub-column pitch: >= HR + 2 and = 8 (mod 16), so that a warp's P1 stores spread over the banks
-    static constexpr int PC = 4 * PS;                      // column pitch of the padded layout
+    static constexpr int PC = 4 * PS + 2;                  // column pitch of the padded layout (= 2 mod 32: the zero-border stores spread over the banks)
     static constexpr int PADM = (W0 + 8) * PC;             // words of (M0 | bin): the bin rides in the 5 low mantissa bits, which are zero (fhog_tables.cpp)
     static constexpr int RAW_PITCH = 432;                  // bytes per staged frame row: 3*(4*32+3) + 2*15 alignment slack, 16-byte multiple
     static constexpr int RAW_FLOATS = RMAX * RAW_PITCH / 4;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     for (int k = tid; k < 8 * (H0 + 8) + 8 * W0; k += NT) {
         int xs, ys;
         if (k < 8 * (H0 + 8)) { const int cxx = k / (H0 + 8); ys = k - cxx * (H0 + 8); xs = cxx < 2 ? cxx : W0 + cxx; }
-        else { const int k2 = k - 8 * (H0 + 8); const int ry = k2 / W0; xs = 2 + (k2 - ry * W0); ys = ry < 2 ? ry : H0 + ry; }
+        else { const int k2 = k - 8 * (H0 + 8); const int ry = k2 & 7; xs = 2 + (k2 >> 3); ys = ry < 2 ? ry : H0 + ry; }
         const int a = xs * PC + (ys & 3) * G::PS + (ys >> 2);
         MB[a] = 0u;
     }
