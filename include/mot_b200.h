@@ -70,6 +70,20 @@ long mot_launch_count(mot_ctx_t *ctx);
 int mot_frame_upload(mot_ctx_t *ctx, int slot, const uint8_t *host_bgr, int stride_bytes);
 /* Zero-copy: make frame slot `slot` refer to a caller-owned DEVICE buffer (BGR u8, rows of stride_bytes). */
 int mot_frame_bind_device(mot_ctx_t *ctx, int slot, const uint8_t *dev_bgr, int stride_bytes);
+/* Copy frame slot `slot` back to the host (rows of stride_bytes >= 3 * frame_w); synchronous. */
+int mot_frame_download(mot_ctx_t *ctx, int slot, uint8_t *host_bgr, int stride_bytes);
+
+/* ---- overlay (replaces the rectangle loop of the tracking thread, top/td.cpp:647-733, and drawRect,
+ *      top/drawlib.c:97-151) ------------------------------------------------------------------------------------ */
+
+/* For entry i, in order: `thickness` nested one-pixel rectangles (box shrunk by 0, 1, ... pixels; the reference draws 3)
+ * of colour rgb[i] (0xRRGGBB, stored as bytes R, G, B like drawRect does) into frame slot frame_slots[i].  Later entries
+ * overwrite earlier ones; reversed boxes are swapped per rectangle; addressing is linear (y * stride + 3 * x) with no
+ * clipping, exactly as drawRect, except that bytes outside the frame buffer are not written.  A frame bound with
+ * mot_frame_bind_device is written in place. */
+int mot_overlay_batch(mot_ctx_t *ctx, int n, const int *frame_slots, const mot_bbox_t *boxes, const uint32_t *rgb, int thickness);
+/* colormap[hashcolor(tid) & 255]: the colour the reference gives track `tid` (top/td.cpp:295-305, 620, 652-699). */
+uint32_t mot_track_color(uint32_t tid);
 
 /* ---- tracker plugin, batched (replaces tracker_new/predict/update/delete, trackers/kcf.cpp:455-491 and
  *      trackers/kalman.cpp:131-163; one call = the reference's loop over tracks, top/td.cpp:344-384, 512-582) --- */
@@ -129,6 +143,9 @@ int mot_td_step_multi(mot_td_t **tds, int n_streams, const uint8_t *const *host_
                       const mot_bbox_t *const *dets, const int *ndet);
 int mot_td_ntracks(mot_td_t *td);
 void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *vis, int *invis);
+/* The overlay loop of top/td.cpp:647-733 for the current track table, drawn on the device into the loop's frame slot
+ * (three nested rectangles per track in colour mot_track_color(tid)); read the frame back with mot_frame_download. */
+int mot_td_overlay(mot_td_t *td);
 int mot_td_last(mot_td_t *td, mot_bbox_t *predicted, int *assigned_trackers);
 
 /* ---- the same frame loop with the track tables resident on the DEVICE (Kalman kind): five launches per frame for all

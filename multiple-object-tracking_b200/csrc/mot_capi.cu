@@ -3,6 +3,7 @@
 // There is deliberately NO CPU fallback: a missing device, a failed launch or an unsupported shape is an error.
 #include "mot_ctx.h"
 #include "fhog_tables.h"
+#include "overlay.h"
 
 #include <algorithm>
 #include <cmath>
@@ -266,6 +267,57 @@ int mot_frame_bind_device(mot_ctx_t *c, int slot, const uint8_t *dev_bgr, int st
     if (any_other && stride_bytes != c->frame_stride) return fail(MOT_ERR_ARG, "all frame slots must share one stride (%d vs %d)", stride_bytes, c->frame_stride);
     c->frame_stride = stride_bytes;
     if (c->frame_ptr_h[slot] != dev_bgr) { c->frame_ptr_h[slot] = dev_bgr; c->frame_ptr_dirty = true; }
+    return 0;
+}
+
+int mot_frame_download(mot_ctx_t *c, int slot, uint8_t *host_bgr, int stride_bytes)
+{
+    if (!c || slot < 0 || slot >= c->n_frames || !host_bgr || stride_bytes < c->W * 3) return fail(MOT_ERR_ARG, "mot_frame_download: bad argument");
+    if (!c->frame_ptr_h[slot]) return fail(MOT_ERR_ARG, "frame slot %d holds no frame", slot);
+    CU(cudaSetDevice(c->device));
+    { const int rc = wait_frames(c, 1, &slot); if (rc) return rc; }
+    CU(cudaMemcpy2DAsync(host_bgr, (size_t)stride_bytes, c->frame_ptr_h[slot], (size_t)c->frame_stride, (size_t)c->W * 3, c->H, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- overlay (top/td.cpp:647-733) -----------------------------------------------------------------------------------------
+uint32_t mot_track_color(uint32_t tid) { return track_color(tid); }
+
+int mot_overlay_batch(mot_ctx_t *c, int n, const int *frame_slots, const mot_bbox_t *boxes, const uint32_t *rgb, int thickness)
+{
+    if (!c || n < 0 || thickness < 0 || (n && (!frame_slots || !boxes || !rgb))) return fail(MOT_ERR_ARG, "mot_overlay_batch: bad argument");
+    if (n == 0 || thickness == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    // entries grouped by frame slot, order kept inside a slot (later entries overwrite earlier ones, like the reference's loop)
+    const int ns = c->n_frames;
+    CU(c->h_slots.ensure((size_t)ns + 1)); CU(c->h_frames.ensure(n)); CU(c->h_boxes.ensure(n)); CU(c->h_TD.ensure(n));
+    CU(c->d_slots.ensure((size_t)ns + 1)); CU(c->d_frames.ensure(n)); CU(c->d_boxes.ensure(n)); CU(c->d_TD.ensure(n));
+    int *begin = c->h_slots.p, *order = c->h_frames.p;
+    for (int s = 0; s <= ns; ++s) begin[s] = 0;
+    for (int i = 0; i < n; ++i) {
+        const int s = frame_slots[i];
+        if (s < 0 || s >= ns || !c->frame_ptr_h[s]) return fail(MOT_ERR_ARG, "entry %d: frame slot %d holds no frame", i, s);
+        begin[s + 1]++;
+    }
+    for (int s = 0; s < ns; ++s) begin[s + 1] += begin[s];
+    {
+        std::vector<int> cur(begin, begin + ns);
+        for (int i = 0; i < n; ++i) order[cur[frame_slots[i]]++] = i;
+    }
+    std::memcpy(c->h_boxes.p, boxes, sizeof(mot_bbox_t) * n);
+    std::memcpy(c->h_TD.p, rgb, sizeof(uint32_t) * n);
+    { const int rc = wait_frames(c, n, frame_slots); if (rc) return rc; }
+    { const int rc = sync_frame_ptrs(c); if (rc) return rc; }
+    CU(cudaMemcpyAsync(c->d_slots.p, begin, sizeof(int) * (ns + 1), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_frames.p, order, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_boxes.p, c->h_boxes.p, sizeof(mot_bbox_t) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_TD.p, c->h_TD.p, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    const int rc = overlay_draw(const_cast<uint8_t *const *>(reinterpret_cast<const uint8_t *const *>(c->d_frame_ptr)), ns, c->frame_stride,
+                                (long)c->frame_stride * c->H, c->d_slots.p, c->d_frames.p, c->d_boxes.p, reinterpret_cast<const uint32_t *>(c->d_TD.p), thickness, c->stream);
+    if (rc) return fail(MOT_ERR_CUDA, "overlay launch failed (%d)", rc);
+    c->launches += 1;
+    CU(cudaStreamSynchronize(c->stream));      // the pinned staging arrays are reused by the next call
     return 0;
 }
 

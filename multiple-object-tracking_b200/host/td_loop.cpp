@@ -182,6 +182,20 @@ void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *v
     }
 }
 
+// The overlay of top/td.cpp:647-733 for the current track table: three nested rectangles per track, in table order, in the
+// colour colormap[hashcolor(tid) & 255] that the reference fixes at spawn time (top/td.cpp:620), drawn on the device into
+// the loop's frame slot.  mot_frame_download brings the annotated frame back.
+int mot_td_overlay(mot_td_t *td)
+{
+    if (!td) return MOT_ERR_ARG;
+    const int n = (int)td->tracks.size();
+    std::vector<int> slots(n, td->frame_slot);
+    std::vector<mot_bbox_t> boxes(n);
+    std::vector<uint32_t> rgb(n);
+    for (int i = 0; i < n; ++i) { boxes[i] = td->tracks[i].bbox; rgb[i] = mot_track_color(td->tracks[i].tid); }
+    return mot_overlay_batch(td->ctx, n, slots.data(), boxes.data(), rgb.data(), 3);
+}
+
 int mot_td_last(mot_td_t *td, mot_bbox_t *predicted, int *assigned_trackers)
 {
     const size_t n = td->predicted.size();

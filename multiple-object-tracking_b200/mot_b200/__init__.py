@@ -20,10 +20,10 @@ BBOX_DTYPE = np.dtype([("l", "<i4"), ("t", "<i4"), ("b", "<i4"), ("r", "<i4"), (
 
 EXPORTS = [
     "mot_ctx_create", "mot_ctx_destroy", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
-    "mot_frame_upload", "mot_frame_bind_device", "mot_tracker_new_batch", "mot_tracker_delete_batch",
+    "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_tracker_new_batch", "mot_tracker_delete_batch",
     "mot_predict_batch", "mot_update_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
-    "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_get", "mot_td_last",
+    "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_get", "mot_td_last", "mot_td_overlay",
     "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_read",
     "mot_debug_enable_dumps", "mot_debug_fetch", "mot_debug_state", "mot_debug_tables",
 ]
@@ -40,6 +40,14 @@ def build(verbose=False):
 
 
 _lib = None
+
+
+def track_color(tid):
+    """colormap[hashcolor(tid) & 255] of top/td.cpp:295-305, 620, 652-699 (host-only helper, no GPU needed)."""
+    L = lib()
+    L.mot_track_color.restype = C.c_uint32
+    L.mot_track_color.argtypes = [C.c_uint32]
+    return int(L.mot_track_color(int(tid) & 0xFFFFFFFF))
 
 
 def lib():
@@ -155,6 +163,17 @@ class Context:
 
     def bind_device(self, slot, dev_ptr, stride):
         _chk(lib().mot_frame_bind_device(self.h, slot, C.c_void_p(dev_ptr), stride))
+
+    def download(self, slot):
+        out = np.zeros((self.H, self.W, 3), np.uint8)
+        _chk(lib().mot_frame_download(self.h, slot, _p(out), out.strides[0]))
+        return out
+
+    def overlay(self, frame_slots, boxes, rgb, thickness=3):
+        """Tracking rectangles of top/td.cpp:647-733 drawn into the frames on the device, entries in order."""
+        fs = _i32(frame_slots); b = _boxes(boxes); col = np.ascontiguousarray(rgb, np.uint32)
+        assert len(fs) == len(b) == len(col)
+        _chk(lib().mot_overlay_batch(self.h, len(fs), _p(fs), _p(b), _p(col), thickness))
 
     # trackers
     def new(self, boxes):
@@ -306,6 +325,10 @@ class TdLoop:
         pred = np.zeros(self.cap, BBOX_DTYPE); asg = np.zeros(self.cap, np.int32)
         n = lib().mot_td_last(self.h, _p(pred), _p(asg))
         return pred[:n], asg[:n]
+
+    def overlay(self):
+        """Draw the current tracks into the loop's frame slot (top/td.cpp:647-733); ctx.download(slot) reads it back."""
+        _chk(lib().mot_td_overlay(self.h))
 
     def close(self):
         if self.h:

@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Generate tests/golden/overlay_v1.npz from the reference (run in the authoring container, where /root/reference exists).
+
+  colormap[256]  the table of top/td.cpp:652-697, parsed from the source text
+  tids[N], hashes[N]  hashcolor (top/td.cpp:295-305) evaluated by compiling the function's own text, extracted from the
+                 source where it lies into a scratch file under /tmp (nothing of the reference is copied into the repo)
+"""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+
+REF = "/root/reference/top/td.cpp"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    src = open(REF).read()
+    blk = src[src.index("static uint32_t colormap[]"):]
+    blk = blk[:blk.index("};")]
+    cmap = np.array([int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]{6})", blk)], np.uint32)
+    assert len(cmap) == 256
+    m = re.search(r"static uint32_t hashcolor\s*\(\s*uint32_t a\)\s*\{.*?\n\}", src, re.S)
+    tmp = tempfile.mkdtemp()
+    cfile = os.path.join(tmp, "h.c")
+    open(cfile, "w").write("#include <stdint.h>\n" + m.group(0).replace("static ", "") + "\n")
+    so = os.path.join(tmp, "h.so")
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", cfile, "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.hashcolor.restype = ctypes.c_uint32
+    lib.hashcolor.argtypes = [ctypes.c_uint32]
+    rng = np.random.default_rng(7)
+    tids = np.concatenate([np.arange(0, 2048, dtype=np.uint32), rng.integers(0, 2 ** 32, 2048, dtype=np.uint64).astype(np.uint32)])
+    hashes = np.array([lib.hashcolor(int(t)) for t in tids], np.uint32)
+    np.savez_compressed(os.path.join(HERE, "overlay_v1.npz"), colormap=cmap, tids=tids, hashes=hashes)
+    print("wrote overlay_v1.npz:", len(cmap), "colours,", len(tids), "hashes")
+
+
+if __name__ == "__main__":
+    main()
