@@ -525,8 +525,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // first radix-2 stage goes through warp shuffles), so the transform fits the 64-register budget of a 1024-thread CTA.
     // Lane `half` of a pair ends up with the output rows j' = 2m + half.  Bins k >= 1 are ordinary columns; bin 0 carries
     // two real-input columns (DC and Nyquist): its raw transform is parked in ZB and P5b, one row per thread on all threads,
-    // separates and finishes both columns (so the bin-0 warps are not the stragglers of the phase).  The two kinds of task
-    // live in different warps (no divergence): tasks [0, 31*(HK-1)) have k >= 1, tasks from K0_BASE on have k = 0.
+    // separates and finishes both columns (the bin-0 lanes only park 16 values while the other lanes of their warp work).
     float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column [31][WC]
     float2 *const ZB = G::ZB_OWN ? MQ + 2 * NT : reinterpret_cast<float2 *>(Ns);   // raw transform of the packed (DC, Nyquist) column [31][WC]
     // (job-level values are re-read from the descriptor where they are needed instead of living in registers across the phases)
@@ -537,16 +536,15 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
     {
         constexpr int HW = WC / 2;
-        constexpr int N_K1 = KCF_CHAN * (HK - 1);
-        constexpr int K0_BASE = (N_K1 + 15) & ~15;                     // 16 pair-tasks per warp
-        static_assert(2 * (K0_BASE + KCF_CHAN) <= NT, "P5 task layout");
+        // task = (channel, bin): HK bins per channel, so a half-warp holds an aligned run of bins (bank-conflict free with
+        // fpos) and every warp has the same mix of work; the bin-0 pair of a warp only parks its transform (see P5b)
+        static_assert(2 * KCF_CHAN * HK <= NT, "P5 task layout");
         const int task = tid >> 1, half = tid & 1;
-        const bool active = task < N_K1 || (task >= K0_BASE && task < K0_BASE + KCF_CHAN);
+        const bool active = task < KCF_CHAN * HK;
         const unsigned msk = __ballot_sync(0xFFFFFFFFu, active);
         if (active) {
-            const bool k0 = task >= K0_BASE;
-            const int c = k0 ? task - K0_BASE : task / (HK - 1);
-            const int k = k0 ? 0 : task - c * (HK - 1) + 1;
+            const int c = task / HK, k = task - c * HK;
+            const bool k0 = k == 0;
             float2 *const mrow = model + c * S + half * SK + k;        // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186): row j' = 2m + half
             // The model column streams in CH values at a time on two paths that alternate chunk by chunk: registers (plain loads)
             // and a private pair of shared-memory slots (cp.async), so 2 * CH values per thread are in flight without
@@ -645,8 +643,11 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // ------------------------------------------------------------------ P6: sum over the 31 channels (in channel order)
     float2 *const zf_s = FN + KCF_CHAN * WC;                           // [WC][SK]
     float *const alpha = p.alpha + (long)jd.slot * p.alpha_stride;
-    for (int e = tid; e < S; e += NT) {
-        const int j = e / SK, k = e - j * SK;
+    static_assert(S <= NT, "P6: one bin per thread");
+    if (tid < S) {
+        // threads [0, WC*HK): packed bins, a half-warp along k of one row (conflict-free with fpos); the rest: the Nyquist bins
+        const int j = tid < WC * HK ? tid / HK : tid - WC * HK, k = tid < WC * HK ? tid - j * HK : HK;
+        const int e = j * SK + k;
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < KCF_CHAN; ++c) {
