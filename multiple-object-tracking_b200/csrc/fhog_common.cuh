@@ -59,36 +59,37 @@ __device__ __forceinline__ float grad_pixel(float gx, float gy, const float *rs_
 }
 
 // ---- the same pixel step with the table indexing folded into a few integer ops (used by the fused kernels) ---------------
-struct LutConsts { int sh_rs; uint32_t mask_rs, flip_rs; int sh_rc; int bin_shift, bin_nseg; float rcp_cap; };
+struct LutConsts { int sh_rs; uint32_t mask_rs, flip_rs; int bin_shift, bin_nseg; uint32_t u_cap, m0_cap_bits; };
 
 __device__ __forceinline__ LutConsts make_lut_consts(const FhogTablesDev &t)
 {
     LutConsts k;
     k.sh_rs = 23 - t.rsqrt_bits; k.mask_rs = (2u << t.rsqrt_bits) - 1u; k.flip_rs = 1u << t.rsqrt_bits;   // [exponent LSB | top mantissa bits], parity of (e - 127)
-    k.sh_rc = 23 - t.rcp_bits; k.bin_shift = t.bin_shift; k.bin_nseg = t.bin_nseg; k.rcp_cap = t.rcp_cap;
+    k.bin_shift = t.bin_shift; k.bin_nseg = t.bin_nseg;
+    k.u_cap = t.u_cap; k.m0_cap_bits = __float_as_uint(__fmul_rn(t.rcp_cap, 0.0625f));
     return k;
 }
 
-__device__ __forceinline__ float grad_pixel_k(float gx, float gy, const float2 *rsrc_tab, const uint32_t *bn_tab, const LutConsts &k, int *bin_out)
+// One pixel of gradMag + gradQuantize for the fused kernel: returns M/16 (gradientMex.cpp:83-84, :192) with the orientation
+// bin (:90-97, :130-131) in its five low mantissa bits, which the rcpps table leaves zero (fhog_tables.cpp).
+__device__ __forceinline__ uint32_t grad_pixel_k(float gx, float gy, const float2 *rsrc_tab, const uint32_t *bn2_tab, const LutConsts &k)
 {
     const float m2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
     // rsqrtps: table[parity(e)][top mantissa bits] * 2^-q, q = e >> 1 = ((biased + 1) >> 1) - 64 (e = unbiased exponent).
-    // rcpps of that value: rcp(T * 2^-q) = rcp(T) * 2^q exactly, and rcp(T) sits next to T in the fused table.
+    // rcpps of that value: rcp(T * 2^-q) = rcp(T) * 2^q exactly, and rcp(T) / 16 sits next to T in the fused table.
     const uint32_t u = __float_as_uint(m2);
     const float2 tr = rsrc_tab[((u >> k.sh_rs) & k.mask_rs) ^ k.flip_rs];
     const uint32_t qs = (((u + 0x00800000u) >> 24) - 64u) << 23;
     float m = __uint_as_float(__float_as_uint(tr.x) - qs);
-    float M = __uint_as_float(__float_as_uint(tr.y) + qs);
-    if (u < 0x00800000u || !(m < 1e10f)) { m = 1e10f; M = k.rcp_cap; }     // rsqrtps(+0 / denormal) = +inf; MIN(., 1e10f)
+    uint32_t M0 = __float_as_uint(tr.y) + qs;
+    if (u <= k.u_cap) { m = 1e10f; M0 = k.m0_cap_bits; }                  // MIN(rsqrtps(M2), 1e10f) saturates (zero / denormal / tiny M2)
     float gn = __fmul_rn(__fmul_rn(gx, m), 10000.0f);
     gn = __uint_as_float(__float_as_uint(gn) ^ (__float_as_uint(gy) & 0x80000000u));
-    int ai = __float2int_rz(gn) + 10010;
-    ai = clampi(ai, 0, 20019);
-    const uint32_t ent = bn_tab[(gy < 0.f ? k.bin_nseg : 0) + (ai >> k.bin_shift)];
-    int bb = (int)(ent & 0xFFu) - ((uint32_t)ai >= (ent >> 8) ? 1 : 0);
-    if (bb >= 18) bb = 0;
-    *bin_out = bb;
-    return __fmul_rn(M, 0.0625f);
+    // |gn| <= 10004 for finite input, so the index needs no clamp; the unsigned min only keeps garbage input inside the table
+    const uint32_t ai = min((uint32_t)(__float2int_rz(gn) + 10010), 20019u);
+    const uint32_t ent = bn2_tab[(gy < 0.f ? k.bin_nseg : 0) + (ai >> k.bin_shift)];
+    const uint32_t bb = (ai >= (ent >> 10)) ? ((ent >> 5) & 31u) : (ent & 31u);
+    return M0 | bb;
 }
 
 }  // namespace mot

@@ -122,8 +122,29 @@ void build(FhogTables &t)
             }
     }
     t.rsrc_tab.resize(2 * t.rsqrt_tab.size());
-    for (size_t i = 0; i < t.rsqrt_tab.size(); ++i) { t.rsrc_tab[2 * i] = t.rsqrt_tab[i]; t.rsrc_tab[2 * i + 1] = emu_rcp(t, t.rsqrt_tab[i]); }
+    for (size_t i = 0; i < t.rsqrt_tab.size(); ++i) { t.rsrc_tab[2 * i] = t.rsqrt_tab[i]; t.rsrc_tab[2 * i + 1] = emu_rcp(t, t.rsqrt_tab[i]) * 0.0625f; }
     t.rcp_cap = emu_rcp(t, 1e10f);
+    {
+        // saturation MIN(rsqrt(M2), 1e10f) as a threshold on the bits of M2: bisect, then verify the equivalence on both ends
+        // of every table run of the binades around 1e-20
+        uint32_t lo = 0x007FFFFFu, hi = f2u(1.0f);            // lo saturates (denormal -> +inf), hi does not
+        while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (!(emu_rsqrt(t, u2f(mid)) < 1e10f)) lo = mid; else hi = mid; }
+        t.u_cap = lo;
+        const int K = t.rsqrt_bits;
+        for (int e = -75; e <= -55; ++e)
+            for (uint32_t key = 0; key < (1u << K); ++key)
+                for (int rep = 0; rep < 2; ++rep) {
+                    const uint32_t u = ((uint32_t)(e + 127) << 23) | (rep ? (((key + 1) << (23 - K)) - 1) : (key << (23 - K)));
+                    if ((!(emu_rsqrt(t, u2f(u)) < 1e10f)) != (u <= t.u_cap)) { t.error = "rsqrt saturation is not a single threshold"; return; }
+                }
+    }
+    t.bin2_tab.resize(t.bin_tab.size());
+    for (size_t i = 0; i < t.bin_tab.size(); ++i) {
+        const uint32_t base = t.bin_tab[i] & 0xFFu, thr = t.bin_tab[i] >> 8;
+        const uint32_t before = base >= 18 ? 0 : base, after = base == 0 ? 0 : ((base - 1) >= 18 ? 0 : base - 1);
+        if (thr != 0xFFFFFFu && (thr > 20019u || base == 0)) { t.error = "orientation-bin table: unexpected step"; return; }
+        t.bin2_tab[i] = ((thr == 0xFFFFFFu ? 0x3FFFFFu : thr) << 10) | (after << 5) | before;
+    }
     // the fused kernel carries the orientation bin (0..17) in the five low mantissa bits of M/16; rcpps results are
     // short-mantissa table values, so those bits are zero -- verified here rather than assumed
     for (size_t i = 0; i < t.rsqrt_tab.size(); ++i)

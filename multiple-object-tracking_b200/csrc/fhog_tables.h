@@ -24,14 +24,19 @@ struct FhogTables {
     // rcp: value for x in [1,2): index = mantissa >> (23 - rcp_bits)
     int rcp_bits = 0;
     std::vector<float> rcp_tab;
-    // fused form for the kernels: rsrc_tab[2i] = rsqrt_tab[i], rsrc_tab[2i+1] = rcp(rsqrt_tab[i]) (both lookups share one index);
-    // rcp_cap = rcp(1e10f), the value taken when MIN(RCPSQRT(M2), 1e10f) saturates (zero gradient)
+    // fused form for the kernels: rsrc_tab[2i] = rsqrt_tab[i], rsrc_tab[2i+1] = rcp(rsqrt_tab[i]) / 16 (both lookups share one
+    // index; the exact power-of-two factor is the M * 0.0625 of the gather, gradientMex.cpp:192, folded in);
+    // rcp_cap = rcp(1e10f), the value taken when MIN(RCPSQRT(M2), 1e10f) saturates (zero gradient);
+    // u_cap = the largest float bit pattern of M2 for which it saturates (rsqrt is non-increasing, so "saturates" is one compare)
     std::vector<float> rsrc_tab;
     float rcp_cap = 0.f;
+    uint32_t u_cap = 0;
     // orientation bin: segment = (idx + 10010) >> bin_shift, entry[sign * nseg + segment] = (thr << 8) | base,
     // bin = base - (idx + 10010 >= thr), then 18 wraps to 0.  idx = (int)(Gx * m * 10000) in [-10010, 10010).
     int bin_shift = 0, bin_nseg = 0;
     std::vector<uint32_t> bin_tab;
+    // the same step table for the fused kernel with the wrap 18 -> 0 folded in: (thr << 10) | (bin at/after thr) << 5 | (bin before thr)
+    std::vector<uint32_t> bin2_tab;
     // the raw acos table (20020 floats, index idx + 10010) kept for tests / debugging dumps
     std::vector<float> acos_tab;
 };

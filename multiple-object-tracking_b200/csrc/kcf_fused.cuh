@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     if (tid < 3) {
         // SSE tables -> shared memory (one arrival on mbar per job)
         if (tid == 0) { mbar_expect_tx(&mbar, lut_smem ? (uint32_t)(n_rs + n_bn) * 4u : 0u); if (lut_smem) bulk_g2s(R1, p.tab.rsrc_tab, n_rs * 4, &mbar); }
-        if (tid == 1 && lut_smem) bulk_g2s(R1 + n_rs, p.tab.bin_tab, n_bn * 4, &mbar);
+        if (tid == 1 && lut_smem) bulk_g2s(R1 + n_rs, p.tab.bin2_tab, n_bn * 4, &mbar);
     }
 
     const int slot = jd.slot;
@@ -301,40 +301,43 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     uint32_t mbr[G::PIX_PER_THREAD];                   // M/16 with the bin in its five low (zero) mantissa bits
     {
         const LutConsts lk = make_lut_consts(p.tab);
+        // thread -> pixels (x0 + q * XS, y): y is fixed per thread and the addresses of the 16 pixels differ by compile-time offsets
+        static_assert(NT % H0 == 0 && (H0 * W0) % NT == 0, "P1 pixel mapping");
+        constexpr int XS = NT / H0;
+        const int y = tid & (H0 - 1), x0 = tid / H0;
+        const float ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
+        const float *const g0 = F + (x0 + 1) * GS + y + 1;
         auto p1_pixels = [&](const float2 *rsrc, const uint32_t *bn) {
 #pragma unroll
             for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
-                const int idx = tid + q * NT;
-                mbr[q] = 0u;
-                if (idx < H0 * W0) {
-                    const int x = idx / H0, y = idx - x * H0;
-                    const float *g = F + (x + 1) * GS + y + 1;
-                    // grad1: one-sided difference (x1) on the border, central difference (x0.5) inside; the apron makes both one form
-                    const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f, ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
-                    const float gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), rx);
-                    const float gy = __fmul_rn(__fsub_rn(g[1], g[-1]), ry);
-                    int bb;
-                    const float m0 = grad_pixel_k(gx, gy, rsrc, bn, lk, &bb);
-                    mbr[q] = __float_as_uint(m0) | (uint32_t)bb;
-                }
+                const int x = x0 + q * XS;
+                const float *g = g0 + q * XS * GS;
+                // grad1: one-sided difference (x1) on the border, central difference (x0.5) inside; the apron makes both one form
+                const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f;
+                const float gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), rx);
+                const float gy = __fmul_rn(__fsub_rn(g[1], g[-1]), ry);
+                mbr[q] = grad_pixel_k(gx, gy, rsrc, bn, lk);
             }
         };
         if (lut_smem) p1_pixels(reinterpret_cast<const float2 *>(R1), reinterpret_cast<const uint32_t *>(R1) + n_rs);   // shared-memory tables (LDS)
-        else p1_pixels(p.tab.rsrc_tab, p.tab.bin_tab);                                                                // oversized tables stay in global memory
+        else p1_pixels(p.tab.rsrc_tab, p.tab.bin2_tab);                                                               // oversized tables stay in global memory
     }
     __syncthreads();
     // (M0, bin) overwrite the gray patch in a zero-bordered layout de-interleaved along y, [x+2][(y+2)&3][(y+2)>>2], so
     // that the cell-parallel gather below reads consecutive words and needs no bounds checks (a zero magnitude adds +0)
     constexpr int PC = G::PC;
     uint32_t *const MB = reinterpret_cast<uint32_t *>(F);
+    {
+        constexpr int XS = NT / H0;
+        const int y = tid & (H0 - 1), x0 = tid / H0;
+        uint32_t *const mb0 = MB + (x0 + 2) * PC + ((y + 2) & 3) * G::PS + ((y + 2) >> 2);
 #pragma unroll
-    for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
-        const int idx = tid + q * NT;
-        if (idx < H0 * W0) {
-            const int x = idx / H0, y = idx - x * H0;
-            const int a = (x + 2) * PC + ((y + 2) & 3) * G::PS + ((y + 2) >> 2);
-            MB[a] = mbr[q];
-            if (DUMP && p.dump.m0) { p.dump.m0[(long)job * p.dump.stride_px + idx] = __uint_as_float(mbr[q] & ~31u); p.dump.bin[(long)job * p.dump.stride_px + idx] = (unsigned char)(mbr[q] & 31u); }
+        for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
+            mb0[q * XS * PC] = mbr[q];
+            if (DUMP && p.dump.m0) {
+                const int idx = (x0 + q * XS) * H0 + y;
+                p.dump.m0[(long)job * p.dump.stride_px + idx] = __uint_as_float(mbr[q] & ~31u); p.dump.bin[(long)job * p.dump.stride_px + idx] = (unsigned char)(mbr[q] & 31u);
+            }
         }
     }
     // zero border: 8 full columns (x+2 in {0,1,W0+2..W0+7}) and 8 rows of the interior columns (y+2 in {0,1,H0+2..H0+7})

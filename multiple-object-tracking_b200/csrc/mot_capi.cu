@@ -203,8 +203,11 @@ int mot_ctx_create(mot_ctx_t **out, int device, int frame_w, int frame_h, int ma
         CU(cudaMemcpy(c->d_tab_bin, ft.bin_tab.data(), sizeof(uint32_t) * ft.bin_tab.size(), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&c->d_tab_rsrc, sizeof(float) * ft.rsrc_tab.size()));
         CU(cudaMemcpy(c->d_tab_rsrc, ft.rsrc_tab.data(), sizeof(float) * ft.rsrc_tab.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_tab_bin2, sizeof(uint32_t) * (ft.bin2_tab.size() + 4)));
+        CU(cudaMemset(c->d_tab_bin2, 0, sizeof(uint32_t) * (ft.bin2_tab.size() + 4)));
+        CU(cudaMemcpy(c->d_tab_bin2, ft.bin2_tab.data(), sizeof(uint32_t) * ft.bin2_tab.size(), cudaMemcpyHostToDevice));
         c->tab = FhogTablesDev{ c->d_tab_rsqrt, ft.rsqrt_bits, c->d_tab_rcp, ft.rcp_bits, c->d_tab_bin, ft.bin_shift, ft.bin_nseg,
-                                reinterpret_cast<const float2 *>(c->d_tab_rsrc), ft.rcp_cap };
+                                reinterpret_cast<const float2 *>(c->d_tab_rsrc), ft.rcp_cap, c->d_tab_bin2, ft.u_cap };
     } else {
         c->kal.cap = max_tracks;
         CU(cudaMalloc(&c->kal.x, sizeof(double) * 6 * max_tracks));
@@ -221,7 +224,7 @@ void mot_ctx_destroy(mot_ctx_t *c)
     cudaStreamSynchronize(c->stream);
     for (auto p : c->frame_owned) if (p) cudaFree(p);
     cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
-    cudaFree(c->d_tab_rsqrt); cudaFree(c->d_tab_rcp); cudaFree(c->d_tab_rsrc); cudaFree(c->d_tab_bin); cudaFree(c->kal.x); cudaFree(c->kal.P);
+    cudaFree(c->d_tab_rsqrt); cudaFree(c->d_tab_rcp); cudaFree(c->d_tab_rsrc); cudaFree(c->d_tab_bin); cudaFree(c->d_tab_bin2); cudaFree(c->kal.x); cudaFree(c->kal.P);
     for (auto &sc : c->classes) { cudaFree(sc.d_wy); cudaFree(sc.d_wx); cudaFree(sc.d_yf); cudaFree(sc.d_twh); cudaFree(sc.d_tww); }
     for (auto &m : c->meta_h) { if (m.model_ptr) cudaFree(m.model_ptr); if (m.alpha_ptr) cudaFree(m.alpha_ptr); }
     c->d_scratch.release();

@@ -64,7 +64,7 @@ struct mot_ctx_s {
     std::vector<SizeClass> classes;
     KcfClassDev *d_classes = nullptr;
     FhogTablesDev tab{};
-    float *d_tab_rsqrt = nullptr, *d_tab_rcp = nullptr, *d_tab_rsrc = nullptr; uint32_t *d_tab_bin = nullptr;
+    float *d_tab_rsqrt = nullptr, *d_tab_rcp = nullptr, *d_tab_rsrc = nullptr; uint32_t *d_tab_bin = nullptr, *d_tab_bin2 = nullptr;
     KalmanState kal{};
     // staging
     DevBuf<int> d_slots, d_frames, d_TD, d_assign;

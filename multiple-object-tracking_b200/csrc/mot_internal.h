@@ -36,8 +36,10 @@ struct FhogTablesDev {
     const float *rsqrt_tab; int rsqrt_bits;
     const float *rcp_tab; int rcp_bits;
     const uint32_t *bin_tab; int bin_shift, bin_nseg;
-    const float2 *rsrc_tab;           // {rsqrt_tab[i], rcp(rsqrt_tab[i])}: one look-up serves RCPSQRT and RCP
+    const float2 *rsrc_tab;           // {rsqrt_tab[i], rcp(rsqrt_tab[i]) / 16}: one look-up serves RCPSQRT and RCP (and the gather's 1/16)
     float rcp_cap;                    // rcp(1e10f)
+    const uint32_t *bin2_tab;         // bin_tab with the wrap folded in: (thr << 10) | after << 5 | before
+    uint32_t u_cap;                   // MIN(rsqrt(M2), 1e10f) saturates iff bits(M2) <= u_cap
 };
 
 // Optional stage dumps (all may be null).  Index = job * stride of that stage.
