@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         __syncthreads();
         if (tid == 0) { s_cls = p.classes[sc]; s_cls_id = sc; }
         __syncthreads();
-        if (tid >= 32 && tid < 32 + HR) wy_s[tid - 32] = s_cls.wy[tid - 32];
+        if (tid >= 32 && tid < 32 + HR) wy_s[tid - 32] = 0.5f * s_cls.wy[tid - 32];   // halved: carries the x0.5 of hogChannels (exact scaling)
         if (tid >= 64 && tid < 64 + WC) wx_s[tid - 64] = s_cls.wx[tid - 64];
     }
     const KcfClassDev &cls = s_cls;
@@ -370,8 +370,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                 for (int o = 0; o < 18; ++o) h[u][o * (WC * RS)] = 0.f;
             }
         }
-#pragma unroll 2
-        for (int dx = 0; dx < 8; ++dx) {
+#pragma unroll
+        for (int dx = 0; dx < 8; ++dx) {                                                     // fully unrolled: weights and offsets are immediates
             const float wxv = 0.125f + 0.25f * (float)(dx < 4 ? dx : 7 - dx);
 #pragma unroll
             for (int dy = 0; dy < 8; ++dy) {
@@ -451,8 +451,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             h3 = __fadd_rn(h3, __fmul_rn(fminf(__fmul_rn(rv, nv3), 0.2f), .2357f));
         }
         const int rot = (i + j) & (HR - 1);
-        F[(27 * WC + j) * HR + rot] = h0; F[(28 * WC + j) * HR + rot] = h1;
-        F[(29 * WC + j) * HR + rot] = h2; F[(30 * WC + j) * HR + rot] = h3;
+        // doubled (exact) because the window rows are stored halved
+        F[(27 * WC + j) * HR + rot] = h0 + h0; F[(28 * WC + j) * HR + rot] = h1 + h1;
+        F[(29 * WC + j) * HR + rot] = h2 + h2; F[(30 * WC + j) * HR + rot] = h3 + h3;
     }
     __syncthreads();
 
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                 float hsum = __fadd_rn(fminf(__fmul_rn(rv, n1[i + 1]), 0.2f), fminf(__fmul_rn(rv, n1[i]), 0.2f));
                 hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i + 1]), 0.2f));
                 hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i]), 0.2f));
-                const float f = __fmul_rn(__fmul_rn(hsum, .5f), __fmul_rn(wy_s[i], wxj));
+                const float f = __fmul_rn(hsum, __fmul_rn(wy_s[i], wxj));           // (hsum * 0.5) * (wy * wx): the 0.5 sits in wy_s
                 if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
             }
         } else {
