@@ -72,6 +72,29 @@ template <int N, int DIR> __device__ __forceinline__ void fft_pair(float2 (&a)[N
     fft_dif<H, DIR>(a);
 }
 
+// The same transform with the first stage fed straight from memory: ld(i) returns point i, both lanes of a pair read all N
+// points (identical addresses inside a pair: one shared-memory broadcast, no shuffles) and each keeps its half of the
+// butterflies: lane 0 u + v, lane 1 (u - v) w^i, written branch-free (sign and twiddle selected per lane).
+template <int N, int DIR, class LD> __device__ __forceinline__ void fft_pair_ld(float2 (&a)[N / 2], int half, unsigned mask, LD ld)
+{
+    constexpr int H = N / 2;
+    const float sg = half ? -1.f : 1.f;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float2 u = ld(i), v = ld(i + H);
+        const float2 r = make_float2(fmaf(sg, v.x, u.x), fmaf(sg, v.y, u.y));       // exactly u + v or u - v
+        const int idx = (i * (64 / N)) & 63;
+        if (idx == 0) a[i] = r;
+        else {
+            const float c = half ? tw::C64[idx] : 1.f;
+            const float sn = half ? (DIR < 0 ? -tw::S64[idx] : tw::S64[idx]) : 0.f;
+            a[i] = make_float2(r.x * c - r.y * sn, r.x * sn + r.y * c);
+        }
+    }
+    __syncwarp(mask);       // in-place callers: every load of the pair precedes either lane's stores
+    fft_dif<H, DIR>(a);
+}
+
 // position of packed bin k in row j of the spectrum buffer: k XOR f(j), with f chosen so that every access pattern of the
 // kernels is bank-conflict free for 64-bit words: (a) the row pass writes rows j = 0..15 / 16..31 at a fixed k (f is a
 // bijection on each half), (b) the column pass reads rows i and i + WC/2 in one instruction (f differs in the top bit),

@@ -565,9 +565,10 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                 cp_async_commit();
             }
             float2 a[HW];
-#pragma unroll
-            for (int i = 0; i < HW; ++i) { const int j = half * HW + i; a[i] = F2[(c * WC + j) * HK + fpos<HK, WC>(k, j)]; }
-            fft_pair<WC, -1>(a, half, msk);
+            {
+                const float2 *const col = F2 + c * WC * HK;
+                fft_pair_ld<WC, -1>(a, half, msk, [&](int j) { return col[j * HK + fpos<HK, WC>(k, j)]; });
+            }
             if (k0) {
                 // slot 0 = FFT(DC_j + i Nyq_j): parked as it is; P5b separates the two columns with all threads
 #pragma unroll
