@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libmot_b200.so")
+LIB_PATH = os.environ.get("MOT_B200_LIB") or os.path.join(PKG_DIR, "libmot_b200.so")   # override: A/B builds side by side on one GPU box
 
 TRACKER_KALMAN, TRACKER_KCF = 0, 1
 COST_REF_CENTROID, COST_IOU_CLAMPED = 0, 1
