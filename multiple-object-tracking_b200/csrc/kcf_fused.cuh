@@ -77,7 +77,8 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one instruction pulls a whole (16-byte aligned, 16-byte multiple) range into L2
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
 
 // ---- bulk asynchronous copies global -> shared on an mbarrier (the copy engine that TMA uses; SASS: UBLKCP) --------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -221,9 +222,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // sees L2 latency instead of HBM latency (there is no shared memory left to stage it in).
     if (MODE == KCF_MODE_PREDICT || !first_update) {
         const char *mp = reinterpret_cast<const char *>(p.model + (long)slot * p.model_stride);
-        for (int o = tid * 128; o < KCF_CHAN * S * 8; o += NT * 128) prefetch_l2(mp + o);
+        if (tid == 96) prefetch_l2_bulk(mp, KCF_CHAN * S * 8);
     }
-    if (tid < (S * 4 + 127) / 128) prefetch_l2(reinterpret_cast<const char *>(p.alpha + (long)slot * p.alpha_stride) + tid * 128);
+    if (tid == 97) prefetch_l2_bulk(p.alpha + (long)slot * p.alpha_stride, (S * 4 + 15) & ~15);
 
     if (p.gray != nullptr) {
         const float *src = p.gray + (long)job * p.gray_stride;
@@ -391,15 +392,15 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         for (int u = 0; u < CPT; ++u) {
             if (!live[u]) continue;
             const int cx = ccx[u], cy = ccy[u];
+            // boundary cells x 8/7 per touching side (gradientMex.cpp:226-229); a cell touches at most one side per axis, and
+            // multiplying by 1.0f is the identity, so two unconditional products reproduce the four conditional ones
+            const float sx = (cx == 0 || cx == WC - 1) ? 8.f / 7.f : 1.f, sy = (cy == 0 || cy == HR - 1) ? 8.f / 7.f : 1.f;
             float e = 0.f;
             float r[18];
 #pragma unroll
             for (int o = 0; o < 18; ++o) {
                 float v = h[u][o * (WC * RS)];
-                if (cx == 0) v = __fmul_rn(v, 8.f / 7.f);
-                if (cy == 0) v = __fmul_rn(v, 8.f / 7.f);
-                if (cx == WC - 1) v = __fmul_rn(v, 8.f / 7.f);
-                if (cy == HR - 1) v = __fmul_rn(v, 8.f / 7.f);
+                v = __fmul_rn(__fmul_rn(v, sx), sy);
                 h[u][o * (WC * RS)] = v; r[o] = v;
             }
             // cell energy over the 9 contrast-insensitive bins, R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309, :242-243)
