@@ -662,6 +662,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         // threads [0, WC*HK): packed bins, a half-warp along k of one row (conflict-free with fpos); the rest: the Nyquist bins
         const int j = tid < WC * HK ? tid / HK : tid - WC * HK, k = tid < WC * HK ? tid - j * HK : HK;
         const int e = j * SK + k;
+        // per-bin inputs first: their global-memory latency hides behind the 31-channel sum
+        const float al0 = alpha[e];
+        const float yf0 = (MODE == KCF_MODE_UPDATE) ? cls.yf_re[e] : 0.f;
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < KCF_CHAN; ++c) {
@@ -669,7 +672,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             if (c == 0) acc = v; else { acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); }
         }
         if (MODE == KCF_MODE_PREDICT) {
-            const float al = alpha[e];
+            const float al = al0;
             acc.x = __fmul_rn(__fmul_rn(acc.x, al), cls.norm);         // kcf.cpp:356-357
             acc.y = __fmul_rn(__fmul_rn(acc.y, al), cls.norm);
             zf_s[e] = acc;
@@ -677,8 +680,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         } else {
             const float kf = __fmul_rn(acc.x, cls.norm);               // kcf.cpp:295-303
             if (DUMP && p.dump.kf) p.dump.kf[(long)job * p.dump.stride_spec + e] = kf;
-            const float an = __fdiv_rn(cls.yf_re[e], __fadd_rn(kf, p.lamda));                // kcf.cpp:373
-            alpha[e] = __fadd_rn(__fmul_rn(omf, alpha[e]), __fmul_rn(fac, an));              // kcf.cpp:374
+            const float an = __fdiv_rn(yf0, __fadd_rn(kf, p.lamda));                         // kcf.cpp:373
+            alpha[e] = __fadd_rn(__fmul_rn(omf, al0), __fmul_rn(fac, an));                   // kcf.cpp:374
         }
     }
     if (MODE == KCF_MODE_UPDATE) {
