@@ -148,18 +148,25 @@ void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *v
 int mot_td_overlay(mot_td_t *td);
 int mot_td_last(mot_td_t *td, mot_bbox_t *predicted, int *assigned_trackers);
 
-/* ---- the same frame loop with the track tables resident on the DEVICE (Kalman kind): five launches per frame for all
- *      streams, no host synchronisation (replaces top/td.cpp:343-644 including the bookkeeping,
+/* ---- the same frame loop with the track tables resident on the DEVICE: for the Kalman kind five launches per frame for all
+ *      streams, for the KCF kind the fused kernels over per-class job lists built on the device; no host synchronisation (replaces top/td.cpp:343-644 including the bookkeeping,
  *      the stable compaction of lost tracks :585-609 and the spawn order :612-644) --------------------------------- */
 typedef struct mot_tdd_s mot_tdd_t;
 /* n_streams independent streams, at most cap tracks (reference: 256, top/td.cpp:12) and max_det detections
- * (reference: 128, top/cnntype.h:46) each, both <= 1024.  The context must be a Kalman context with >= n_streams*cap slots. */
+ * (reference: 128, top/cnntype.h:46) each, both <= 1024.  The context needs >= n_streams*cap free slots and no host-managed
+ * trackers.  KCF contexts: stream s reads frame slot s (mot_frame_upload / mot_frame_bind_device before each step), and only
+ * detections whose window has a fused kernel (cell grid sides 8, 16 or 32, i.e. 32..35, 64..67 or 128..131 pixels per side)
+ * can spawn a track; the others are counted (mot_tdd_dropped) -- the host-side loop mot_td_step serves every size. */
 int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *ctx, int n_streams, int cap, int max_det, int cost_mode);
 void mot_tdd_destroy(mot_tdd_t *tdd);
 /* detections already on the device: d_dets[n_streams][max_det], d_ndet[n_streams]; asynchronous on the context stream */
 int mot_tdd_step_dev(mot_tdd_t *tdd, const mot_bbox_t *d_dets, const int *d_ndet);
 /* detections in host arrays (dets[s] points at ndet[s] boxes); staged, uploaded and stepped; asynchronous */
 int mot_tdd_step(mot_tdd_t *tdd, const mot_bbox_t *const *dets, const int *ndet);
+/* KCF kind: declare the window sizes (pixels) the detections will have; the kernels of all other classes are not launched */
+int mot_tdd_kcf_windows(mot_tdd_t *tdd, int n, const int *rows, const int *cols);
+/* KCF kind: number of detections of stream s that could not spawn a track so far (synchronises) */
+int mot_tdd_dropped(mot_tdd_t *tdd, int stream);
 /* snapshot of stream s (synchronises); returns the number of live tracks or a negative error */
 int mot_tdd_read(mot_tdd_t *tdd, int stream, uint32_t *tid, mot_bbox_t *boxes, int *age, int *vis, int *invis);
 

@@ -109,6 +109,7 @@ struct JobDesc {
     const uint8_t *frame;             // p.frame_ptr[p.frames[job]] (null with pre-cropped gray input)
     int slot, rows, cols, size_class, first_update;
     float scale_horiz, scale_vert;
+    int box_idx;                      // where the job's box lives in p.boxes (job index, or p.box_index[job])
 };
 
 template <int HR, int WC, int MODE, bool DUMP>
@@ -148,7 +149,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     auto fetch_desc = [&](int jb, JobDesc *d) {
         const int sl = p.slots[jb];
         const KcfMeta *m = p.meta + sl;
-        d->box = p.boxes[jb];
+        const int bi = p.box_index ? p.box_index[jb] : jb;
+        d->box = p.boxes[bi]; d->box_idx = bi;
         d->frame = (p.gray == nullptr) ? p.frame_ptr[p.frames[jb]] : nullptr;
         d->slot = sl; d->rows = m->rows; d->cols = m->cols; d->size_class = m->size_class; d->first_update = m->first_update;
         d->pos = m->pos; d->scale_horiz = m->scale_horiz; d->scale_vert = m->scale_vert;
@@ -173,17 +175,19 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // Persistent CTA: jobs blockIdx.x, blockIdx.x + gridDim.x, ...; the crop of the NEXT job streams into shared memory
     // while the spectral phases of the current one run (the staging area is free from P5 on).
     uint32_t phase = 0;
+    // the job count may live on the device (job lists built by a previous kernel, csrc/td_device.cu); p.n_jobs then bounds it
+    const int n_jobs = p.n_jobs_dev ? min(*p.n_jobs_dev, p.n_jobs) : p.n_jobs;
     if (tid == 0) s_cls_id = -1;
-    if ((tid >> 5) == ROI_WARP && (int)blockIdx.x < p.n_jobs) {
+    if ((tid >> 5) == ROI_WARP && (int)blockIdx.x < n_jobs) {
         if ((tid & 31) == 0) {
             fetch_desc(blockIdx.x, &s_desc[0]);
-            if ((int)(blockIdx.x + gridDim.x) < p.n_jobs) fetch_desc(blockIdx.x + gridDim.x, &s_desc[1]);
+            if ((int)(blockIdx.x + gridDim.x) < n_jobs) fetch_desc(blockIdx.x + gridDim.x, &s_desc[1]);
         }
         __syncwarp();
         issue_roi(s_desc[0].box, s_desc[0].frame);
     }
     int it = 0;
-    for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, phase ^= 1u, ++it) {
+    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x, phase ^= 1u, ++it) {
     __syncthreads();                                   // the previous job is done with every shared-memory region
     const JobDesc &jd = s_desc[it & 3];
     // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
@@ -527,10 +531,10 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     }
     __syncthreads();
     // The histograms are consumed: the staging area is free again -> start streaming the next job's crop underneath P5..P7
-    if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < p.n_jobs) {
+    if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < n_jobs) {
         const JobDesc &nd = s_desc[(it + 1) & 3];
         issue_roi(nd.box, nd.frame);
-        if ((tid & 31) == 0 && job + 2 * (int)gridDim.x < p.n_jobs) fetch_desc(job + 2 * gridDim.x, &s_desc[(it + 2) & 3]);
+        if ((tid & 31) == 0 && job + 2 * (int)gridDim.x < n_jobs) fetch_desc(job + 2 * gridDim.x, &s_desc[(it + 2) & 3]);
     }
 
     // ------------------------------------------------------------------ P5: complex FFT along the WC columns + spectral work
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             const float kf = __fmul_rn(acc.x, cls.norm);               // kcf.cpp:295-303
             if (DUMP && p.dump.kf) p.dump.kf[(long)job * p.dump.stride_spec + e] = kf;
             const float an = __fdiv_rn(yf0, __fadd_rn(kf, p.lamda));                         // kcf.cpp:373
-            alpha[e] = __fadd_rn(__fmul_rn(omf, al0), __fmul_rn(fac, an));                   // kcf.cpp:374
+            alpha[e] = first ? an : __fadd_rn(__fmul_rn(omf, al0), __fmul_rn(fac, an));      // kcf.cpp:374 (factor 1 on the first update: the old value drops out)
         }
     }
     if (MODE == KCF_MODE_UPDATE) {
@@ -768,7 +772,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             pos.l = clampi(pos.l, 0, p.frame_w - 1); pos.r = clampi(pos.r, 0, p.frame_w - 1);
             pos.t = clampi(pos.t, 0, p.frame_h - 1); pos.b = clampi(pos.b, 0, p.frame_h - 1);
         }
-        p.boxes[job] = pos;
+        p.boxes[jd.box_idx] = pos;
     }
     }   // persistent job loop
 }

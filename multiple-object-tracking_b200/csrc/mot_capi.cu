@@ -157,6 +157,28 @@ static int sync_frame_ptrs(mot_ctx_t *c)
     return 0;
 }
 
+extern "C" { static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, const int *d_frames, mot_bbox_t *d_boxes, int clamp); }
+
+int mot_ctx_kcf_class(mot_ctx_t *c, int hr, int wc, int *cls_out) { return get_class(c, hr, wc, cls_out); }
+
+int mot_ctx_frames_ready(mot_ctx_t *c)
+{
+    { const int rc = sync_frame_ptrs(c); if (rc) return rc; }
+    return wait_frames(c, 0, nullptr);
+}
+
+int mot_ctx_kcf_launch(mot_ctx_t *c, int mode, int cls, int n_max, const int *n_dev, const int *slots, const int *frames,
+                       mot_bbox_t *boxes, const int *box_index, int clamp)
+{
+    if (cls < 0 || cls >= (int)c->classes.size() || !c->classes[cls].fast) return fail(MOT_ERR_SHAPE, "class %d has no fused kernel", cls);
+    KcfLaunch L; fill_launch(c, L, n_max, slots, frames, boxes, clamp);
+    L.n_jobs_dev = n_dev; L.box_index = box_index; L.dump = KcfDump{};
+    const int rc = kcf_launch_fast(mode, c->classes[cls].hr, c->classes[cls].wc, L, c->stream);
+    if (rc) return fail(MOT_ERR_CUDA, "KCF launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
+}
+
 // =====================================================================================================================
 extern "C" {
 

@@ -61,6 +61,8 @@ struct KcfDump {
 
 struct KcfLaunch {
     int n_jobs;
+    const int *n_jobs_dev;            // optional: the job count lives on the device (min'ed with n_jobs, which then sizes the grid)
+    const int *box_index;             // optional: job j's box is boxes[box_index[j]] instead of boxes[j]
     const int *slots;                 // [n] track slot of each job
     const int *frames;                // [n] frame slot of each job (ignored when gray != null)
     mot_bbox_t *boxes;                // [n] predict: in = crop box, out = predicted box; update: in = new position / crop box

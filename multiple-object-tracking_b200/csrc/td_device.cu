@@ -1,11 +1,20 @@
-// td_device.cu -- the frame loop of the reference with the track table RESIDENT ON THE DEVICE (Kalman tracker kind).
+// td_device.cu -- the frame loop of the reference with the track table RESIDENT ON THE DEVICE (both tracker kinds).
 //
 // One iteration of pthread_mtcnn_trkn (top/td.cpp:343-644) for S independent streams is five launches and no host
 // synchronisation: kalman_predict (+clamp, :344-384) -> cost matrices + Munkres (:386-470) -> td_scatter (:472-547,
 // :550-556 bookkeeping) -> kalman_update (:539, :581) -> td_lifecycle (delete lost with stable compaction :585-609, spawn
 // per unassigned detection in ascending order :612-644).  The bookkeeping, the order of the track table and the ids are
 // the reference's, per stream; host/td_loop.cpp is the same loop with the table on the host.
-// Stream s owns the Kalman slots [s*cap, (s+1)*cap).
+// Stream s owns the tracker slots [s*cap, (s+1)*cap).
+//
+// KCF kind: the same loop with the fused KCF kernels in place of the Kalman ones.  The track table does not say which
+// window class a track has in a form the host could read without synchronising, so every frame a small kernel sorts the
+// live tracks into one job list per fused window class (cell grids with sides 8/16/32); the fused kernels take their job
+// count from the device and exit at once when their list is empty.  tracker_new (trackers/kcf.cpp:484-491, :139-213) runs
+// inside the lifecycle kernel (metadata only: model and alpha are fully written by the first update), followed by one
+// more update launch over the tracks spawned in this frame (the reference's first update, top/td.cpp:629-641).  Stream s
+// reads frame slot s.  Detections whose window has no fused kernel cannot spawn here and are counted (mot_tdd_dropped);
+// the host-side loop (host/td_loop.cpp) serves those through the any-size path.
 #include "mot_ctx.h"
 
 namespace mot {
@@ -17,7 +26,38 @@ struct TddState {
     int *assign;                                 // [S][md] rows of the cost matrix -> column
     int *assigned_detected;                      // [S][max_det]
     int md;
+    // KCF kind
+    int kcf, frame_w, frame_h;
+    int cls_id[9];                               // context class index of fused class 3*hi + wi (cell sides 8, 16, 32); -1: disabled
+    KcfMeta *meta;
+    int *jl_slot, *jl_frame, *jl_box, *jl_count; // [9][S*cap] x 3, [9]: live tracks grouped by window class
+    int *sp_slot, *sp_frame, *sp_box, *sp_count; // the same for the tracks spawned in this frame
+    int *dropped;                                // [S] detections that could not spawn (no fused kernel for their window)
 };
+
+__device__ __forceinline__ int fused_side(int cells) { return cells == 8 ? 0 : cells == 16 ? 1 : cells == 32 ? 2 : -1; }
+__device__ __forceinline__ int fused_class_of(const TddState &st, int rows, int cols)
+{
+    if (rows > st.frame_h || cols > st.frame_w) return -1;
+    const int hi = fused_side(rows / KCF_CELL), wi = fused_side(cols / KCF_CELL);
+    if (hi < 0 || wi < 0) return -1;
+    return st.cls_id[3 * hi + wi] >= 0 ? 3 * hi + wi : -1;
+}
+
+// live tracks -> one job list per window class (order inside a list is irrelevant: jobs are independent)
+__global__ void td_joblist_kernel(TddState st)
+{
+    const int s = blockIdx.x, T = st.ntracks[s];
+    const long N = (long)st.S * st.cap;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const long e = (long)s * st.cap + i;
+        const int slot = st.slot[e];
+        const KcfMeta *m = st.meta + slot;
+        const int k = 3 * fused_side(m->hr) + fused_side(m->wc);
+        const int at = atomicAdd(&st.jl_count[k], 1);
+        st.jl_slot[k * N + at] = slot; st.jl_frame[k * N + at] = s; st.jl_box[k * N + at] = (int)e;
+    }
+}
 
 // scatter of the assignment + bookkeeping of assigned / unassigned tracks (top/td.cpp:472-502, 512-556)
 __global__ void td_scatter_kernel(TddState st, const mot_bbox_t *dets, const int *ndet)
@@ -82,7 +122,14 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
     if (tid < 32) used[tid] = 0;
     __syncthreads();
     for (int i = tid; i < n2; i += NTH) { const int ls = st.slot[(long)s * cap + i] - s * cap; atomicOr(&used[ls >> 5], 1u << (ls & 31)); }
-    for (int j = tid; j < D; j += NTH) pos[j] = st.assigned_detected[(long)s * st.max_det + j] < 0 ? 1 : 0;
+    for (int j = tid; j < D; j += NTH) {
+        bool cand = st.assigned_detected[(long)s * st.max_det + j] < 0;
+        if (cand && st.kcf) {
+            const mot_bbox_t b = dets[(long)s * st.max_det + j];
+            if (fused_class_of(st, b.b - b.t + 1, b.r - b.l + 1) < 0) { cand = false; atomicAdd(&st.dropped[s], 1); }
+        }
+        pos[j] = cand ? 1 : 0;
+    }
     __syncthreads();
     if (tid == 0) {
         int nf = 0;
@@ -102,6 +149,19 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
         const mot_bbox_t b = dets[(long)s * st.max_det + j];
         const int sl = s * cap + freeid[rk];
         st.tid[o] = id0 + (uint32_t)rk; st.slot[o] = sl; st.age[o] = 0; st.vis[o] = 0; st.invis[o] = 0; st.bbox[o] = b;      // :618-627
+        if (st.kcf) {
+            // tracker_new, trackers/kcf.cpp:484-491 + kcf_init :139-213: sizes frozen, pos = box, scales 1, first_update set
+            KcfMeta m{};
+            m.rows = b.b - b.t + 1; m.cols = b.r - b.l + 1; m.hr = m.rows / KCF_CELL; m.wc = m.cols / KCF_CELL;
+            m.pos = b; m.scale_horiz = 1.0f; m.scale_vert = 1.0f; m.first_update = 1;
+            const int k = fused_class_of(st, m.rows, m.cols);
+            m.size_class = st.cls_id[k]; m.model_ptr = nullptr; m.alpha_ptr = nullptr;
+            st.meta[sl] = m;
+            const long N = (long)st.S * cap;
+            const int at = atomicAdd(&st.sp_count[k], 1);
+            st.sp_slot[k * N + at] = sl; st.sp_frame[k * N + at] = s; st.sp_box[k * N + at] = (int)o;
+            continue;
+        }
         // tracker_new, trackers/kalman.cpp:147-163: x0 = [l,t,r,b,0,0], P0 = 1e4 I
         const double x0[6] = { (double)b.l, (double)b.t, (double)b.r, (double)b.b, 0.0, 0.0 };
         for (int k = 0; k < 6; ++k) kal.x[(long)k * kal.cap + sl] = x0[k];
@@ -130,10 +190,13 @@ struct mot_tdd_s {
 
 extern "C" {
 
+static int tdd_step_kcf(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet);
+
 int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int max_det, int cost_mode)
 {
     if (!out || !c || n_streams <= 0 || cap <= 0 || cap > 1024 || max_det <= 0 || max_det > 1024) return mot_fail(MOT_ERR_ARG, "mot_tdd_create: bad argument (cap and max_det must be in 1..1024)");
-    if (c->kind != MOT_TRACKER_KALMAN) return mot_fail(MOT_ERR_KIND, "the device-resident frame loop is available for Kalman contexts");
+    const bool kcf = c->kind == MOT_TRACKER_KCF;
+    if (kcf && c->n_frames < n_streams) return mot_fail(MOT_ERR_ARG, "the KCF frame loop reads stream s from frame slot s: the context has %d frame slots, %d are needed", c->n_frames, n_streams);
     if ((long)n_streams * cap > c->max_tracks) return mot_fail(MOT_ERR_CAPACITY, "context has %d track slots, %d streams x %d are needed", c->max_tracks, n_streams, cap);
     for (char u : c->used) if (u) return mot_fail(MOT_ERR_ARG, "the context already holds host-managed trackers");
     CU(cudaSetDevice(c->device));
@@ -151,6 +214,18 @@ int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int ma
     CU(cudaMemsetAsync(st.slot, 0xFF, sizeof(int) * n, c->stream));
     CU(cudaMemsetAsync(st.age, 0, sizeof(int) * n, c->stream)); CU(cudaMemsetAsync(st.vis, 0, sizeof(int) * n, c->stream)); CU(cudaMemsetAsync(st.invis, 0, sizeof(int) * n, c->stream));
     CU(cudaMemsetAsync(st.bbox, 0, sizeof(mot_bbox_t) * n, c->stream)); CU(cudaMemsetAsync(st.tid, 0, sizeof(uint32_t) * n, c->stream));
+    st.kcf = kcf ? 1 : 0; st.frame_w = c->W; st.frame_h = c->H; st.meta = c->d_meta;
+    for (int k = 0; k < 9; ++k) st.cls_id[k] = -1;
+    if (kcf) {
+        static const int side[3] = { 8, 16, 32 };
+        for (int hi = 0; hi < 3; ++hi)
+            for (int wi = 0; wi < 3; ++wi) { const int rc = mot_ctx_kcf_class(c, side[hi], side[wi], &st.cls_id[3 * hi + wi]); if (rc) { delete t; return rc; } }
+        CU(cudaMalloc(&st.jl_slot, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.jl_frame, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.jl_box, sizeof(int) * 9 * n));
+        CU(cudaMalloc(&st.sp_slot, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.sp_frame, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.sp_box, sizeof(int) * 9 * n));
+        CU(cudaMalloc(&st.jl_count, sizeof(int) * 18)); st.sp_count = st.jl_count + 9;
+        CU(cudaMalloc(&st.dropped, sizeof(int) * n_streams));
+        CU(cudaMemsetAsync(st.dropped, 0, sizeof(int) * n_streams, c->stream));
+    }
     for (long i = 0; i < (long)n_streams * cap; ++i) c->used[i] = 1;        // these slots now belong to the device-side tables
     c->free_slots.erase(std::remove_if(c->free_slots.begin(), c->free_slots.end(), [&](int s) { return s < n_streams * cap; }), c->free_slots.end());
     *out = t;
@@ -164,10 +239,40 @@ void mot_tdd_destroy(mot_tdd_t *t)
     TddState &st = t->st;
     cudaFree(st.ntracks); cudaFree(st.tracker_id); cudaFree(st.tid); cudaFree(st.slot); cudaFree(st.age); cudaFree(st.vis); cudaFree(st.invis);
     cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost);
+    if (st.kcf) { cudaFree(st.jl_slot); cudaFree(st.jl_frame); cudaFree(st.jl_box); cudaFree(st.sp_slot); cudaFree(st.sp_frame); cudaFree(st.sp_box); cudaFree(st.jl_count); cudaFree(st.dropped); }
     if (t->graph) cudaGraphExecDestroy(t->graph);
     t->d_dets.release(); t->d_ndet.release(); t->h_dets.release(); t->h_ndet.release();
     for (long i = 0; i < (long)st.S * st.cap; ++i) { t->ctx->used[i] = 0; t->ctx->free_slots.push_back((int)i); }
     delete t;
+}
+
+// KCF kind: job lists -> predict per class -> association -> scatter -> update per class -> lifecycle -> first update of the spawned
+static int tdd_step_kcf(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet)
+{
+    mot_ctx_t *c = t->ctx; TddState &st = t->st;
+    const int n = st.S * st.cap;
+    int rc = mot_ctx_frames_ready(c); if (rc) return rc;
+    CU(cudaMemsetAsync(st.jl_count, 0, sizeof(int) * 18, c->stream));
+    td_joblist_kernel<<<st.S, 256, 0, c->stream>>>(st);
+    auto per_class = [&](int mode, const int *count, const int *slot, const int *frame, const int *box, int clamp) {
+        for (int k = 0; k < 9; ++k) {
+            if (st.cls_id[k] < 0) continue;
+            const int r = mot_ctx_kcf_launch(c, mode, st.cls_id[k], n, count + k, slot + (long)k * n, frame + (long)k * n, st.bbox, box + (long)k * n, clamp);
+            if (r) return r;
+        }
+        return 0;
+    };
+    rc = per_class(KCF_MODE_PREDICT, st.jl_count, st.jl_slot, st.jl_frame, st.jl_box, 1); if (rc) return rc;       // top/td.cpp:344-384
+    rc = mot_associate_batch_dev(c, st.S, st.ntracks, d_ndet, st.bbox, st.cap, d_dets, st.max_det, t->cost_mode,
+                                 t->d_dist, (long)st.md * st.md, st.assign, st.md, t->d_cost, st.md);
+    if (rc) return rc;
+    td_scatter_kernel<<<st.S, 256, 0, c->stream>>>(st, d_dets, d_ndet);
+    rc = per_class(KCF_MODE_UPDATE, st.jl_count, st.jl_slot, st.jl_frame, st.jl_box, 0); if (rc) return rc;        // top/td.cpp:512-582
+    td_lifecycle_kernel<<<st.S, 256, sizeof(int) * 2048, c->stream>>>(st, c->kal, d_dets, d_ndet);
+    rc = per_class(KCF_MODE_UPDATE, st.sp_count, st.sp_slot, st.sp_frame, st.sp_box, 0); if (rc) return rc;        // top/td.cpp:629-641
+    CU(cudaGetLastError());
+    c->launches += 3;           // job lists, scatter, lifecycle (the fused launches and the association count themselves)
+    return 0;
 }
 
 /* detections: device arrays dets[S][max_det], ndet[S]; everything is enqueued on the context stream, nothing synchronises */
@@ -177,6 +282,7 @@ int mot_tdd_step_dev(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet)
     mot_ctx_t *c = t->ctx; TddState &st = t->st;
     CU(cudaSetDevice(c->device));
     const int n = st.S * st.cap;
+    if (st.kcf) return tdd_step_kcf(t, d_dets, d_ndet);
     int rc = kalman_predict(c->kal, n, st.slot, st.bbox, 1, c->W, c->H, c->stream);
     if (rc) return mot_fail(MOT_ERR_CUDA, "kalman_predict launch failed (%d)", rc);
     rc = mot_associate_batch_dev(c, st.S, st.ntracks, d_ndet, st.bbox, st.cap, d_dets, st.max_det, t->cost_mode,
@@ -204,6 +310,12 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
         t->h_ndet.p[s] = ndet[s];
         if (ndet[s]) memcpy(t->h_dets.p + (size_t)s * st.max_det, dets[s], sizeof(mot_bbox_t) * ndet[s]);
     }
+    if (st.kcf) {
+        // the KCF sequence waits for frame uploads recorded on another stream, which a captured graph would freeze: plain launches
+        CU(cudaMemcpyAsync(t->d_dets.p, t->h_dets.p, sizeof(mot_bbox_t) * (size_t)st.S * st.max_det, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(t->d_ndet.p, t->h_ndet.p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream));
+        return mot_tdd_step_dev(t, t->d_dets.p, t->d_ndet.p);
+    }
     if (t->graph && t->graph_stream == c->stream) { CU(cudaGraphLaunch(t->graph, c->stream)); c->launches += 6; return 0; }
     if (t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
     // first call (or the stream changed): make every lazy allocation happen outside the capture, then record the sequence
@@ -224,6 +336,41 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
     CU(cudaGraphLaunch(t->graph, c->stream));
     c->launches += 6;
     return 0;
+}
+
+/* KCF kind: restrict the loop to the listed window sizes (pixels); detections of any other size are counted as dropped */
+int mot_tdd_kcf_windows(mot_tdd_t *t, int n, const int *rows, const int *cols)
+{
+    if (!t || n < 0 || (n && (!rows || !cols))) return mot_fail(MOT_ERR_ARG, "mot_tdd_kcf_windows: bad argument");
+    if (!t->st.kcf) return mot_fail(MOT_ERR_KIND, "not a KCF frame loop");
+    static const int side[3] = { 8, 16, 32 };
+    int keep[9] = { 0 };
+    for (int i = 0; i < n; ++i) {
+        int hi = -1, wi = -1;
+        for (int q = 0; q < 3; ++q) { if (rows[i] / KCF_CELL == side[q]) hi = q; if (cols[i] / KCF_CELL == side[q]) wi = q; }
+        if (hi < 0 || wi < 0) return mot_fail(MOT_ERR_SHAPE, "window %dx%d px has no fused kernel (cell sides 8, 16, 32)", rows[i], cols[i]);
+        keep[3 * hi + wi] = 1;
+    }
+    for (int hi = 0; hi < 3; ++hi)
+        for (int wi = 0; wi < 3; ++wi) {
+            int &id = t->st.cls_id[3 * hi + wi];
+            if (!keep[3 * hi + wi]) id = -1;
+            else if (id < 0) { const int rc = mot_ctx_kcf_class(t->ctx, side[hi], side[wi], &id); if (rc) return rc; }
+        }
+    return 0;
+}
+
+/* KCF kind: detections of stream s that could not spawn a track so far (window without a fused kernel); synchronises */
+int mot_tdd_dropped(mot_tdd_t *t, int s)
+{
+    if (!t || s < 0 || s >= t->st.S) return mot_fail(MOT_ERR_ARG, "mot_tdd_dropped: bad argument");
+    if (!t->st.kcf) return 0;
+    mot_ctx_t *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    int n = 0;
+    CU(cudaMemcpy(&n, t->st.dropped + s, sizeof(int), cudaMemcpyDeviceToHost));
+    return n;
 }
 
 /* snapshot of one stream's track table (synchronises); returns the number of tracks */

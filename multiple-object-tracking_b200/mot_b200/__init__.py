@@ -24,7 +24,7 @@ EXPORTS = [
     "mot_predict_batch", "mot_update_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
     "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_get", "mot_td_last", "mot_td_overlay",
-    "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_read",
+    "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_read", "mot_tdd_kcf_windows", "mot_tdd_dropped",
     "mot_debug_enable_dumps", "mot_debug_fetch", "mot_debug_state", "mot_debug_tables",
 ]
 
@@ -268,7 +268,7 @@ class Context:
 
 
 class DeviceLoop:
-    """mot_tdd_*: the frame loop with the track tables resident on the device (Kalman contexts)."""
+    """mot_tdd_*: the frame loop with the track tables resident on the device (Kalman or KCF contexts; KCF: stream s reads frame slot s)."""
 
     def __init__(self, ctx, n_streams, cap=256, max_det=128, cost_mode=COST_REF_CENTROID):
         self.ctx, self.n, self.cap = ctx, n_streams, cap
@@ -284,6 +284,16 @@ class DeviceLoop:
 
     def step_dev(self, d_dets, d_ndet):
         _chk(lib().mot_tdd_step_dev(self.h, C.c_void_p(d_dets), C.c_void_p(d_ndet)))
+
+    def kcf_windows(self, sizes):
+        r = np.array([a for a, _ in sizes], np.int32); c = np.array([b for _, b in sizes], np.int32)
+        _chk(lib().mot_tdd_kcf_windows(self.h, len(r), _p(r), _p(c)))
+
+    def dropped(self, s):
+        n = lib().mot_tdd_dropped(self.h, s)
+        if n < 0:
+            _chk(n)
+        return n
 
     def tracks(self, s):
         tid = np.zeros(self.cap, np.uint32); boxes = np.zeros(self.cap, BBOX_DTYPE)

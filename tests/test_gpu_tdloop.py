@@ -129,3 +129,55 @@ def test_device_resident_loop_trace(oracle, mode):
     for r in refs:
         r.close()
     ctx.close()
+
+
+def test_device_resident_kcf_loop_trace(oracle):
+    """The KCF kind of mot_tdd_*: job lists per window class built on the device, fused predict / update over them,
+    tracker_new + first update inside the loop.  Trace-identical to the oracle's KCF loop for three streams with different
+    window classes (64x64 and 128x128 px detections in the same context) through births, misses and deaths; a detection
+    whose window has no fused kernel is dropped and counted, and changes nothing else."""
+    require_gpu()
+    M = mot()
+    W, H, ns, cap = 1280, 720, 3, 24
+    wins = [64, 128, 64]
+    scs = [Scene(900 + 7 * s, W, H, 6 if wins[s] == 128 else 9, tsize=wins[s] * 5 // 8, win=wins[s]) for s in range(ns)]
+    ctx = M.Context(W, H, max_tracks=(ns + 1) * cap, n_frame_slots=ns + 1, kind=M.TRACKER_KCF)
+    loop = M.DeviceLoop(ctx, ns + 1, cap=cap, max_det=32, cost_mode=0)       # stream ns stays empty until the last step
+    loop.kcf_windows([(64, 64), (128, 128)])
+    refs = [oracle.td_new("kcf", W, H, cap, 0) for _ in range(ns)]
+    drng = np.random.default_rng(23)
+    for f in range(26):
+        dets, frames = [], []
+        for s, sc in enumerate(scs):
+            sc.step()
+            frames.append(sc.render())
+            d = sc.windows(jitter=2)
+            keep = drng.random(len(d)) > (0.6 if 8 <= f < 20 and s == 0 else 0.1)         # a drought on stream 0: tracks die
+            d = np.ascontiguousarray(d[keep])
+            if f % 6 == 2 and len(d):                                                      # a false positive: a short-lived track
+                fp = d[:1].copy(); fp["l"] = (fp["l"] + 311) % (W - 140); fp["r"] = fp["l"] + wins[s] - 1
+                d = np.ascontiguousarray(np.concatenate([d, fp]))
+            dets.append(d)
+        for s in range(ns):
+            ctx.upload(s, frames[s])
+        ctx.upload(ns, frames[0])
+        loop.step(dets + [dets[0][:0]])
+        for s in range(ns):
+            refs[s].step(frames[s], dets[s])
+        if f % 2 == 0 or f > 20:
+            for s in range(ns):
+                a, b = loop.tracks(s), refs[s].tracks()
+                for k in a:
+                    assert np.array_equal(a[k], b[k]), (f, s, k)
+    assert all(loop.dropped(s) == 0 for s in range(ns + 1))
+    # a detection of a size without a fused kernel on the empty stream: not spawned, counted; the other streams carry on
+    odd = dets[0][:1].copy(); odd["l"] = 20; odd["r"] = 20 + 99; odd["t"] = 30; odd["b"] = 30 + 59
+    before = loop.tracks(1)
+    loop.step([dets[0], dets[1][:0], dets[2], odd])
+    assert loop.dropped(ns) == 1 and loop.dropped(0) == 0 and len(loop.tracks(ns)["tid"]) == 0
+    after = loop.tracks(1)
+    assert np.array_equal(after["tid"], before["tid"]) and np.array_equal(after["inv"], before["inv"] + 1)
+    loop.close()
+    for r in refs:
+        r.close()
+    ctx.close()
