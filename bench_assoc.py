@@ -145,11 +145,76 @@ def config2(args):
     return {"config": "C2: Kalman + Hungarian, 64 tracks x 64 detections, one 1080p stream, %d frames (host-array frame loop, one sync per stage)" % frames, **out}
 
 
+def config3(args):
+    """C3: 256 concurrent KCF tracks in one 1080p stream, the whole frame loop (predict, association, update, lifecycle):
+    host-side loop, device-resident loop, and the CPU restatement on one core; then the device-resident loop on 64 streams x 128."""
+    import mot_b200 as M
+    import oraclelib
+    from synth import Scene
+    W, H, F = 1920, 1080, 10
+    sc = Scene(0x5EED0300, W, H, 256, tsize=56, win=128)
+    frames, dets = [], []
+    for f in range(F):
+        sc.step(); frames.append(sc.render()); dets.append(sc.windows(jitter=2))
+    out = {}
+    ctx = M.Context(W, H, max_tracks=512, n_frame_slots=1, kind=M.TRACKER_KCF)
+    td = ctx.td(0, cap=256, cost_mode=0)
+    td.step(frames[0], dets[0])
+    t0 = time.perf_counter()
+    for f in range(1, F):
+        td.step(frames[f], dets[f])
+    out["gpu_frames_per_s_host_loop"] = (F - 1) / (time.perf_counter() - t0)
+    host_tab = td.tracks()
+    td.close(); ctx.close()
+    ctx = M.Context(W, H, max_tracks=256, n_frame_slots=1, kind=M.TRACKER_KCF)
+    loop = M.DeviceLoop(ctx, 1, cap=256, max_det=256, cost_mode=0)
+    loop.kcf_windows([(128, 128)])
+    ctx.upload(0, frames[0]); loop.step([dets[0]]); ctx.sync()
+    t0 = time.perf_counter()
+    for f in range(1, F):
+        ctx.upload(0, frames[f]); loop.step([dets[f]])
+    ctx.sync()
+    out["gpu_frames_per_s_device_loop"] = (F - 1) / (time.perf_counter() - t0)
+    dev_tab = loop.tracks(0)
+    loop.close(); ctx.close()
+    orc = oraclelib.Oracle(oraclelib.best())
+    ref = orc.td_new("kcf", W, H, 256, 0)
+    ref.step(frames[0], dets[0])
+    t0 = time.perf_counter()
+    for f in range(1, F):
+        ref.step(frames[f], dets[f])
+    out["cpu_frames_per_s_one_core"] = (F - 1) / (time.perf_counter() - t0)
+    rt = ref.tracks()
+    out["identical_final_track_table"] = bool(all(np.array_equal(host_tab[k], rt[k]) and np.array_equal(dev_tab[k], rt[k]) for k in ("tid", "boxes", "age")))
+    ref.close()
+    # 64 streams x 128 tracks, frames resident (uploaded once): the loop itself, no PCIe in the timed region
+    ns = 64
+    sc2 = Scene(0x5EED0400, W, H, 128, tsize=96, win=128)
+    fr = sc2.render(); d2 = sc2.windows(jitter=0)
+    ctx = M.Context(W, H, max_tracks=ns * 128, n_frame_slots=ns, kind=M.TRACKER_KCF)
+    loop = M.DeviceLoop(ctx, ns, cap=128, max_det=128, cost_mode=0)
+    loop.kcf_windows([(128, 128)])
+    for s_ in range(ns):
+        ctx.upload(s_, fr)
+    dl = [d2] * ns
+    loop.step(dl); loop.step(dl); ctx.sync()
+    K = 10
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loop.step(dl)
+    ctx.sync()
+    dt = (time.perf_counter() - t0) / K
+    out["device_loop_64_streams_x_128_tracks"] = {"ms_per_frame_step": dt * 1e3, "stream_frames_per_s": ns / dt, "track_updates_per_s": ns * 128 / dt}
+    loop.close(); ctx.close()
+    return {"config": "C3: multi-target KCF, 256 tracks (128x128 px) in one 1080p stream, whole frame loop, %d frames" % F, **out}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--matrices", type=int, default=1024)
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--cpu-matrices", type=int, default=2)
     args = ap.parse_args()
+    print(json.dumps(config3(args)))
     print(json.dumps(config2(args)))
     print(json.dumps(config5(args)))
