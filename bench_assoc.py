@@ -145,6 +145,58 @@ def config2(args):
     return {"config": "C2: Kalman + Hungarian, 64 tracks x 64 detections, one 1080p stream, %d frames (host-array frame loop, one sync per stage)" % frames, **out}
 
 
+def use_mkl_fft_for_the_cpu_side():
+    """The compiled reference links FFTW; the oracle build shims it with a slow but exact double DFT by default and with MKL's DFTI
+    (the fastest FFT on the box, out of libtorch_cpu.so) on request: timing comparisons use the latter, like bench.py does."""
+    try:
+        import torch
+        lib = os.path.join(os.path.dirname(torch.__file__), "lib", "libtorch_cpu.so")
+        if os.path.exists(lib):
+            os.environ.setdefault("REF_FFT_PROVIDER", "mkl"); os.environ.setdefault("REF_FFT_MKL_LIB", lib)
+            os.environ.setdefault("MKL_NUM_THREADS", "1"); os.environ.setdefault("OMP_NUM_THREADS", "1")
+    except Exception:
+        pass
+
+
+def config1(args):
+    """C1: single-target KCF on one synthetic 640x480 300-frame sequence with a seeded 128x128 box: upload + predict + update per
+    frame through the host-array ABI (three synchronising calls per frame: latency, not throughput) vs the CPU restatement."""
+    import ctypes as C
+    import mot_b200 as M
+    import oraclelib
+    from synth import Scene, boxes_array, BBox
+    from gpu_common import crop_gray
+    W, H, F = 640, 480, 300
+    sc = Scene(0x5EED0100, W, H, 1, tsize=51, win=128, vmax=2.0)
+    sc.pos[:] = [[320.0, 240.0]]
+    frames = []
+    for f in range(F):
+        frames.append(sc.render()); sc.step()
+    b = boxes_array(1); b["l"], b["t"], b["r"], b["b"], b["type"], b["score"] = 256, 176, 383, 303, 1, 1.0
+    ctx = M.Context(W, H, max_tracks=2, n_frame_slots=1, kind=M.TRACKER_KCF)
+    ctx.upload(0, frames[0]); h = ctx.new(b); ctx.update(h, [0], b)
+    g = b.copy()
+    t0 = time.perf_counter()
+    for f in range(1, F):
+        ctx.upload(0, frames[f]); g = ctx.predict(h, [0], g, clamp=1); ctx.update(h, [0], g)
+    gpu = (F - 1) / (time.perf_counter() - t0)
+    ctx.close()
+    orc = oraclelib.Oracle(oraclelib.best())
+    fft = orc.kcf.ref_fft_provider().decode() if orc.kind == "ref" else "dft64 (restatement)"
+    ob = BBox(256, 176, 303, 383, 1, 1.0); oh = orc.kcf_new(ob)
+    orc.kcf_update(oh, crop_gray(orc, frames[0], ob, 128, 128), ob)
+    t0 = time.perf_counter()
+    for f in range(1, F):
+        orc.kcf_predict(oh, crop_gray(orc, frames[f], ob, 128, 128), ob)
+        ob.l, ob.r = min(max(0, ob.l), W - 1), min(max(0, ob.r), W - 1); ob.t, ob.b = min(max(0, ob.t), H - 1), min(max(0, ob.b), H - 1)
+        orc.kcf_update(oh, crop_gray(orc, frames[f], ob, 128, 128), ob)
+    cpu = (F - 1) / (time.perf_counter() - t0)
+    same = tuple(int(g[0][k]) for k in "ltbr") == ob.tup()
+    orc.kcf_delete(oh)
+    return {"config": "C1: single-target KCF, 640x480, %d frames, one 128x128 window" % F, "gpu_frames_per_s_host_api": gpu,
+            "cpu_frames_per_s_one_core": cpu, "cpu_fft": fft, "identical_final_box": bool(same)}
+
+
 def config3(args):
     """C3: 256 concurrent KCF tracks in one 1080p stream, the whole frame loop (predict, association, update, lifecycle):
     host-side loop, device-resident loop, and the CPU restatement on one core; then the device-resident loop on 64 streams x 128."""
@@ -210,11 +262,13 @@ def config3(args):
 
 
 if __name__ == "__main__":
+    use_mkl_fft_for_the_cpu_side()
     ap = argparse.ArgumentParser()
     ap.add_argument("--matrices", type=int, default=1024)
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--cpu-matrices", type=int, default=2)
     args = ap.parse_args()
+    print(json.dumps(config1(args)))
     print(json.dumps(config3(args)))
     print(json.dumps(config2(args)))
     print(json.dumps(config5(args)))
