@@ -74,6 +74,8 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
+// barrier among a subset of the CTA's warps (id 1..15; __syncthreads is id 0)
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -174,6 +176,85 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
 
     // Persistent CTA: jobs blockIdx.x, blockIdx.x + gridDim.x, ...; the crop of the NEXT job streams into shared memory
     // while the spectral phases of the current one run (the staging area is free from P5 on).
+    // ------------------------------------------------------------------ P7: response = c2r(zf), first-max argmax, box shift
+    // Run by the first two warps only (it is a 34-thread and a 32-thread transform plus a reduction), synchronised with a
+    // named barrier, so that the other thirty warps can already convert the next job's crop (see P0): zf_s, resp and red
+    // are not touched by anything else until the next job's tables are staged, which these two warps do themselves.
+    float2 *const zf_s = reinterpret_cast<float2 *>(R1) + KCF_CHAN * WC;      // [WC][SK], behind the Nyquist column FN
+    float *const resp = reinterpret_cast<float *>(zf_s + S);                  // [WC][HR]
+    auto p7_tail = [&](const JobDesc &pj, int pjob) {
+        {
+        // inverse complex FFT along the WC columns of every half-spectrum bin k, one lane pair per bin
+        constexpr int HW = WC / 2;
+        const int kk = tid >> 1, half = tid & 1;
+        const bool active = kk < SK;
+        const unsigned msk = __ballot_sync(0xFFFFFFFFu, active);
+        if (active) {
+            float2 a[HW];
+            fft_pair_ld<WC, +1>(a, half, msk, [&](int j) { return zf_s[j * SK + kk]; });
+#pragma unroll
+            for (int m = 0; m < HW; ++m) zf_s[(2 * m + half) * SK + kk] = a[brev<HW>(m)];
+        }
+    }
+    bar_sync_named(1, 64);
+    if (tid < WC) {
+        // c2r along the HR rows of column j = tid: Hermitian half spectrum -> HR reals through one complex FFT of HR/2
+        const float2 *Y = zf_s + tid * SK;
+        float2 q[HK];
+        q[0] = make_float2(Y[0].x + Y[HK].x, Y[0].x - Y[HK].x);      // c2r ignores Im(DC), Im(Nyquist)
+#pragma unroll
+        for (int k = 1; k < HK; ++k) {
+            const float2 A = Y[k], B = Y[HK - k];
+            const int ti = (k * (64 / HR)) & 63;
+            const float cs = tw::C64[ti], sn = tw::S64[ti];
+            const float sx_ = A.x + B.x, sy_ = A.y - B.y, dx_ = A.x - B.x, dy_ = A.y + B.y;
+            // Q[k] = (A + conj(B)) + i exp(+2 pi i k / HR) (A - conj(B))
+            q[k] = make_float2(sx_ - dx_ * sn - dy_ * cs, sy_ + dx_ * cs - dy_ * sn);
+        }
+        fft_dif<HK, +1>(q);
+#pragma unroll
+        for (int m = 0; m < HK; ++m) { const float2 v = q[brev<HK>(m)]; resp[tid * HR + 2 * m] = v.x; resp[tid * HR + 2 * m + 1] = v.y; }
+    }
+    bar_sync_named(1, 64);
+    if (DUMP && p.dump.resp) {
+        float *d = p.dump.resp + (long)pjob * p.dump.stride_cell;
+        for (int i = tid; i < NB; i += 64) d[i] = resp[i];
+    }
+    // first maximum in memory order (j outer, i inner), strict '>' from -99999 (kcf.cpp:402-417)
+    float best = -99999.0f; int besti = 0x7FFFFFFF;
+    for (int i = tid; i < NB; i += 64) { const float v = resp[i]; if (v > best) { best = v; besti = i; } }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_down_sync(0xFFFFFFFFu, best, off);
+        const int oi = __shfl_down_sync(0xFFFFFFFFu, besti, off);
+        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    int *const redi = reinterpret_cast<int *>(red) + 32;
+    if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = besti; }
+    bar_sync_named(1, 64);
+    if (tid == 0) {
+        for (int w = 1; w < 2; ++w) { const float ov = red[w]; const int oi = redi[w]; if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; } }
+        int vd = 1, hd = 1;                                            // reference leaves these uninitialised when nothing beats -99999
+        if (besti != 0x7FFFFFFF) { hd = besti / HR + 1; vd = besti - (hd - 1) * HR + 1; }
+        if (DUMP && p.dump.peak) { p.dump.peak[2 * pjob] = vd; p.dump.peak[2 * pjob + 1] = hd; }
+        if (vd > HR / 2) vd -= HR;                                     // kcf.cpp:419-420
+        if (hd > WC / 2) hd -= WC;
+        mot_bbox_t pos = pj.pos;
+        const float dv = __fmul_rn((float)(KCF_CELL * (vd - 1)), pj.scale_vert);
+        const float dh = __fmul_rn((float)(KCF_CELL * (hd - 1)), pj.scale_horiz);
+        pos.t = __float2int_rz(__fadd_rn((float)pos.t, dv));           // kcf.cpp:423-426 (float math, truncation)
+        pos.b = __float2int_rz(__fadd_rn((float)pos.b, dv));
+        pos.l = __float2int_rz(__fadd_rn((float)pos.l, dh));
+        pos.r = __float2int_rz(__fadd_rn((float)pos.r, dh));
+        (p.meta + pj.slot)->pos = pos;
+        if (p.clamp_to_frame) {                                        // top/td.cpp:378-381
+            pos.l = clampi(pos.l, 0, p.frame_w - 1); pos.r = clampi(pos.r, 0, p.frame_w - 1);
+            pos.t = clampi(pos.t, 0, p.frame_h - 1); pos.b = clampi(pos.b, 0, p.frame_h - 1);
+        }
+        p.boxes[pj.box_idx] = pos;
+    }
+    };
+    bool p7_pending = false;
     uint32_t phase = 0;
     // the job count may live on the device (job lists built by a previous kernel, csrc/td_device.cu); p.n_jobs then bounds it
     const int n_jobs = p.n_jobs_dev ? min(*p.n_jobs_dev, p.n_jobs) : p.n_jobs;
@@ -191,11 +272,12 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     __syncthreads();                                   // the previous job is done with every shared-memory region
     const JobDesc &jd = s_desc[it & 3];
     // ------------------------------------------------------------------ P0: tables, Hann vectors, ROI -> gray
-    if (tid < 3) {
-        // SSE tables -> shared memory (one arrival on mbar per job)
+    // SSE tables -> shared memory (one arrival on mbar per job); issued by threads 0 and 1 once P7 of the previous job, which
+    // still works in that area, is done
+    auto stage_tables = [&]() {
         if (tid == 0) { mbar_expect_tx(&mbar, lut_smem ? (uint32_t)(n_rs + n_bn) * 4u : 0u); if (lut_smem) bulk_g2s(R1, p.tab.rsrc_tab, n_rs * 4, &mbar); }
         if (tid == 1 && lut_smem) bulk_g2s(R1 + n_rs, p.tab.bin2_tab, n_bn * 4, &mbar);
-    }
+    };
 
     const int slot = jd.slot;
     mot_bbox_t box = jd.box;
@@ -230,23 +312,39 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     }
     if (tid == 97) prefetch_l2_bulk(p.alpha + (long)slot * p.alpha_stride, (S * 4 + 15) & ~15);
 
+    // P7 of the previous job (predict only): underneath the crop conversion when the staged fast path is taken -- warps 0-1
+    // finish the previous job while warps 2-31 convert -- otherwise first, by itself
+    const bool p7_now = (MODE == KCF_MODE_PREDICT) && p7_pending;
+    const bool overlap = p7_now && staged;
+    const JobDesc &pjd = s_desc[(it - 1) & 3];
+    if (p7_now && !overlap) {
+        if (tid < 64) p7_tail(pjd, job - (int)gridDim.x);
+        __syncthreads();
+    }
+    p7_pending = false;
+    if (!overlap) stage_tables();
     if (p.gray != nullptr) {
         const float *src = p.gray + (long)job * p.gray_stride;
         for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; F[(x + 1) * GS + y + 1] = src[idx]; }
+    } else if (staged && overlap && tid < 64) {
+        p7_tail(pjd, job - (int)gridDim.x);
+        stage_tables();
     } else if (staged) {
-        if (tid < 32) mbar_wait(&mbar2, phase);    // one warp polls, the others sleep at the barrier
-        __syncthreads();
+        // one warp polls for the staged rows, the others sleep at the barrier (all warps, or warps 2-31 next to a running P7)
+        const int w0 = overlap ? 2 : 0, nw = NT / 32 - w0;
+        if ((tid >> 5) == w0) mbar_wait(&mbar2, phase);
+        if (overlap) bar_sync_named(2, NT - 64); else __syncthreads();
         // staged bytes -> gray: one warp per row, lanes along x (3-byte pixels: conflict-free shared loads)
-        const int warp = tid >> 5, lane = tid & 31;
+        const int warp = (tid >> 5) - w0, lane = tid & 31;
         if (l >= 0 && l + cols - 1 <= Wm) {
             // crop inside the frame horizontally (the common case): no per-pixel clamping
-            for (int y = warp; y < rows; y += NT / 32) {
+            for (int y = warp; y < rows; y += nw) {
                 const unsigned char *rrow = raw + y * G::RAW_PITCH + (l * 3 - a0);
 #pragma unroll 4
                 for (int x = lane; x < cols; x += 32) F[(x + 1) * GS + y + 1] = bgr_gray(rrow + x * 3);
             }
         } else {
-            for (int y = warp; y < rows; y += NT / 32) {
+            for (int y = warp; y < rows; y += nw) {
                 const unsigned char *rrow = raw + y * G::RAW_PITCH - a0;
 #pragma unroll 4
                 for (int x = lane; x < cols; x += 32) F[(x + 1) * GS + y + 1] = bgr_gray(rrow + clampi(l + x, 0, Wm) * 3);
@@ -659,7 +757,6 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     __syncthreads();
 
     // ------------------------------------------------------------------ P6: sum over the 31 channels (in channel order)
-    float2 *const zf_s = FN + KCF_CHAN * WC;                           // [WC][SK]
     float *const alpha = p.alpha + (long)jd.slot * p.alpha_stride;
     static_assert(S <= NT, "P6: one bin per thread");
     if (tid < S) {
@@ -700,81 +797,12 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         }
         continue;                                      // next job (uniform: MODE is a template parameter)
     }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ P7: response = c2r(zf), first-max argmax, box shift
-    float *const resp = reinterpret_cast<float *>(zf_s + S);           // [WC][HR]
-    {
-        // inverse complex FFT along the WC columns of every half-spectrum bin k, one lane pair per bin
-        constexpr int HW = WC / 2;
-        const int kk = tid >> 1, half = tid & 1;
-        const bool active = kk < SK;
-        const unsigned msk = __ballot_sync(0xFFFFFFFFu, active);
-        if (active) {
-            float2 a[HW];
-            fft_pair_ld<WC, +1>(a, half, msk, [&](int j) { return zf_s[j * SK + kk]; });
-#pragma unroll
-            for (int m = 0; m < HW; ++m) zf_s[(2 * m + half) * SK + kk] = a[brev<HW>(m)];
-        }
-    }
-    __syncthreads();
-    if (tid < WC) {
-        // c2r along the HR rows of column j = tid: Hermitian half spectrum -> HR reals through one complex FFT of HR/2
-        const float2 *Y = zf_s + tid * SK;
-        float2 q[HK];
-        q[0] = make_float2(Y[0].x + Y[HK].x, Y[0].x - Y[HK].x);      // c2r ignores Im(DC), Im(Nyquist)
-#pragma unroll
-        for (int k = 1; k < HK; ++k) {
-            const float2 A = Y[k], B = Y[HK - k];
-            const int ti = (k * (64 / HR)) & 63;
-            const float cs = tw::C64[ti], sn = tw::S64[ti];
-            const float sx_ = A.x + B.x, sy_ = A.y - B.y, dx_ = A.x - B.x, dy_ = A.y + B.y;
-            // Q[k] = (A + conj(B)) + i exp(+2 pi i k / HR) (A - conj(B))
-            q[k] = make_float2(sx_ - dx_ * sn - dy_ * cs, sy_ + dx_ * cs - dy_ * sn);
-        }
-        fft_dif<HK, +1>(q);
-#pragma unroll
-        for (int m = 0; m < HK; ++m) { const float2 v = q[brev<HK>(m)]; resp[tid * HR + 2 * m] = v.x; resp[tid * HR + 2 * m + 1] = v.y; }
-    }
-    __syncthreads();
-    if (DUMP && p.dump.resp) {
-        float *d = p.dump.resp + (long)job * p.dump.stride_cell;
-        for (int i = tid; i < NB; i += NT) d[i] = resp[i];
-    }
-    // first maximum in memory order (j outer, i inner), strict '>' from -99999 (kcf.cpp:402-417)
-    float best = -99999.0f; int besti = 0x7FFFFFFF;
-    for (int i = tid; i < NB; i += NT) { const float v = resp[i]; if (v > best) { best = v; besti = i; } }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const float ov = __shfl_down_sync(0xFFFFFFFFu, best, off);
-        const int oi = __shfl_down_sync(0xFFFFFFFFu, besti, off);
-        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
-    }
-    int *const redi = reinterpret_cast<int *>(red) + 32;
-    if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = besti; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < NT / 32; ++w) { const float ov = red[w]; const int oi = redi[w]; if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; } }
-        int vd = 1, hd = 1;                                            // reference leaves these uninitialised when nothing beats -99999
-        if (besti != 0x7FFFFFFF) { hd = besti / HR + 1; vd = besti - (hd - 1) * HR + 1; }
-        if (DUMP && p.dump.peak) { p.dump.peak[2 * job] = vd; p.dump.peak[2 * job + 1] = hd; }
-        if (vd > HR / 2) vd -= HR;                                     // kcf.cpp:419-420
-        if (hd > WC / 2) hd -= WC;
-        mot_bbox_t pos = jd.pos;
-        const float dv = __fmul_rn((float)(KCF_CELL * (vd - 1)), jd.scale_vert);
-        const float dh = __fmul_rn((float)(KCF_CELL * (hd - 1)), jd.scale_horiz);
-        pos.t = __float2int_rz(__fadd_rn((float)pos.t, dv));           // kcf.cpp:423-426 (float math, truncation)
-        pos.b = __float2int_rz(__fadd_rn((float)pos.b, dv));
-        pos.l = __float2int_rz(__fadd_rn((float)pos.l, dh));
-        pos.r = __float2int_rz(__fadd_rn((float)pos.r, dh));
-        (p.meta + jd.slot)->pos = pos;
-        if (p.clamp_to_frame) {                                        // top/td.cpp:378-381
-            pos.l = clampi(pos.l, 0, p.frame_w - 1); pos.r = clampi(pos.r, 0, p.frame_w - 1);
-            pos.t = clampi(pos.t, 0, p.frame_h - 1); pos.b = clampi(pos.b, 0, p.frame_h - 1);
-        }
-        p.boxes[jd.box_idx] = pos;
-    }
+    p7_pending = true;                                 // P7 of this job runs underneath P0 of the next one (or after the loop)
     }   // persistent job loop
+    if (MODE == KCF_MODE_PREDICT && p7_pending) {
+        __syncthreads();
+        if (tid < 64) p7_tail(s_desc[(it - 1) & 3], (int)blockIdx.x + (it - 1) * (int)gridDim.x);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
