@@ -167,26 +167,6 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def pin_to_gpu_numa_node(local):
-    """Run this rank on the cores NVML reports as local to its GPU, so that the pinned host buffers of the e2e leg are
-    allocated on that NUMA node (several ranks uploading through one socket halve each other's H2D rate).  Best effort."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local)
-        words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            pin_to_gpu_numa_node.original = os.sched_getaffinity(0)
-            os.sched_setaffinity(0, cpus)
-            return "gpu%d -> %d local cores" % (local, len(cpus))
-    except Exception as e:              # no NVML / restricted cpuset: keep the default placement
-        return "unpinned (%s)" % type(e).__name__
-    return "unpinned"
-
-
 # ======================================================================================================= CUDA arm
 def run_b200(args):
     import torch
@@ -200,7 +180,6 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = pin_to_gpu_numa_node(local)            # pinned frame buffers are first-touched next to the GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -314,7 +293,7 @@ def run_b200(args):
         dt = max_over_ranks(dt, dev)
         e2e = {"value": world * n * ke / dt, "unit": "track-updates/s", "h2d_bytes_per_step": NS * H * W * 3 + 2 * n * (24 + 8),
                "d2h_bytes_per_step": n * 24, "steps": ke, "ms_per_step": 1e3 * dt / ke,
-               "h2d_alone_ms": 1e3 * h2d_s, "h2d_alone_gbs": NS * H * W * 3 / h2d_s / 1e9, "host_placement": numa}
+               "h2d_alone_ms": 1e3 * h2d_s, "h2d_alone_gbs": NS * H * W * 3 / h2d_s / 1e9}
         ctx2.close()
 
     if rank == 0:
@@ -340,8 +319,6 @@ def run_b200(args):
                     "step_frac": (B_PAIR * n / ((t_pred + t_upd) * 1e-3) / 1e9) / peak}
         cb = None
         if world == 1 and not args.no_cpu:
-            if getattr(pin_to_gpu_numa_node, "original", None):
-                os.sched_setaffinity(0, pin_to_gpu_numa_node.original)      # the CPU baseline may use every host core
             cb, _ = cpu_reference(os.cpu_count() or 1, 32, 2, 24)
         line = {"metric": "KCF track-updates/sec", "value": value, "unit": "track-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
