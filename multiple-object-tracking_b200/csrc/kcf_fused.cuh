@@ -340,8 +340,12 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             // crop inside the frame horizontally (the common case): no per-pixel clamping
             for (int y = warp; y < rows; y += nw) {
                 const unsigned char *rrow = raw + y * G::RAW_PITCH + (l * 3 - a0);
-#pragma unroll 4
-                for (int x = lane; x < cols; x += 32) F[(x + 1) * GS + y + 1] = bgr_gray(rrow + x * 3);
+                // WC full 32-pixel chunks (cols >= 4 * WC) with compile-time offsets, then the 0..3 leftover pixels
+                const unsigned char *px = rrow + lane * 3;
+                float *dst = F + (lane + 1) * GS + y + 1;
+#pragma unroll
+                for (int c = 0; c < W0 / 32; ++c) dst[c * 32 * GS] = bgr_gray(px + c * 96);
+                if (lane + W0 < cols) dst[W0 * GS] = bgr_gray(px + W0 * 3);
             }
         } else {
             for (int y = warp; y < rows; y += nw) {
