@@ -420,7 +420,9 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                 const int x = x0 + q * XS;
                 const float *g = g0 + q * XS * GS;
                 // grad1: one-sided difference (x1) on the border, central difference (x0.5) inside; the apron makes both one form
-                const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f;
+                // only the first and the last pixel of a thread can sit on the left / right border (cols >= W0): the selects of
+                // the others fold away
+                const float rx = (q == 0 || q == G::PIX_PER_THREAD - 1) ? ((x == 0 || x == cols - 1) ? 1.f : .5f) : .5f;
                 const float gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), rx);
                 const float gy = __fmul_rn(__fsub_rn(g[1], g[-1]), ry);
                 mbr[q] = grad_pixel_k(gx, gy, rsrc, bn, lk);
