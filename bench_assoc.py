@@ -218,13 +218,13 @@ def config3(args):
     out["gpu_frames_per_s_host_loop"] = (F - 1) / (time.perf_counter() - t0)
     host_tab = td.tracks()
     td.close(); ctx.close()
-    ctx = M.Context(W, H, max_tracks=256, n_frame_slots=1, kind=M.TRACKER_KCF)
+    ctx = M.Context(W, H, max_tracks=256, n_frame_slots=2, kind=M.TRACKER_KCF)
     loop = M.DeviceLoop(ctx, 1, cap=256, max_det=256, cost_mode=0)
     loop.kcf_windows([(128, 128)])
     ctx.upload(0, frames[0]); loop.step([dets[0]]); ctx.sync()
     t0 = time.perf_counter()
     for f in range(1, F):
-        ctx.upload(0, frames[f]); loop.step([dets[f]])
+        ctx.upload(f & 1, frames[f]); loop.frame_base(f & 1); loop.step([dets[f]])       # two slots: frame f uploads under the kernels of f-1
     ctx.sync()
     out["gpu_frames_per_s_device_loop"] = (F - 1) / (time.perf_counter() - t0)
     dev_tab = loop.tracks(0)

@@ -154,7 +154,8 @@ int mot_td_last(mot_td_t *td, mot_bbox_t *predicted, int *assigned_trackers);
 typedef struct mot_tdd_s mot_tdd_t;
 /* n_streams independent streams, at most cap tracks (reference: 256, top/td.cpp:12) and max_det detections
  * (reference: 128, top/cnntype.h:46) each, both <= 1024.  The context needs >= n_streams*cap free slots and no host-managed
- * trackers.  KCF contexts: stream s reads frame slot s (mot_frame_upload / mot_frame_bind_device before each step), and only
+ * trackers.  KCF contexts: stream s reads frame slot base + s (mot_tdd_frame_base; mot_frame_upload / mot_frame_bind_device
+ * before each step), and only
  * detections whose window has a fused kernel (cell grid sides 8, 16 or 32, i.e. 32..35, 64..67 or 128..131 pixels per side)
  * can spawn a track; the others are counted (mot_tdd_dropped) -- the host-side loop mot_td_step serves every size. */
 int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *ctx, int n_streams, int cap, int max_det, int cost_mode);
@@ -163,6 +164,9 @@ void mot_tdd_destroy(mot_tdd_t *tdd);
 int mot_tdd_step_dev(mot_tdd_t *tdd, const mot_bbox_t *d_dets, const int *d_ndet);
 /* detections in host arrays (dets[s] points at ndet[s] boxes); staged, uploaded and stepped; asynchronous */
 int mot_tdd_step(mot_tdd_t *tdd, const mot_bbox_t *const *dets, const int *ndet);
+/* KCF kind: from the next step on, stream s reads frame slot base + s (default 0).  Steps are asynchronous: do not upload
+ * into a slot that a step still in flight reads -- alternate two bases (2 * n_streams frame slots) or call mot_sync first. */
+int mot_tdd_frame_base(mot_tdd_t *tdd, int base);
 /* KCF kind: declare the window sizes (pixels) the detections will have; the kernels of all other classes are not launched */
 int mot_tdd_kcf_windows(mot_tdd_t *tdd, int n, const int *rows, const int *cols);
 /* KCF kind: number of detections of stream s that could not spawn a track so far (synchronises) */

@@ -13,7 +13,7 @@
 // count from the device and exit at once when their list is empty.  tracker_new (trackers/kcf.cpp:484-491, :139-213) runs
 // inside the lifecycle kernel (metadata only: model and alpha are fully written by the first update), followed by one
 // more update launch over the tracks spawned in this frame (the reference's first update, top/td.cpp:629-641).  Stream s
-// reads frame slot s.  Detections whose window has no fused kernel cannot spawn here and are counted (mot_tdd_dropped);
+// reads frame slot frame_base + s (mot_tdd_frame_base: alternate two bases to upload frame k+1 under the kernels of frame k).  Detections whose window has no fused kernel cannot spawn here and are counted (mot_tdd_dropped);
 // the host-side loop (host/td_loop.cpp) serves those through the any-size path.
 #include "mot_ctx.h"
 
@@ -28,6 +28,7 @@ struct TddState {
     int md;
     // KCF kind
     int kcf, frame_w, frame_h;
+    int frame_base;                              // stream s reads frame slot frame_base + s
     int cls_id[9];                               // context class index of fused class 3*hi + wi (cell sides 8, 16, 32); -1: disabled
     KcfMeta *meta;
     int *jl_slot, *jl_frame, *jl_box, *jl_count; // [9][S*cap] x 3, [9]: live tracks grouped by window class
@@ -55,7 +56,7 @@ __global__ void td_joblist_kernel(TddState st)
         const KcfMeta *m = st.meta + slot;
         const int k = 3 * fused_side(m->hr) + fused_side(m->wc);
         const int at = atomicAdd(&st.jl_count[k], 1);
-        st.jl_slot[k * N + at] = slot; st.jl_frame[k * N + at] = s; st.jl_box[k * N + at] = (int)e;
+        st.jl_slot[k * N + at] = slot; st.jl_frame[k * N + at] = st.frame_base + s; st.jl_box[k * N + at] = (int)e;
     }
 }
 
@@ -159,7 +160,7 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
             st.meta[sl] = m;
             const long N = (long)st.S * cap;
             const int at = atomicAdd(&st.sp_count[k], 1);
-            st.sp_slot[k * N + at] = sl; st.sp_frame[k * N + at] = s; st.sp_box[k * N + at] = (int)o;
+            st.sp_slot[k * N + at] = sl; st.sp_frame[k * N + at] = st.frame_base + s; st.sp_box[k * N + at] = (int)o;
             continue;
         }
         // tracker_new, trackers/kalman.cpp:147-163: x0 = [l,t,r,b,0,0], P0 = 1e4 I
@@ -214,7 +215,7 @@ int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int ma
     CU(cudaMemsetAsync(st.slot, 0xFF, sizeof(int) * n, c->stream));
     CU(cudaMemsetAsync(st.age, 0, sizeof(int) * n, c->stream)); CU(cudaMemsetAsync(st.vis, 0, sizeof(int) * n, c->stream)); CU(cudaMemsetAsync(st.invis, 0, sizeof(int) * n, c->stream));
     CU(cudaMemsetAsync(st.bbox, 0, sizeof(mot_bbox_t) * n, c->stream)); CU(cudaMemsetAsync(st.tid, 0, sizeof(uint32_t) * n, c->stream));
-    st.kcf = kcf ? 1 : 0; st.frame_w = c->W; st.frame_h = c->H; st.meta = c->d_meta;
+    st.kcf = kcf ? 1 : 0; st.frame_w = c->W; st.frame_h = c->H; st.meta = c->d_meta; st.frame_base = 0;
     for (int k = 0; k < 9; ++k) st.cls_id[k] = -1;
     if (kcf) {
         static const int side[3] = { 8, 16, 32 };
@@ -335,6 +336,17 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
     t->graph_stream = c->stream;
     CU(cudaGraphLaunch(t->graph, c->stream));
     c->launches += 6;
+    return 0;
+}
+
+/* KCF kind: from the next step on, stream s reads frame slot base + s.  The steps are asynchronous, so a slot must not be
+ * uploaded again while a step that reads it is still in flight: alternate two bases (2 * n_streams slots), or mot_sync first. */
+int mot_tdd_frame_base(mot_tdd_t *t, int base)
+{
+    if (!t || base < 0) return mot_fail(MOT_ERR_ARG, "mot_tdd_frame_base: bad argument");
+    if (!t->st.kcf) return mot_fail(MOT_ERR_KIND, "not a KCF frame loop");
+    if (base + t->st.S > t->ctx->n_frames) return mot_fail(MOT_ERR_ARG, "frame slots %d..%d do not exist (the context has %d)", base, base + t->st.S - 1, t->ctx->n_frames);
+    t->st.frame_base = base;
     return 0;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "mot_predict_batch", "mot_update_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
     "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_get", "mot_td_last", "mot_td_overlay",
-    "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_read", "mot_tdd_kcf_windows", "mot_tdd_dropped",
+    "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_read", "mot_tdd_kcf_windows", "mot_tdd_dropped", "mot_tdd_frame_base",
     "mot_debug_enable_dumps", "mot_debug_fetch", "mot_debug_state", "mot_debug_tables",
 ]
 
@@ -284,6 +284,10 @@ class DeviceLoop:
 
     def step_dev(self, d_dets, d_ndet):
         _chk(lib().mot_tdd_step_dev(self.h, C.c_void_p(d_dets), C.c_void_p(d_ndet)))
+
+    def frame_base(self, base):
+        """KCF kind: stream s reads frame slot base + s from the next step on (alternate two bases to overlap uploads)."""
+        _chk(lib().mot_tdd_frame_base(self.h, base))
 
     def kcf_windows(self, sizes):
         r = np.array([a for a, _ in sizes], np.int32); c = np.array([b for _, b in sizes], np.int32)

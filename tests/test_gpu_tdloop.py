@@ -141,7 +141,7 @@ def test_device_resident_kcf_loop_trace(oracle):
     W, H, ns, cap = 1280, 720, 3, 24
     wins = [64, 128, 64]
     scs = [Scene(900 + 7 * s, W, H, 6 if wins[s] == 128 else 9, tsize=wins[s] * 5 // 8, win=wins[s]) for s in range(ns)]
-    ctx = M.Context(W, H, max_tracks=(ns + 1) * cap, n_frame_slots=ns + 1, kind=M.TRACKER_KCF)
+    ctx = M.Context(W, H, max_tracks=(ns + 1) * cap, n_frame_slots=2 * (ns + 1), kind=M.TRACKER_KCF)
     loop = M.DeviceLoop(ctx, ns + 1, cap=cap, max_det=32, cost_mode=0)       # stream ns stays empty until the last step
     loop.kcf_windows([(64, 64), (128, 128)])
     refs = [oracle.td_new("kcf", W, H, cap, 0) for _ in range(ns)]
@@ -158,9 +158,11 @@ def test_device_resident_kcf_loop_trace(oracle):
                 fp = d[:1].copy(); fp["l"] = (fp["l"] + 311) % (W - 140); fp["r"] = fp["l"] + wins[s] - 1
                 d = np.ascontiguousarray(np.concatenate([d, fp]))
             dets.append(d)
+        base = (f & 1) * (ns + 1)                          # two sets of frame slots: the step of frame f-1 may still be reading the other one
         for s in range(ns):
-            ctx.upload(s, frames[s])
-        ctx.upload(ns, frames[0])
+            ctx.upload(base + s, frames[s])
+        ctx.upload(base + ns, frames[0])
+        loop.frame_base(base)
         loop.step(dets + [dets[0][:0]])
         for s in range(ns):
             refs[s].step(frames[s], dets[s])
