@@ -1,5 +1,7 @@
-// kcf_fused.cuh -- the fused KCF/DCF kernels: one CTA per (track, frame) job, everything between the BGR frame
-// bytes and the updated model in ONE launch, so a track touches HBM once per predict and once per update.
+// kcf_fused.cuh -- the fused KCF/DCF kernels: persistent CTAs (one per SM) looping over (track, frame) jobs, everything
+// between the BGR frame bytes and the updated model in ONE launch, so a track touches HBM once per predict and once per
+// update.  Across jobs a CTA is software-pipelined: the next job's descriptor and crop rows are fetched during the spectral
+// phases of the current one, and (predict) the response stage of a job runs on two warps underneath the next crop conversion.
 //
 // Replaces, for one track (reference paths relative to its root):
 //   rgb2Gray + bilinearInterpolationGray      top/drawlib.c:192-240, 542-637   (called top/td.cpp:348-364)
@@ -8,15 +10,17 @@
 //   predict: kcf_linear_correlation_zf + kcf_predict_ifft2 (+ the clamp of top/td.cpp:378-381)   kcf.cpp:306-362, 397-439
 //   update : kcf_linear_correlation_kf + kcf_update_alpha + kcf_update_xf                         kcf.cpp:269-304, 364-395, 441-476
 //
-// Shared-memory plan for HR x WC cells (floats; 32x32 -> 207 KB, one CTA per SM):
+// Shared-memory plan for HR x WC cells (floats; 32x32 -> 223 KB, one CTA of 1024 threads per SM):
 //   F   [31*NB]              gray patch -> (M/16, orientation bin) -> packed half spectra of all 31 channels, in place
 //   R1  [18*WC*(HR+1)]       SSE look-up tables (gradient phase) -> 18-bin cell histograms -> Nyquist column, zf, response
-//   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies;  wy[HR], wx[WC] Hann vectors
+//   MQ  [2 float2 / thread]  cp.async landing slots of the model stream in the column pass
+//   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies (both later: raw transform of the packed DC/Nyquist column);  wy[HR], wx[WC] Hann vectors
 // The 31-channel feature tensor is never materialised: each channel column is generated from R1 and N in registers,
 // windowed, transformed (real FFT of HR points as a complex FFT of HR/2) and stored PACKED (DC.re, Nyquist.re share one
 // complex slot), so the column pass is exactly HR/2 complex FFTs per channel: 31*16 = 496 thread-sized transforms at 32x32.
 //
-// Arithmetic follows the reference operation by operation where its rounding is observable (gray in double, unfused
+// Arithmetic follows the reference operation by operation where its rounding is observable (gray: the double expression
+// reproduced exactly in integers + three f32 operations, unfused
 // f32 MUL/ADD in fHOG via __fmul_rn/__fadd_rn, SSE rsqrt/rcp through host-harvested tables, the histogram summed in the
 // reference's pixel order); the FFTs and the spectral products are ordinary f32.
 #pragma once
@@ -824,7 +828,7 @@ template <int HR, int WC> int kcf_launch_size(int mode, const KcfLaunch &p, cuda
     else                          fn = dump ? (const void *)kcf_fused_kernel<HR, WC, KCF_MODE_UPDATE, true> : (const void *)kcf_fused_kernel<HR, WC, KCF_MODE_UPDATE, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    // persistent CTAs: one per SM (207 KB of shared memory each), looping over the jobs
+    // persistent CTAs: one per SM (223 KB of shared memory each at 32x32), looping over the jobs
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
