@@ -27,6 +27,7 @@
 #include "mot_internal.h"
 #include "fhog_common.cuh"
 #include "fft_reg.cuh"
+#include <type_traits>
 
 namespace mot {
 
@@ -592,15 +593,19 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             const float *const n0 = Ns + j * (HR + 1), *const n1 = n0 + (HR + 1);
             const float *const ra = R1 + (c < 18 ? c : c - 18) * (WC * RS) + j * RS;
             const float *const rb = R1 + (c < 18 ? c : c - 9) * (WC * RS) + j * RS;
+            auto column = [&](auto insensitive) {
 #pragma unroll
-            for (int i = 0; i < HR; ++i) {
-                const float rv = (c < 18) ? ra[i] : __fadd_rn(ra[i], rb[i]);       // R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309)
-                float hsum = __fadd_rn(fminf(__fmul_rn(rv, n1[i + 1]), 0.2f), fminf(__fmul_rn(rv, n1[i]), 0.2f));
-                hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i + 1]), 0.2f));
-                hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i]), 0.2f));
-                const float f = __fmul_rn(hsum, __fmul_rn(wy_s[i], wxj));           // (hsum * 0.5) * (wy * wx): the 0.5 sits in wy_s
-                if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
-            }
+                for (int i = 0; i < HR; ++i) {
+                    const float rv = insensitive ? __fadd_rn(ra[i], rb[i]) : ra[i];     // R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309)
+                    float hsum = __fadd_rn(fminf(__fmul_rn(rv, n1[i + 1]), 0.2f), fminf(__fmul_rn(rv, n1[i]), 0.2f));
+                    hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i + 1]), 0.2f));
+                    hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i]), 0.2f));
+                    const float f = __fmul_rn(hsum, __fmul_rn(wy_s[i], wxj));           // (hsum * 0.5) * (wy * wx): the 0.5 sits in wy_s
+                    if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
+                }
+            };
+            // warp-uniform: a warp holds one channel, so the two forms are separate loops rather than a select per point
+            if (c < 18) column(std::false_type{}); else column(std::true_type{});
         } else {
             const float *const tp = F + (c * WC + j) * HR;
 #pragma unroll
