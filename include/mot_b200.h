@@ -181,7 +181,9 @@ int mot_debug_enable_dumps(mot_ctx_t *ctx, int enable);
 long mot_debug_fetch(mot_ctx_t *ctx, int stage, void *host_out, long max_bytes);
 /* Raw per-slot state: which = 0 xf_md (31*S float pairs) | 1 alpha (S floats) | 2 Kalman x[6] | 3 Kalman P[36] col-major. */
 long mot_debug_state(mot_ctx_t *ctx, int handle, int which, void *host_out, long max_bytes);
-/* Host-harvested SSE tables: which = 0 rsqrt | 1 rcp | 2 acos(20020) ; info[0..3] = rsqrt_bits, rcp_bits, bin_shift, bin_nseg */
+/* Host-harvested SSE tables (no GPU needed): which = 0 rsqrt | 1 rcp | 2 acos(20020) | 3 fused {rsqrt, rcp(rsqrt)/16} pairs |
+ * 4 orientation-bin step table (u32 bits) | 5 the same with the wrap folded in (u32 bits) | 6 {saturation threshold bits, rcp(1e10f)};
+ * info[0..3] = rsqrt_bits, rcp_bits, bin_shift, bin_nseg */
 long mot_debug_tables(int which, float *out, long max_floats, int *info);
 
 #if defined(__GNUC__)

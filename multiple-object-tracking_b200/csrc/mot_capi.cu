@@ -795,7 +795,16 @@ long mot_debug_tables(int which, float *out, long max_floats, int *info)
     const FhogTables &t = fhog_tables();
     if (!t.ok) return fail(MOT_ERR_TABLES, "%s", t.error.c_str());
     if (info) { info[0] = t.rsqrt_bits; info[1] = t.rcp_bits; info[2] = t.bin_shift; info[3] = t.bin_nseg; }
-    const std::vector<float> *v = which == 0 ? &t.rsqrt_tab : which == 1 ? &t.rcp_tab : which == 2 ? &t.acos_tab : nullptr;
+    if (which == 4 || which == 5) {                     // 32-bit entries handed out through the float buffer, bit for bit
+        const std::vector<uint32_t> &u = which == 4 ? t.bin_tab : t.bin2_tab;
+        if (out) { if ((long)u.size() > max_floats) return fail(MOT_ERR_ARG, "buffer too small"); memcpy(out, u.data(), sizeof(uint32_t) * u.size()); }
+        return (long)u.size();
+    }
+    if (which == 6) {                                   // constants: bits of M2 up to which MIN(rsqrt(M2), 1e10f) saturates; rcp(1e10f)
+        if (out) { if (max_floats < 2) return fail(MOT_ERR_ARG, "buffer too small"); memcpy(out, &t.u_cap, 4); memcpy(out + 1, &t.rcp_cap, 4); }
+        return 2;
+    }
+    const std::vector<float> *v = which == 0 ? &t.rsqrt_tab : which == 1 ? &t.rcp_tab : which == 2 ? &t.acos_tab : which == 3 ? &t.rsrc_tab : nullptr;
     if (!v) return fail(MOT_ERR_ARG, "unknown table %d", which);
     if (out) { if ((long)v->size() > max_floats) return fail(MOT_ERR_ARG, "buffer too small"); memcpy(out, v->data(), sizeof(float) * v->size()); }
     return (long)v->size();

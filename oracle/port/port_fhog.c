@@ -26,6 +26,10 @@
 static float sse_rsqrt(float x) { return _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(x))); }
 static float sse_rcp(float x)   { return _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(x))); }
 
+/* the two instructions on arrays, for the tests that pin the product's harvested tables against the CPU they run on */
+__attribute__((visibility("default"))) void port_sse_rsqrt(const float *x, float *y, long n) { for (long i = 0; i < n; ++i) y[i] = sse_rsqrt(x[i]); }
+__attribute__((visibility("default"))) void port_sse_rcp(const float *x, float *y, long n) { for (long i = 0; i < n; ++i) y[i] = sse_rcp(x[i]); }
+
 /* gradientMex.cpp:47-56.  a1[i] ~ acos(i/10000) for i in [-10010, 10010); the argument is a float and the
  * reference is C++, so the float overload of acos is the one called. */
 static const float *acos_table(void)

@@ -75,3 +75,77 @@ def test_gray_conversion_identity_for_all_colours():
     # distance of the exact fma argument to the nearest float rounding boundary dwarfs one double rounding
     qf = q.astype(np.float32)
     assert np.array_equal(ref, qf)
+
+
+def _table(which, dtype=None):
+    import ctypes as C
+    import numpy as np
+    import mot_b200
+    info = (C.c_int * 4)()
+    n = mot_b200.lib().mot_debug_tables(which, None, 0, info)
+    assert n > 0
+    a = np.zeros(n, np.float32)
+    assert mot_b200.lib().mot_debug_tables(which, a.ctypes.data_as(C.c_void_p), n, info) == n
+    return (a if dtype is None else a.view(dtype)), [int(v) for v in info]
+
+
+def test_harvested_tables_reproduce_the_sse_instructions(port):
+    """The fused kernel never executes rsqrtps / rcpps: it looks them up in tables harvested from the host CPU.  Pin those
+    tables against the instructions themselves (through the oracle's C wrappers) on random inputs over many binades, and
+    check the three properties the kernel leans on: rcp results leave the five low mantissa bits zero (the orientation bin
+    is stored there), the fused table holds {rsqrt, rcp(rsqrt)/16}, and MIN(rsqrt(M2), 1e10f) saturates exactly for
+    bits(M2) <= u_cap."""
+    import ctypes as C
+    import numpy as np
+    rs, info = _table(0); rc, _ = _table(1); fused, _ = _table(3); consts, _ = _table(6, np.uint32)
+    kb_rs, kb_rc = info[0], info[1]
+    rng = np.random.default_rng(5)
+    x = (rng.uniform(1.0, 2.0, 200000) * np.exp2(rng.integers(-60, 60, 200000))).astype(np.float32)
+
+    def sse(name, v):
+        out = np.zeros_like(v)
+        getattr(port.kcf, name)(v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_long(len(v)))
+        return out
+
+    def emu_rsqrt(v):                                   # table[parity(e)][top mantissa bits] * 2^-(e >> 1), like the kernel
+        u = v.view(np.uint32).astype(np.int64)
+        e = (u >> 23) - 127
+        key = (u & 0x7FFFFF) >> (23 - kb_rs)
+        t = rs[((e & 1) << kb_rs) + key].view(np.uint32).astype(np.int64)
+        return (t - ((e >> 1) << 23)).astype(np.uint32).view(np.float32)
+
+    def emu_rcp(v):
+        u = v.view(np.uint32).astype(np.int64)
+        e = (u >> 23) - 127
+        t = rc[(u & 0x7FFFFF) >> (23 - kb_rc)].view(np.uint32).astype(np.int64)
+        return (t - (e << 23)).astype(np.uint32).view(np.float32)
+
+    assert np.array_equal(emu_rsqrt(x).view(np.uint32), sse("port_sse_rsqrt", x).view(np.uint32))
+    assert np.array_equal(emu_rcp(x).view(np.uint32), sse("port_sse_rcp", x).view(np.uint32))
+    # fused table: {T, rcp(T) / 16}, and the low five mantissa bits of the second entry are free
+    T = fused[0::2].copy(); R16 = fused[1::2].copy()
+    assert np.array_equal(T, rs)
+    assert np.array_equal(R16, (sse("port_sse_rcp", T) * np.float32(0.0625)).astype(np.float32))
+    assert not np.any(R16.view(np.uint32) & 31) and not (int(consts[1]) & 31)
+    # saturation threshold: exhaustive over the float patterns around it, plus zero / denormals / ordinary values
+    u_cap = int(consts[0])
+    u = np.concatenate([np.arange(max(0, u_cap - 200000), u_cap + 200000, dtype=np.uint32),
+                        np.array([0, 1, 0x7FFFFF, 0x800000, 0x3F800000], np.uint32)])
+    m = sse("port_sse_rsqrt", u.view(np.float32))
+    saturates = ~(m < np.float32(1e10))
+    assert np.array_equal(saturates, u <= u_cap)
+
+
+def test_folded_orientation_table_equals_the_step_table():
+    """bin2 (wrap 18 -> 0 folded in, both values stored) decodes to the same bin as the step table for every index."""
+    import numpy as np
+    b1, info = _table(4, np.uint32); b2, _ = _table(5, np.uint32)
+    shift, nseg = info[2], info[3]
+    ai = np.arange(20020, dtype=np.int64)
+    for s in (0, 1):
+        e1 = b1[s * nseg + (ai >> shift)].astype(np.int64)
+        want = (e1 & 0xFF) - (ai >= (e1 >> 8)).astype(np.int64)
+        want[want >= 18] = 0
+        e2 = b2[s * nseg + (ai >> shift)].astype(np.int64)
+        got = np.where(ai >= (e2 >> 10), (e2 >> 5) & 31, e2 & 31)
+        assert np.array_equal(got, want)
