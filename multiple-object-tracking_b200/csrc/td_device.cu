@@ -82,6 +82,37 @@ __global__ void td_scatter_kernel(TddState st, const mot_bbox_t *dets, const int
     }
 }
 
+// Exclusive scan of 0/1 flags v[0..n), n <= 1024, by a CTA of 256 threads (four consecutive entries per thread, warp shuffles,
+// one pass over the eight warp totals): on return v[i] = number of set flags before i; returns the number of set flags.
+__device__ int block_scan_flags(int *v, int n, int *wsum /* [9] shared */)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int i = 4 * tid + q; a[q] = i < n ? v[i] : 0; }
+    const int e1 = a[0], e2 = e1 + a[1], e3 = e2 + a[2], sum = e3 + a[3];
+    int inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, off); if (lane >= off) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < 8 ? wsum[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, winc, off); if (lane >= off) winc += t; }
+        if (lane < 8) wsum[lane] = winc - w;
+        if (lane == 7) wsum[8] = winc;
+    }
+    __syncthreads();
+    const int base = wsum[warp] + inc - sum;
+    const int ex[4] = { 0, e1, e2, e3 };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int i = 4 * tid + q; if (i < n) v[i] = base + ex[q]; }
+    __syncthreads();
+    return wsum[8];
+}
+
 // delete lost tracks with stable compaction (top/td.cpp:585-609), then spawn (top/td.cpp:612-644)
 __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox_t *dets, const int *ndet)
 {
@@ -89,19 +120,17 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
     extern __shared__ int sm[];
     int *pos = sm;                    // [cap] new position of a kept track / [max_det] rank of a spawning detection
     int *freeid = sm + 1024;          // [cap] free local slot ids in ascending order
-    __shared__ int total;
-    // ---- keep flags in parallel, exclusive scan by one thread on shared memory (tables are a few hundred entries) ----------
+    int *flag = sm + 2048;            // [1024] scratch flags of the scans
+    __shared__ int wsum[9];
+    // ---- keep flags and their exclusive scan -------------------------------------------------------------------------------
     for (int i = tid; i < T; i += NTH) {
         const long o = (long)s * cap + i;
         const bool lost = ((st.age[o] < 10) && (st.vis[o] * 5 < 3 * st.age[o])) || (st.invis[o] >= 20);        // :587-590
-        pos[i] = lost ? -1 : 0;
+        flag[i] = lost ? 0 : 1; pos[i] = lost ? -1 : 0;
     }
     __syncthreads();
-    if (tid == 0) {
-        int n = 0;
-        for (int i = 0; i < T; ++i) if (pos[i] == 0) pos[i] = n++;
-        total = n;
-    }
+    const int n2 = block_scan_flags(flag, T, wsum);
+    for (int i = tid; i < T; i += NTH) if (pos[i] == 0) pos[i] = flag[i];
     __syncthreads();
     // stable compaction through registers
     uint32_t r_tid[4]; int r_slot[4], r_age[4], r_vis[4], r_inv[4]; mot_bbox_t r_box[4]; int r_pos[4];
@@ -111,7 +140,6 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
         if (i < T) { const long o = (long)s * cap + i; r_pos[q] = pos[i]; r_tid[q] = st.tid[o]; r_slot[q] = st.slot[o]; r_age[q] = st.age[o]; r_vis[q] = st.vis[o]; r_inv[q] = st.invis[o]; r_box[q] = st.bbox[o]; }
     }
     __syncthreads();
-    const int n2 = total;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         if (r_pos[q] >= 0) { const long o = (long)s * cap + r_pos[q]; st.tid[o] = r_tid[q]; st.slot[o] = r_slot[q]; st.age[o] = r_age[q]; st.vis[o] = r_vis[q]; st.invis[o] = r_inv[q]; st.bbox[o] = r_box[q]; }
@@ -132,16 +160,27 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
         pos[j] = cand ? 1 : 0;
     }
     __syncthreads();
-    if (tid == 0) {
-        int nf = 0;
-        for (int ls = 0; ls < cap; ++ls) if (!((used[ls >> 5] >> (ls & 31)) & 1u)) freeid[nf++] = ls;
-        (void)nf;
-        int rk = 0;
-        for (int j = 0; j < D; ++j) { const bool ok = pos[j] && n2 + rk < cap; pos[j] = ok ? rk : -1; if (ok) ++rk; }
-        total = rk;
+    // free local slot ids in ascending order
+    for (int ls = tid; ls < cap; ls += NTH) flag[ls] = ((used[ls >> 5] >> (ls & 31)) & 1u) ? 0 : 1;
+    __syncthreads();
+    {
+        int isfree[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int ls = tid + q * NTH; isfree[q] = ls < cap ? flag[ls] : 0; }
+        __syncthreads();
+        block_scan_flags(flag, cap, wsum);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int ls = tid + q * NTH; if (isfree[q]) freeid[flag[ls]] = ls; }
     }
     __syncthreads();
-    const int spawned = total;
+    // ranks of the spawning detections (ascending detection order), cut off where the table is full
+    for (int j = tid; j < D; j += NTH) flag[j] = pos[j];
+    __syncthreads();
+    const int cand = block_scan_flags(flag, D, wsum);
+    const int room = cap - n2;
+    for (int j = tid; j < D; j += NTH) pos[j] = (pos[j] && flag[j] < room) ? flag[j] : -1;
+    __syncthreads();
+    const int spawned = cand < room ? cand : (room > 0 ? room : 0);
     const uint32_t id0 = st.tracker_id[s];
     for (int j = tid; j < D; j += NTH) {
         const int rk = pos[j];
@@ -269,7 +308,7 @@ static int tdd_step_kcf(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_nde
     if (rc) return rc;
     td_scatter_kernel<<<st.S, 256, 0, c->stream>>>(st, d_dets, d_ndet);
     rc = per_class(KCF_MODE_UPDATE, st.jl_count, st.jl_slot, st.jl_frame, st.jl_box, 0); if (rc) return rc;        // top/td.cpp:512-582
-    td_lifecycle_kernel<<<st.S, 256, sizeof(int) * 2048, c->stream>>>(st, c->kal, d_dets, d_ndet);
+    td_lifecycle_kernel<<<st.S, 256, sizeof(int) * 3072, c->stream>>>(st, c->kal, d_dets, d_ndet);
     rc = per_class(KCF_MODE_UPDATE, st.sp_count, st.sp_slot, st.sp_frame, st.sp_box, 0); if (rc) return rc;        // top/td.cpp:629-641
     CU(cudaGetLastError());
     c->launches += 3;           // job lists, scatter, lifecycle (the fused launches and the association count themselves)
@@ -292,7 +331,7 @@ int mot_tdd_step_dev(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet)
     td_scatter_kernel<<<st.S, 256, 0, c->stream>>>(st, d_dets, d_ndet);
     rc = kalman_update(c->kal, n, st.slot, st.bbox, c->stream);
     if (rc) return mot_fail(MOT_ERR_CUDA, "kalman_update launch failed (%d)", rc);
-    td_lifecycle_kernel<<<st.S, 256, sizeof(int) * 2048, c->stream>>>(st, c->kal, d_dets, d_ndet);
+    td_lifecycle_kernel<<<st.S, 256, sizeof(int) * 3072, c->stream>>>(st, c->kal, d_dets, d_ndet);
     CU(cudaGetLastError());
     c->launches += 4;           // predict, scatter, update, lifecycle (+2 counted by the association call)
     return 0;
