@@ -11,7 +11,12 @@ namespace mot {
 // float; one Newton step on q0 = N * RN(1/1000) gives the correctly rounded quotient without touching the FP64 pipe.
 __device__ __forceinline__ float bgr_gray(const uint8_t *p)
 {
-    const float nf = (float)(144 * (int)p[0] + 587 * (int)p[1] + 299 * (int)p[2]);
+    // three integer multiply-adds (FMA pipe); written as PTX because the compiler otherwise packs the bytes with three
+    // permutes to feed a dot-product instruction, which costs two instructions more on the busier ALU pipe
+    unsigned n = 144u * p[0];
+    asm("mad.lo.u32 %0, %1, 587, %0;" : "+r"(n) : "r"((unsigned)p[1]));
+    asm("mad.lo.u32 %0, %1, 299, %0;" : "+r"(n) : "r"((unsigned)p[2]));
+    const float nf = (float)n;
     const float rcp = 1.0f / 1000.0f;
     const float q0 = __fmul_rn(nf, rcp);
     const float rem = __fmaf_rn(-q0, 1000.0f, nf);
