@@ -84,7 +84,8 @@ __device__ __forceinline__ uint32_t grad_pixel_k(float gx, float gy, const float
     // rcpps of that value: rcp(T * 2^-q) = rcp(T) * 2^q exactly, and rcp(T) / 16 sits next to T in the fused table.
     const uint32_t u = __float_as_uint(m2);
     const float2 tr = rsrc_tab[((u >> k.sh_rs) & k.mask_rs) ^ k.flip_rs];
-    const uint32_t qs = (((u + 0x00800000u) >> 24) - 64u) << 23;
+    // q << 23 = qs - 0x20000000 with qs as below; the constant is folded into the device copy of the table (mot_capi.cu)
+    const uint32_t qs = ((u + 0x00800000u) >> 1) & 0x7F800000u;
     float m = __uint_as_float(__float_as_uint(tr.x) - qs);
     uint32_t M0 = __float_as_uint(tr.y) + qs;
     if (u <= k.u_cap) { m = 1e10f; M0 = k.m0_cap_bits; }                  // MIN(rsqrtps(M2), 1e10f) saturates (zero / denormal / tiny M2)

@@ -223,8 +223,19 @@ int mot_ctx_create(mot_ctx_t **out, int device, int frame_w, int frame_h, int ma
         CU(cudaMemcpy(c->d_tab_rsqrt, ft.rsqrt_tab.data(), sizeof(float) * ft.rsqrt_tab.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_tab_rcp, ft.rcp_tab.data(), sizeof(float) * ft.rcp_tab.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_tab_bin, ft.bin_tab.data(), sizeof(uint32_t) * ft.bin_tab.size(), cudaMemcpyHostToDevice));
-        CU(cudaMalloc(&c->d_tab_rsrc, sizeof(float) * ft.rsrc_tab.size()));
-        CU(cudaMemcpy(c->d_tab_rsrc, ft.rsrc_tab.data(), sizeof(float) * ft.rsrc_tab.size(), cudaMemcpyHostToDevice));
+        {
+            // device copy of the fused {rsqrt, rcp/16} table with the constant part of the exponent arithmetic folded in:
+            // the kernel computes m = T * 2^-q and M/16 = R16 * 2^q as bits(T) - qs and bits(R16) + qs with
+            // qs = (q << 23) = qs' - 0x20000000, qs' = ((bits(M2) + 0x00800000) >> 1) & 0x7F800000; storing
+            // bits(T) + 0x20000000 and bits(R16) - 0x20000000 saves the subtraction per pixel (fhog_common.cuh)
+            std::vector<uint32_t> biased(ft.rsrc_tab.size());
+            for (size_t i = 0; i < biased.size(); ++i) {
+                uint32_t u; memcpy(&u, &ft.rsrc_tab[i], 4);
+                biased[i] = (i & 1) ? u - 0x20000000u : u + 0x20000000u;
+            }
+            CU(cudaMalloc(&c->d_tab_rsrc, sizeof(float) * biased.size()));
+            CU(cudaMemcpy(c->d_tab_rsrc, biased.data(), sizeof(uint32_t) * biased.size(), cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&c->d_tab_bin2, sizeof(uint32_t) * (ft.bin2_tab.size() + 4)));
         CU(cudaMemset(c->d_tab_bin2, 0, sizeof(uint32_t) * (ft.bin2_tab.size() + 4)));
         CU(cudaMemcpy(c->d_tab_bin2, ft.bin2_tab.data(), sizeof(uint32_t) * ft.bin2_tab.size(), cudaMemcpyHostToDevice));
