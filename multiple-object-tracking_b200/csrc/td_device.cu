@@ -217,9 +217,9 @@ using namespace mot;
 
 struct mot_tdd_s {
     mot_ctx_t *ctx;
-    TddState st;
+    TddState st{};
     int cost_mode;
-    double *d_dist, *d_cost;
+    double *d_dist = nullptr, *d_cost = nullptr;
     DevBuf<mot_bbox_t> d_dets; DevBuf<int> d_ndet;
     PinBuf<mot_bbox_t> h_dets; PinBuf<int> h_ndet;
     // The host-array step is launch-latency bound (two copies + six kernels for a few hundred tracks): its fixed sequence is
@@ -232,16 +232,20 @@ extern "C" {
 
 static int tdd_step_kcf(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet);
 
-int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int max_det, int cost_mode)
+static void tdd_release(mot_tdd_t *t)
 {
-    if (!out || !c || n_streams <= 0 || cap <= 0 || cap > 1024 || max_det <= 0 || max_det > 1024) return mot_fail(MOT_ERR_ARG, "mot_tdd_create: bad argument (cap and max_det must be in 1..1024)");
-    const bool kcf = c->kind == MOT_TRACKER_KCF;
-    if (kcf && c->n_frames < n_streams) return mot_fail(MOT_ERR_ARG, "the KCF frame loop reads stream s from frame slot s: the context has %d frame slots, %d are needed", c->n_frames, n_streams);
-    if ((long)n_streams * cap > c->max_tracks) return mot_fail(MOT_ERR_CAPACITY, "context has %d track slots, %d streams x %d are needed", c->max_tracks, n_streams, cap);
-    for (char u : c->used) if (u) return mot_fail(MOT_ERR_ARG, "the context already holds host-managed trackers");
-    CU(cudaSetDevice(c->device));
-    mot_tdd_t *t = new mot_tdd_s();
-    t->ctx = c; t->cost_mode = cost_mode;
+    TddState &st = t->st;
+    cudaFree(st.ntracks); cudaFree(st.tracker_id); cudaFree(st.tid); cudaFree(st.slot); cudaFree(st.age); cudaFree(st.vis); cudaFree(st.invis);
+    cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost);
+    cudaFree(st.jl_slot); cudaFree(st.jl_frame); cudaFree(st.jl_box); cudaFree(st.sp_slot); cudaFree(st.sp_frame); cudaFree(st.sp_box);
+    cudaFree(st.jl_count); cudaFree(st.dropped);
+    if (t->graph) cudaGraphExecDestroy(t->graph);
+    t->d_dets.release(); t->d_ndet.release(); t->h_dets.release(); t->h_ndet.release();
+}
+
+// every allocation of a loop object; on failure the caller releases whatever was obtained (all pointers start out null)
+static int tdd_alloc(mot_tdd_t *t, mot_ctx_t *c, int n_streams, int cap, int max_det, bool kcf)
+{
     TddState &st = t->st;
     st.S = n_streams; st.cap = cap; st.max_det = max_det; st.md = cap > max_det ? cap : max_det;
     const size_t n = (size_t)n_streams * cap;
@@ -259,13 +263,28 @@ int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int ma
     if (kcf) {
         static const int side[3] = { 8, 16, 32 };
         for (int hi = 0; hi < 3; ++hi)
-            for (int wi = 0; wi < 3; ++wi) { const int rc = mot_ctx_kcf_class(c, side[hi], side[wi], &st.cls_id[3 * hi + wi]); if (rc) { delete t; return rc; } }
+            for (int wi = 0; wi < 3; ++wi) { const int rc = mot_ctx_kcf_class(c, side[hi], side[wi], &st.cls_id[3 * hi + wi]); if (rc) return rc; }
         CU(cudaMalloc(&st.jl_slot, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.jl_frame, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.jl_box, sizeof(int) * 9 * n));
         CU(cudaMalloc(&st.sp_slot, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.sp_frame, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.sp_box, sizeof(int) * 9 * n));
         CU(cudaMalloc(&st.jl_count, sizeof(int) * 18)); st.sp_count = st.jl_count + 9;
         CU(cudaMalloc(&st.dropped, sizeof(int) * n_streams));
         CU(cudaMemsetAsync(st.dropped, 0, sizeof(int) * n_streams, c->stream));
     }
+    return 0;
+}
+
+int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int max_det, int cost_mode)
+{
+    if (!out || !c || n_streams <= 0 || cap <= 0 || cap > 1024 || max_det <= 0 || max_det > 1024) return mot_fail(MOT_ERR_ARG, "mot_tdd_create: bad argument (cap and max_det must be in 1..1024)");
+    const bool kcf = c->kind == MOT_TRACKER_KCF;
+    if (kcf && c->n_frames < n_streams) return mot_fail(MOT_ERR_ARG, "the KCF frame loop reads stream s from frame slot s: the context has %d frame slots, %d are needed", c->n_frames, n_streams);
+    if ((long)n_streams * cap > c->max_tracks) return mot_fail(MOT_ERR_CAPACITY, "context has %d track slots, %d streams x %d are needed", c->max_tracks, n_streams, cap);
+    for (char u : c->used) if (u) return mot_fail(MOT_ERR_ARG, "the context already holds host-managed trackers");
+    CU(cudaSetDevice(c->device));
+    mot_tdd_t *t = new mot_tdd_s();
+    t->ctx = c; t->cost_mode = cost_mode;
+    const int rc = tdd_alloc(t, c, n_streams, cap, max_det, kcf);
+    if (rc) { tdd_release(t); delete t; return rc; }
     for (long i = 0; i < (long)n_streams * cap; ++i) c->used[i] = 1;        // these slots now belong to the device-side tables
     c->free_slots.erase(std::remove_if(c->free_slots.begin(), c->free_slots.end(), [&](int s) { return s < n_streams * cap; }), c->free_slots.end());
     *out = t;
@@ -276,13 +295,9 @@ void mot_tdd_destroy(mot_tdd_t *t)
 {
     if (!t) return;
     cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->stream);
-    TddState &st = t->st;
-    cudaFree(st.ntracks); cudaFree(st.tracker_id); cudaFree(st.tid); cudaFree(st.slot); cudaFree(st.age); cudaFree(st.vis); cudaFree(st.invis);
-    cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost);
-    if (st.kcf) { cudaFree(st.jl_slot); cudaFree(st.jl_frame); cudaFree(st.jl_box); cudaFree(st.sp_slot); cudaFree(st.sp_frame); cudaFree(st.sp_box); cudaFree(st.jl_count); cudaFree(st.dropped); }
-    if (t->graph) cudaGraphExecDestroy(t->graph);
-    t->d_dets.release(); t->d_ndet.release(); t->h_dets.release(); t->h_ndet.release();
+    const TddState &st = t->st;
     for (long i = 0; i < (long)st.S * st.cap; ++i) { t->ctx->used[i] = 0; t->ctx->free_slots.push_back((int)i); }
+    tdd_release(t);
     delete t;
 }
 
