@@ -18,8 +18,8 @@ def one_box(l, t, rows, cols, typ=1):
     return b
 
 
-@pytest.mark.parametrize("rows,cols", [(128, 128), (64, 64), (64, 128), (130, 67), (35, 34),
-                                       (120, 160), (100, 60), (37, 53), (150, 91), (8, 8)])   # second row: sizes without a fused kernel (any-size path)
+@pytest.mark.parametrize("rows,cols", [(128, 128), (64, 64), (64, 128), (130, 67), (35, 34), (35, 66), (66, 33), (129, 34), (34, 131),
+                                       (120, 160), (100, 60), (37, 53), (150, 91), (8, 8)])   # first row: every fused class (cell sides 8/16/32 in all nine combinations, 64x128 px = 16x32 cells included); second row: any-size path
 def test_stagewise_vs_oracle(oracle, rows, cols):
     require_gpu()
     M = mot()
