@@ -95,3 +95,14 @@ def test_port_equals_golden_fixture():
             assert np.array_equal(det[k], want[k]), k
         # the scores go through expf: identical with the same libm, else equal to the last bits
         assert np.allclose(det["score"], want["score"], rtol=2e-6, atol=0)
+
+
+def test_expf_recipe_reproduces_the_c_library():
+    """What a bit-exact GPU version of the decode step needs: the C library's expf restated in plain double operations
+    (oracle/port/port_expf.c) equals it on every 97th float bit pattern with |x| <= 87 (23 million arguments)."""
+    port = oraclelib.Oracle("port").kcf
+    port.port_expf_mismatches.restype = C.c_long
+    tested = C.c_long(0)
+    bad = port.port_expf_mismatches(C.c_uint32(97), C.byref(tested))
+    assert tested.value > 20_000_000
+    assert bad == 0, "%d of %d differ: this C library evaluates expf differently (glibc < 2.27?)" % (bad, tested.value)
