@@ -85,6 +85,16 @@ int mot_overlay_batch(mot_ctx_t *ctx, int n, const int *frame_slots, const mot_b
 /* colormap[hashcolor(tid) & 255]: the colour the reference gives track `tid` (top/td.cpp:295-305, 620, 652-699). */
 uint32_t mot_track_color(uint32_t tid);
 
+/* ---- detector post-processing (replaces decode_netout / correct_yolo_boxes / sort / do_nms, detectors/yolo3.cpp:141-356, and
+ *      the per-image driver in tensorRunB, :487-527) ---------------------------------------------------------------------- */
+
+/* out0/out1/out2: the three YOLO3 output maps of ONE image (host memory; grids (tensor/32) << 0, 1, 2; 3 anchors x (5 + classes)
+ * values per cell), anchors18 as in yolo3_options_t (:88-94).  Writes the detections exactly as the reference would put them into
+ * bbox_chain_t (same boxes, classes, scores and order: the C library's expf, the exchange sort and the never-cleared suppression
+ * flags are reproduced) and returns their number (>= 0), or a negative error (MOT_ERR_CAPACITY beyond 4096 candidates). */
+int mot_yolo_post(mot_ctx_t *ctx, const float *out0, const float *out1, const float *out2, const int *anchors18, float obj_thresh, float nms_thresh,
+                  int tensor_h, int tensor_w, int image_h, int image_w, int num_classes, mot_bbox_t *out, int max_out);
+
 /* ---- tracker plugin, batched (replaces tracker_new/predict/update/delete, trackers/kcf.cpp:455-491 and
  *      trackers/kalman.cpp:131-163; one call = the reference's loop over tracks, top/td.cpp:344-384, 512-582) --- */
 

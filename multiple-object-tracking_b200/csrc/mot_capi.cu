@@ -4,6 +4,7 @@
 #include "mot_ctx.h"
 #include "fhog_tables.h"
 #include "overlay.h"
+#include "yolo_post.h"
 
 #include <algorithm>
 #include <cmath>
@@ -158,6 +159,14 @@ static int sync_frame_ptrs(mot_ctx_t *c)
 }
 
 extern "C" { static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, const int *d_frames, mot_bbox_t *d_boxes, int clamp); }
+
+namespace {
+struct DevScratch {                      // frees whatever was allocated when the call returns, on every path
+    std::vector<void *> p;
+    ~DevScratch() { for (void *q : p) cudaFree(q); }
+    template <class T> cudaError_t get(T **out, size_t bytes) { void *q = nullptr; const cudaError_t e = cudaMalloc(&q, bytes); if (e == cudaSuccess) { p.push_back(q); *out = (T *)q; } return e; }
+};
+}
 
 int mot_ctx_kcf_class(mot_ctx_t *c, int hr, int wc, int *cls_out) { return get_class(c, hr, wc, cls_out); }
 
@@ -355,6 +364,37 @@ int mot_overlay_batch(mot_ctx_t *c, int n, const int *frame_slots, const mot_bbo
     c->launches += 1;
     CU(cudaStreamSynchronize(c->stream));      // the pinned staging arrays are reused by the next call
     return 0;
+}
+
+// ---- detector post-processing (detectors/yolo3.cpp:141-356, 487-527) ---------------------------------------------------------
+int mot_yolo_post(mot_ctx_t *c, const float *out0, const float *out1, const float *out2, const int *anchors18, float obj_thresh, float nms_thresh,
+                  int tensor_h, int tensor_w, int image_h, int image_w, int num_classes, mot_bbox_t *out, int max_out)
+{
+    if (!c || !out0 || !out1 || !out2 || !anchors18 || !out || max_out <= 0) return fail(MOT_ERR_ARG, "mot_yolo_post: null argument");
+    if (tensor_h < 32 || tensor_w < 32 || tensor_h % 32 || tensor_w % 32 || image_h <= 0 || image_w <= 0 || num_classes < 1 || num_classes > 1024)
+        return fail(MOT_ERR_SHAPE, "mot_yolo_post: tensor %dx%d (multiples of 32), image %dx%d, %d classes (1..1024)", tensor_h, tensor_w, image_h, image_w, num_classes);
+    CU(cudaSetDevice(c->device));
+    DevScratch ds;
+    const float *host[3] = { out0, out1, out2 };
+    float *d_o[3]; int *d_anch, *d_cnt; void *d_cand; mot_bbox_t *d_boxes;
+    const size_t per = (size_t)3 * (5 + num_classes);
+    for (int k = 0; k < 3; ++k) {
+        const size_t nfl = (size_t)((tensor_h / 32) << k) * ((tensor_w / 32) << k) * per;
+        CU(ds.get(&d_o[k], sizeof(float) * nfl));
+        CU(cudaMemcpyAsync(d_o[k], host[k], sizeof(float) * nfl, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(ds.get(&d_anch, sizeof(int) * 18)); CU(ds.get(&d_cnt, sizeof(int) * 2)); CU(ds.get(&d_cand, yolo_cand_bytes())); CU(ds.get(&d_boxes, sizeof(mot_bbox_t) * max_out));
+    CU(cudaMemcpyAsync(d_anch, anchors18, sizeof(int) * 18, cudaMemcpyHostToDevice, c->stream));
+    const float *d_oc[3] = { d_o[0], d_o[1], d_o[2] };
+    const int rc = yolo_post_launch(d_oc, d_anch, obj_thresh, nms_thresh, tensor_h, tensor_w, image_h, image_w, num_classes, d_cand, d_cnt, d_boxes, max_out, d_cnt + 1, c->stream);
+    if (rc) return fail(MOT_ERR_CUDA, "YOLO post-processing launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 4;
+    int h_cnt[2] = { 0, 0 };
+    CU(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h_cnt[0] > yolo_cap()) return fail(MOT_ERR_CAPACITY, "%d candidates pass the objectness threshold (capacity %d)", h_cnt[0], yolo_cap());
+    if (h_cnt[1] > 0) CU(cudaMemcpy(out, d_boxes, sizeof(mot_bbox_t) * h_cnt[1], cudaMemcpyDeviceToHost));
+    return h_cnt[1];
 }
 
 // ---- tracker slots -----------------------------------------------------------------------------------------------------

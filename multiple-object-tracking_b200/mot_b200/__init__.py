@@ -20,7 +20,7 @@ BBOX_DTYPE = np.dtype([("l", "<i4"), ("t", "<i4"), ("b", "<i4"), ("r", "<i4"), (
 
 EXPORTS = [
     "mot_ctx_create", "mot_ctx_destroy", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
-    "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_tracker_new_batch", "mot_tracker_delete_batch",
+    "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_yolo_post", "mot_tracker_new_batch", "mot_tracker_delete_batch",
     "mot_predict_batch", "mot_update_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
     "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_get", "mot_td_last", "mot_td_overlay",
@@ -168,6 +168,17 @@ class Context:
         out = np.zeros((self.H, self.W, 3), np.uint8)
         _chk(lib().mot_frame_download(self.h, slot, _p(out), out.strides[0]))
         return out
+
+    def yolo_post(self, outs, anchors, obj_thresh, nms_thresh, th, tw, ih, iw, nc, max_out=4096):
+        """detectors/yolo3.cpp:141-356 + 487-527 on the device: three output maps of one image -> detections (bbox array)."""
+        o = [np.ascontiguousarray(a, np.float32) for a in outs]; an = np.ascontiguousarray(anchors, np.int32)
+        out = np.zeros(max_out, BBOX_DTYPE)
+        f = lib().mot_yolo_post
+        f.restype = C.c_int
+        n = f(self.h, _p(o[0]), _p(o[1]), _p(o[2]), _p(an), C.c_float(obj_thresh), C.c_float(nms_thresh), th, tw, ih, iw, nc, _p(out), max_out)
+        if n < 0:
+            _chk(n)
+        return out[:n]
 
     def overlay(self, frame_slots, boxes, rgb, thickness=3):
         """Tracking rectangles of top/td.cpp:647-733 drawn into the frames on the device, entries in order."""

@@ -106,3 +106,32 @@ def test_expf_recipe_reproduces_the_c_library():
     bad = port.port_expf_mismatches(C.c_uint32(97), C.byref(tested))
     assert tested.value > 20_000_000
     assert bad == 0, "%d of %d differ: this C library evaluates expf differently (glibc < 2.27?)" % (bad, tested.value)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("th,tw,ih,iw,nc,nobj,obj,nms", [
+    (416, 416, 720, 1280, 80, 60, 0.5, 0.45), (480, 480, 480, 640, 1, 40, 0.5, 0.45), (416, 416, 1080, 1920, 3, 120, 0.3, 0.3),
+    (320, 608, 720, 1280, 20, 80, 0.25, 0.6), (416, 416, 1280, 720, 5, 200, 0.1, 0.45)])
+def test_gpu_yolo_post_equals_oracle(th, tw, ih, iw, nc, nobj, obj, nms):
+    """mot_yolo_post (csrc/yolo_post.cu) against the oracle: same boxes, classes, order and score BITS (expf reproduced in FP64)."""
+    from gpu_common import require_gpu, mot
+    require_gpu()
+    M = mot()
+    ctx = M.Context(iw, ih, max_tracks=4, kind=M.TRACKER_KALMAN)
+    port = oraclelib.Oracle("port").kcf
+    rng = np.random.default_rng(th * 7 + iw + nc)
+    total = 0
+    for rep in range(3):
+        outs = synth_outputs(rng, th, tw, nc, nobj)
+        if rep == 2:                                     # exact score ties: the literal exchange sort path
+            o = outs[0].reshape(th // 32, tw // 32, 3, 5 + nc)
+            o[1, 1, 0, :] = o[2, 2, 1, :] = o[3, 1, 2, :]
+            o[1, 1, 0, 4] = o[2, 2, 1, 4] = o[3, 1, 2, 4] = 5.0
+            o[1, 1, 0, 5] = o[2, 2, 1, 5] = o[3, 1, 2, 5] = 4.0
+        want = run(port, "port_yolo_post", outs, obj, nms, th, tw, ih, iw, nc)
+        got = ctx.yolo_post(outs, ANCHORS, obj, nms, th, tw, ih, iw, nc)
+        assert len(got) == len(want), (rep, len(got), len(want))
+        assert got.tobytes() == want.tobytes(), rep
+        total += len(got)
+    assert total > 0
+    ctx.close()
