@@ -13,7 +13,9 @@
  *     void tracker_update(void*, float*, bbox_t*); void tracker_delete(void*);
  *     void assignmentoptimal(int*, double*, double*, int, int);
  *     extern "C" rgb2Gray(...), bilinearInterpolationGray(...)
- * are provided on top of this ABI by multiple-object-tracking_b200/host/tracker_shim.cpp.
+ * are provided on top of this ABI by multiple-object-tracking_b200/host/tracker_shim.cpp, with bbox_t = struct _bbox_pos_s as in
+ * top/cnntype.h:36-41 so that the mangled names are the ones top/td.cpp links against (tests/test_link_plugin.py links a client
+ * written against the reference's declarations with -Wl,--no-undefined).
  */
 #ifndef MOT_B200_H
 #define MOT_B200_H
@@ -82,7 +84,8 @@ int mot_frame_download(mot_ctx_t *ctx, int slot, uint8_t *host_bgr, int stride_b
  * clipping, exactly as drawRect, except that bytes outside the frame buffer are not written.  A frame bound with
  * mot_frame_bind_device is written in place. */
 int mot_overlay_batch(mot_ctx_t *ctx, int n, const int *frame_slots, const mot_bbox_t *boxes, const uint32_t *rgb, int thickness);
-/* colormap[hashcolor(tid) & 255]: the colour the reference gives track `tid` (top/td.cpp:295-305, 620, 652-699). */
+/* The colour the reference gives track `tid`: colormap[hashcolor(tid + 1) & 255] -- top/td.cpp:619-620 hashes the id counter
+ * after `tid = tracker_id++` (hashcolor :295-305, palette :652-699). */
 uint32_t mot_track_color(uint32_t tid);
 
 /* ---- detector post-processing (replaces decode_netout / correct_yolo_boxes / sort / do_nms, detectors/yolo3.cpp:141-356, and
@@ -101,6 +104,9 @@ int mot_yolo_post(mot_ctx_t *ctx, const float *out0, const float *out1, const fl
 /* tracker_new for n boxes; writes n handles (slot numbers >= 0). */
 int mot_tracker_new_batch(mot_ctx_t *ctx, int n, const mot_bbox_t *boxes, int *handles_out);
 int mot_tracker_delete_batch(mot_ctx_t *ctx, int n, const int *handles);
+/* 1 when mot_tracker_new_batch can build a tracker for this box (Kalman: always; KCF: at least 2x2 cells = 8x8 px and not larger
+ * than the frame), else 0.  The frame loops use it to count-and-skip such detections instead of failing the step. */
+int mot_tracker_spawnable(mot_ctx_t *ctx, const mot_bbox_t *box);
 
 /* tracker_predict for n tracks, fused with the crop + gray + resize in front of it (top/td.cpp:348-364):
  * boxes[i] in  = crop rectangle in frame frame_slots[i] (the caller's tracker_info.bbox),
@@ -122,6 +128,14 @@ int mot_update_gray(mot_ctx_t *ctx, int handle, const float *gray_host, const mo
 
 /* ---- patch preprocessing on its own (replaces rgb2Gray + bilinearInterpolationGray, top/drawlib.c:192-240, 542-637) */
 int mot_crop_gray_resize(mot_ctx_t *ctx, int frame_slot, const mot_bbox_t *box, int rows_d, int cols_d, float *gray_host_out);
+
+/* The reference's two patch helpers with their own signatures' semantics, HOST pointers in and out (one upload, one kernel, one
+ * download): what host/tracker_shim.cpp exports as the C-linkage symbols rgb2Gray / bilinearInterpolationGray of top/td.cpp:245-261.
+ * mot_rgb2gray_host: crop [l..r] x [t..b] (swapped when reversed, top/drawlib.c:203-215) of a BGR u8 frame with rows of stride_bytes
+ * (the reference hard-codes 3840, :9-10) -> gray f32, column-major rows x cols; reads exactly the bytes the reference reads (no clipping).
+ * mot_resize_gray_host: top/drawlib.c:542-637 literally -- both buffers row-major height x width. */
+int mot_rgb2gray_host(mot_ctx_t *ctx, const uint8_t *host_bgr, int stride_bytes, int l, int t, int r, int b, float *gray_host_out);
+int mot_resize_gray_host(mot_ctx_t *ctx, float *dst_host, const float *src_host, int h_src, int w_src, int h, int w);
 
 /* ---- association (replaces the cost loops top/td.cpp:386-457 and assignmentoptimal, trackers/hungarian/hungarian.cpp:29) */
 
@@ -152,6 +166,8 @@ int mot_td_step(mot_td_t *td, const uint8_t *host_bgr, int stride_bytes, const m
 int mot_td_step_multi(mot_td_t **tds, int n_streams, const uint8_t *const *host_bgr, int stride_bytes,
                       const mot_bbox_t *const *dets, const int *ndet);
 int mot_td_ntracks(mot_td_t *td);
+/* detections skipped so far because no tracker can be built for their window (see mot_tracker_spawnable) */
+long mot_td_dropped(mot_td_t *td);
 void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *vis, int *invis);
 /* The overlay loop of top/td.cpp:647-733 for the current track table, drawn on the device into the loop's frame slot
  * (three nested rectangles per track in colour mot_track_color(tid)); read the frame back with mot_frame_download. */

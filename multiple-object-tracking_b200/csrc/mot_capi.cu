@@ -188,6 +188,25 @@ int mot_ctx_kcf_launch(mot_ctx_t *c, int mode, int cls, int n_max, const int *n_
     return 0;
 }
 
+// cost matrices + assignment over device arrays with a caller-owned working copy (n_mat * max_dim^2 doubles): the device-resident
+// frame loop passes its own, so that a captured graph never holds a pointer into a context buffer that may be reallocated
+int mot_ctx_associate_dev(mot_ctx_t *c, int n_mat, const int *d_T, const int *d_D, const mot_bbox_t *d_trk, long trk_stride,
+                          const mot_bbox_t *d_det, long det_stride, int cost_mode, double *d_dist, long dist_stride,
+                          int *d_assign, long assign_stride, double *d_cost, int max_dim, double *d_work)
+{
+    if (n_mat == 0) return 0;
+    if (!d_dist || dist_stride < (long)max_dim * max_dim) return fail(MOT_ERR_ARG, "the cost matrices need a device buffer of max_dim^2 doubles per problem");
+    AssocLaunch A{};
+    A.n_mat = n_mat; A.T = d_T; A.D = d_D; A.trk = d_trk; A.trk_stride = trk_stride; A.det = d_det; A.det_stride = det_stride;
+    A.cost_mode = cost_mode; A.screen_dis = 1.0 / (double)c->W;
+    A.dist = d_dist; A.dist_stride = dist_stride; A.assign = d_assign; A.assign_stride = assign_stride; A.cost = d_cost; A.max_dim = max_dim;
+    A.work = d_work; A.work_stride = (long)max_dim * max_dim;
+    int rc = assoc_cost(A, c->stream); if (rc) return fail(MOT_ERR_CUDA, "cost kernel launch failed (%d)", rc);
+    rc = assoc_solve(A, nullptr, c->stream); if (rc) return fail(MOT_ERR_CUDA, "munkres kernel launch failed (%d)", rc);
+    c->launches += 2;
+    return 0;
+}
+
 // =====================================================================================================================
 extern "C" {
 
@@ -457,6 +476,14 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
     return 0;
 }
 
+int mot_tracker_spawnable(mot_ctx_t *c, const mot_bbox_t *box)
+{
+    if (!c || !box) return 0;
+    if (c->kind != MOT_TRACKER_KCF) return 1;
+    const int rows = box->b - box->t + 1, cols = box->r - box->l + 1;
+    return rows / KCF_CELL >= 2 && cols / KCF_CELL >= 2 && rows <= c->H && cols <= c->W;
+}
+
 int mot_tracker_delete_batch(mot_ctx_t *c, int n, const int *handles)
 {
     if (!c || n < 0 || (n && !handles)) return fail(MOT_ERR_ARG, "mot_tracker_delete_batch: bad argument");
@@ -656,18 +683,9 @@ int mot_associate_batch_dev(mot_ctx_t *c, int n_mat, const int *d_T, const int *
 {
     if (!c || n_mat < 0 || max_dim < 1 || max_dim > 1024) return fail(MOT_ERR_ARG, "mot_associate_batch_dev: bad argument (max_dim %d)", max_dim);
     if (n_mat == 0) return 0;
-    if (!d_dist || dist_stride < (long)max_dim * max_dim) return fail(MOT_ERR_ARG, "the cost matrices need a device buffer of max_dim^2 doubles per problem");
     CU(cudaSetDevice(c->device));
-    AssocLaunch A{};
-    A.n_mat = n_mat; A.T = d_T; A.D = d_D; A.trk = d_trk; A.trk_stride = trk_stride; A.det = d_det; A.det_stride = det_stride;
-    A.cost_mode = cost_mode; A.screen_dis = 1.0 / (double)c->W;
-    A.dist = d_dist; A.dist_stride = dist_stride; A.assign = d_assign; A.assign_stride = assign_stride; A.cost = d_cost; A.max_dim = max_dim;
     CU(c->d_work.ensure((size_t)n_mat * max_dim * max_dim));
-    A.work = c->d_work.p; A.work_stride = (long)max_dim * max_dim;
-    int rc = assoc_cost(A, c->stream); if (rc) return fail(MOT_ERR_CUDA, "cost kernel launch failed (%d)", rc);
-    rc = assoc_solve(A, nullptr, c->stream); if (rc) return fail(MOT_ERR_CUDA, "munkres kernel launch failed (%d)", rc);
-    c->launches += 2;
-    return 0;
+    return mot_ctx_associate_dev(c, n_mat, d_T, d_D, d_trk, trk_stride, d_det, det_stride, cost_mode, d_dist, dist_stride, d_assign, assign_stride, d_cost, max_dim, c->d_work.p);
 }
 
 int mot_associate_batch(mot_ctx_t *c, int n_mat, const int *T, const int *D, const mot_bbox_t *trk, long trk_stride,

@@ -18,11 +18,17 @@ struct SizeClass { int hr, wc, live; bool fast; float *d_wy, *d_wx, *d_yf; doubl
 
 template <class T> struct DevBuf {
     T *p = nullptr; size_t n = 0;
+    // grows geometrically; the old block is released only after the new one exists, so a failed allocation leaves the buffer
+    // as it was (contents are NOT carried over: every user refills the buffer after ensure())
     cudaError_t ensure(size_t want) {
         if (want <= n) return cudaSuccess;
+        const size_t nn = std::max(want, n * 2);
+        T *q = nullptr;
+        const cudaError_t e = cudaMalloc(&q, sizeof(T) * nn);
+        if (e != cudaSuccess) return e;
         if (p) cudaFree(p);
-        n = std::max(want, n * 2);
-        return cudaMalloc(&p, sizeof(T) * n);
+        p = q; n = nn;
+        return cudaSuccess;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
@@ -30,9 +36,13 @@ template <class T> struct PinBuf {
     T *p = nullptr; size_t n = 0;
     cudaError_t ensure(size_t want) {
         if (want <= n) return cudaSuccess;
+        const size_t nn = std::max(want, n * 2);
+        T *q = nullptr;
+        const cudaError_t e = cudaMallocHost(&q, sizeof(T) * nn);
+        if (e != cudaSuccess) return e;
         if (p) cudaFreeHost(p);
-        n = std::max(want, n * 2);
-        return cudaMallocHost(&p, sizeof(T) * n);
+        p = q; n = nn;
+        return cudaSuccess;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
 };
@@ -86,6 +96,9 @@ struct mot_ctx_s {
 // ---- internal services of mot_capi.cu used by the device-resident frame loop (csrc/td_device.cu) ---------------------------
 int mot_ctx_kcf_class(mot_ctx_t *c, int hr, int wc, int *cls_out);       // index of the (created on demand) per-size constant tables
 int mot_ctx_frames_ready(mot_ctx_t *c);                                  // frame pointer table on the device, pending uploads waited for
+int mot_ctx_associate_dev(mot_ctx_t *c, int n_mat, const int *d_T, const int *d_D, const mot_bbox_t *d_trk, long trk_stride,
+                          const mot_bbox_t *d_det, long det_stride, int cost_mode, double *d_dist, long dist_stride,
+                          int *d_assign, long assign_stride, double *d_cost, int max_dim, double *d_work);
 // one fused launch for class `cls` over a device-resident job list: n_dev jobs (at most n_max), job j = (slots[j], frames[j],
 // boxes[box_index[j]])
 int mot_ctx_kcf_launch(mot_ctx_t *c, int mode, int cls, int n_max, const int *n_dev, const int *slots, const int *frames,

@@ -55,14 +55,16 @@ int overlay_draw(uint8_t *const *d_frame_ptr, int n_slots, int stride, long fram
 // a 24-step gray ramp 08 + 0a*i -- except for two gray entries that it spells 0x606060 and 0x666666 (top/td.cpp:693).
 uint32_t track_color(uint32_t tid)
 {
-    uint32_t a = tid;                                   // hashcolor, top/td.cpp:295-305
+    // top/td.cpp:619-620: `tid = tracker_id++; color = hashcolor(tracker_id) & 255` -- the hash is taken of the counter AFTER
+    // the increment, i.e. of tid + 1 (wrapping like the reference's uint32_t counter)
+    uint32_t a = tid + 1u;                              // hashcolor, top/td.cpp:295-305
     a = (a + 0x7ed55d16u) + (a << 12);
     a = (a ^ 0xc761c23cu) ^ (a >> 19);
     a = (a + 0x165667b1u) + (a << 5);
     a = (a + 0xd3a2646cu) ^ (a << 9);
     a = (a + 0xfd7046c5u) + (a << 3);
     a = (a ^ 0xb55a4f09u) ^ (a >> 16);
-    const uint32_t idx = a & 255u;                      // top/td.cpp:620
+    const uint32_t idx = a & 255u;
     static const uint32_t sys16[16] = { 0x000000, 0x800000, 0x008000, 0x808000, 0x000080, 0x800080, 0x008080, 0xc0c0c0,
                                         0x808080, 0xff0000, 0x00ff00, 0xffff00, 0x0000ff, 0xff00ff, 0x00ffff, 0xffffff };
     static const uint32_t lv[6] = { 0x00, 0x5f, 0x87, 0xaf, 0xd7, 0xff };

@@ -219,7 +219,7 @@ struct mot_tdd_s {
     mot_ctx_t *ctx;
     TddState st{};
     int cost_mode;
-    double *d_dist = nullptr, *d_cost = nullptr;
+    double *d_dist = nullptr, *d_cost = nullptr, *d_work = nullptr;      // cost matrices, totals, the solver's working copy (owned: graph-safe)
     DevBuf<mot_bbox_t> d_dets; DevBuf<int> d_ndet;
     PinBuf<mot_bbox_t> h_dets; PinBuf<int> h_ndet;
     // The host-array step is launch-latency bound (two copies + six kernels for a few hundred tracks): its fixed sequence is
@@ -236,7 +236,7 @@ static void tdd_release(mot_tdd_t *t)
 {
     TddState &st = t->st;
     cudaFree(st.ntracks); cudaFree(st.tracker_id); cudaFree(st.tid); cudaFree(st.slot); cudaFree(st.age); cudaFree(st.vis); cudaFree(st.invis);
-    cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost);
+    cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost); cudaFree(t->d_work);
     cudaFree(st.jl_slot); cudaFree(st.jl_frame); cudaFree(st.jl_box); cudaFree(st.sp_slot); cudaFree(st.sp_frame); cudaFree(st.sp_box);
     cudaFree(st.jl_count); cudaFree(st.dropped);
     if (t->graph) cudaGraphExecDestroy(t->graph);
@@ -254,6 +254,7 @@ static int tdd_alloc(mot_tdd_t *t, mot_ctx_t *c, int n_streams, int cap, int max
     CU(cudaMalloc(&st.vis, sizeof(int) * n)); CU(cudaMalloc(&st.invis, sizeof(int) * n)); CU(cudaMalloc(&st.bbox, sizeof(mot_bbox_t) * n));
     CU(cudaMalloc(&st.assign, sizeof(int) * (size_t)n_streams * st.md)); CU(cudaMalloc(&st.assigned_detected, sizeof(int) * (size_t)n_streams * max_det));
     CU(cudaMalloc(&t->d_dist, sizeof(double) * (size_t)n_streams * st.md * st.md)); CU(cudaMalloc(&t->d_cost, sizeof(double) * n_streams));
+    CU(cudaMalloc(&t->d_work, sizeof(double) * (size_t)n_streams * st.md * st.md));
     CU(cudaMemsetAsync(st.ntracks, 0, sizeof(int) * n_streams, c->stream)); CU(cudaMemsetAsync(st.tracker_id, 0, sizeof(uint32_t) * n_streams, c->stream));
     CU(cudaMemsetAsync(st.slot, 0xFF, sizeof(int) * n, c->stream));
     CU(cudaMemsetAsync(st.age, 0, sizeof(int) * n, c->stream)); CU(cudaMemsetAsync(st.vis, 0, sizeof(int) * n, c->stream)); CU(cudaMemsetAsync(st.invis, 0, sizeof(int) * n, c->stream));
@@ -318,8 +319,8 @@ static int tdd_step_kcf(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_nde
         return 0;
     };
     rc = per_class(KCF_MODE_PREDICT, st.jl_count, st.jl_slot, st.jl_frame, st.jl_box, 1); if (rc) return rc;       // top/td.cpp:344-384
-    rc = mot_associate_batch_dev(c, st.S, st.ntracks, d_ndet, st.bbox, st.cap, d_dets, st.max_det, t->cost_mode,
-                                 t->d_dist, (long)st.md * st.md, st.assign, st.md, t->d_cost, st.md);
+    rc = mot_ctx_associate_dev(c, st.S, st.ntracks, d_ndet, st.bbox, st.cap, d_dets, st.max_det, t->cost_mode,
+                               t->d_dist, (long)st.md * st.md, st.assign, st.md, t->d_cost, st.md, t->d_work);
     if (rc) return rc;
     td_scatter_kernel<<<st.S, 256, 0, c->stream>>>(st, d_dets, d_ndet);
     rc = per_class(KCF_MODE_UPDATE, st.jl_count, st.jl_slot, st.jl_frame, st.jl_box, 0); if (rc) return rc;        // top/td.cpp:512-582
@@ -340,8 +341,8 @@ int mot_tdd_step_dev(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet)
     if (st.kcf) return tdd_step_kcf(t, d_dets, d_ndet);
     int rc = kalman_predict(c->kal, n, st.slot, st.bbox, 1, c->W, c->H, c->stream);
     if (rc) return mot_fail(MOT_ERR_CUDA, "kalman_predict launch failed (%d)", rc);
-    rc = mot_associate_batch_dev(c, st.S, st.ntracks, d_ndet, st.bbox, st.cap, d_dets, st.max_det, t->cost_mode,
-                                 t->d_dist, (long)st.md * st.md, st.assign, st.md, t->d_cost, st.md);
+    rc = mot_ctx_associate_dev(c, st.S, st.ntracks, d_ndet, st.bbox, st.cap, d_dets, st.max_det, t->cost_mode,
+                               t->d_dist, (long)st.md * st.md, st.assign, st.md, t->d_cost, st.md, t->d_work);
     if (rc) return rc;
     td_scatter_kernel<<<st.S, 256, 0, c->stream>>>(st, d_dets, d_ndet);
     rc = kalman_update(c->kal, n, st.slot, st.bbox, c->stream);
@@ -373,8 +374,9 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
     }
     if (t->graph && t->graph_stream == c->stream) { CU(cudaGraphLaunch(t->graph, c->stream)); c->launches += 6; return 0; }
     if (t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
-    // first call (or the stream changed): make every lazy allocation happen outside the capture, then record the sequence
-    CU(c->d_work.ensure((size_t)st.S * st.md * st.md));
+    // first call (or the stream changed): record the sequence.  Every buffer the captured kernels touch belongs to this loop
+    // object (tables, cost matrices, the solver's working copy) or to the context's fixed Kalman state: nothing a later call on
+    // the context can reallocate.
     cudaGraph_t g = nullptr;
     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e1 = cudaMemcpyAsync(t->d_dets.p, t->h_dets.p, sizeof(mot_bbox_t) * (size_t)st.S * st.max_det, cudaMemcpyHostToDevice, c->stream);

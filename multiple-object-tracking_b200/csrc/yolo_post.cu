@@ -32,6 +32,9 @@ __constant__ unsigned long long c_exp2f_tab[32] = {      // bits(2^(i/32)) - ((i
 };
 
 // expf as glibc >= 2.27 evaluates it (sysdeps/ieee754/flt-32/e_expf.c), in separate IEEE double operations
+// x86 cvttss2si: truncation toward zero, and INT_MIN for NaN or |v| >= 2^31
+__device__ __forceinline__ int cvttss2si(float v) { return (v >= -2147483648.0f && v < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000; }
+
 __device__ float expf_glibc(float x)
 {
     const double N = 32.0;
@@ -131,8 +134,11 @@ __global__ void __launch_bounds__(YOLO_THREADS) yolo_nms_kernel(const YoloCand *
         const float w = __fmul_rn(__fdiv_rn(ci.u, x_scale), (float)iw);
         const float h = __fmul_rn(__fdiv_rn(ci.w, y_scale), (float)ih);
         YoloDet d;
-        d.xmin = (int)__fsub_rn(x, __fdiv_rn(w, 2.0f)); d.xmax = (int)__fadd_rn(x, __fdiv_rn(w, 2.0f));
-        d.ymin = (int)__fsub_rn(y, __fdiv_rn(h, 2.0f)); d.ymax = (int)__fadd_rn(y, __fdiv_rn(h, 2.0f));
+        // (int) of a float on the reference's x86 build is cvttss2si: out-of-range, infinite and NaN values all give INT_MIN
+        // ("integer indefinite"), whereas CUDA's conversion saturates (+inf -> INT_MAX, NaN -> 0).  A box whose raw t_w / t_h
+        // overflows expf must come out as the reference's, so the x86 result is reproduced.
+        d.xmin = cvttss2si(__fsub_rn(x, __fdiv_rn(w, 2.0f))); d.xmax = cvttss2si(__fadd_rn(x, __fdiv_rn(w, 2.0f)));
+        d.ymin = cvttss2si(__fsub_rn(y, __fdiv_rn(h, 2.0f))); d.ymax = cvttss2si(__fadd_rn(y, __fdiv_rn(h, 2.0f)));
         d.cls = ci.c; d.s = ci.s;
         det[seg[ci.c] + rank] = d;
     }

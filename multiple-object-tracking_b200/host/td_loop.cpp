@@ -32,6 +32,7 @@ struct mot_td_s {
     mot_ctx_t *ctx;
     int frame_slot, cap, cost_mode, kcf;
     uint32_t tracker_id = 0;
+    long dropped = 0;                    // detections that could not spawn a track (window the KCF plugin cannot serve)
     std::vector<TrackInfo> tracks;
     std::vector<mot_bbox_t> predicted;
     std::vector<int> assigned_trackers, assigned_detected;
@@ -145,6 +146,9 @@ int mot_td_step_multi(mot_td_t **tds, int ns, const uint8_t *const *host_bgr, in
         for (int j = 0; j < ndet[s]; ++j) {
             if (td->assigned_detected[j] >= 0) continue;
             if ((int)td->tracks.size() >= td->cap) break;       // the reference has no guard (256-slot stack array, top/td.cpp:312)
+            // a detection the plugin cannot build a tracker for (KCF: smaller than 2x2 cells or larger than the frame) is counted
+            // and skipped BEFORE anything is mutated, like the device-resident loop does: one bad box must not poison the table
+            if (!mot_tracker_spawnable(ctx, &dets[s][j])) { td->dropped++; continue; }
             TrackInfo t{};
             t.tid = td->tracker_id++; t.bbox = dets[s][j]; t.handle = -1;
             td->tracks.push_back(t);
@@ -154,7 +158,15 @@ int mot_td_step_multi(mot_td_t **tds, int ns, const uint8_t *const *host_bgr, in
     if (!nb.empty()) {
         std::vector<int> nh(nb.size());
         rc = mot_tracker_new_batch(ctx, (int)nb.size(), nb.data(), nh.data());
-        if (rc) return rc;
+        if (rc) {
+            // nothing was created (the call validates before it allocates): take the half-made entries out again so that the
+            // next step sees a consistent table; the ids are handed back too
+            for (size_t i = where.size(); i-- > 0;) {
+                mot_td_t *td = tds[where[i].first];
+                td->tracks.pop_back(); td->tracker_id--;
+            }
+            return rc;
+        }
         for (size_t i = 0; i < nb.size(); ++i) tds[where[i].first]->tracks[where[i].second].handle = nh[i];
         if (tds[0]->kcf) { rc = mot_update_batch(ctx, (int)nb.size(), nh.data(), nframe.data(), nb.data()); if (rc) return rc; }   // first update (:629-641)
     }
@@ -169,6 +181,7 @@ int mot_td_step(mot_td_t *td, const uint8_t *host_bgr, int stride_bytes, const m
 }
 
 int mot_td_ntracks(mot_td_t *td) { return td ? (int)td->tracks.size() : 0; }
+long mot_td_dropped(mot_td_t *td) { return td ? td->dropped : 0; }
 
 void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *vis, int *invis)
 {
@@ -183,7 +196,7 @@ void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *v
 }
 
 // The overlay of top/td.cpp:647-733 for the current track table: three nested rectangles per track, in table order, in the
-// colour colormap[hashcolor(tid) & 255] that the reference fixes at spawn time (top/td.cpp:620), drawn on the device into
+// colour colormap[hashcolor(tid + 1) & 255] that the reference fixes at spawn time (top/td.cpp:619-620), drawn on the device into
 // the loop's frame slot.  mot_frame_download brings the annotated frame back.
 int mot_td_overlay(mot_td_t *td)
 {

@@ -20,10 +20,10 @@ BBOX_DTYPE = np.dtype([("l", "<i4"), ("t", "<i4"), ("b", "<i4"), ("r", "<i4"), (
 
 EXPORTS = [
     "mot_ctx_create", "mot_ctx_destroy", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
-    "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_yolo_post", "mot_tracker_new_batch", "mot_tracker_delete_batch",
+    "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_yolo_post", "mot_tracker_new_batch", "mot_tracker_delete_batch", "mot_tracker_spawnable",
     "mot_predict_batch", "mot_update_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
-    "mot_crop_gray_resize", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
-    "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_get", "mot_td_last", "mot_td_overlay",
+    "mot_crop_gray_resize", "mot_rgb2gray_host", "mot_resize_gray_host", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
+    "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_dropped", "mot_td_get", "mot_td_last", "mot_td_overlay",
     "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_read", "mot_tdd_kcf_windows", "mot_tdd_dropped", "mot_tdd_frame_base",
     "mot_debug_enable_dumps", "mot_debug_fetch", "mot_debug_state", "mot_debug_tables",
 ]
@@ -43,7 +43,7 @@ _lib = None
 
 
 def track_color(tid):
-    """colormap[hashcolor(tid) & 255] of top/td.cpp:295-305, 620, 652-699 (host-only helper, no GPU needed)."""
+    """colormap[hashcolor(tid + 1) & 255] of top/td.cpp:295-305, 619-620, 652-699 (host-only helper, no GPU needed)."""
     L = lib()
     L.mot_track_color.restype = C.c_uint32
     L.mot_track_color.argtypes = [C.c_uint32]

@@ -31,6 +31,21 @@ REF_API void ref_kal_state(void *p, double *x, double *P, double *K)
     if (K) memcpy(K, Ks.memptr(), sizeof(double) * 24);
 }
 
+/* a whole sequence in one call (stress tests): n tracks x nframes, measurements meas[f][i], predicted boxes out[f][i] */
+REF_API void ref_kal_run(int n, int nframes, bbox_t *init, bbox_t *meas, bbox_t *out)
+{
+    for (int i = 0; i < n; ++i) {
+        void *t = tracker_new(&init[i]);
+        for (int f = 0; f < nframes; ++f) {
+            bbox_t b = init[i];
+            tracker_predict(t, nullptr, &b);
+            out[(long)f * n + i] = b;
+            tracker_update(t, nullptr, &meas[(long)f * n + i]);
+        }
+        tracker_delete(t);
+    }
+}
+
 #define TDL_PREFIX(n) ref_kal_##n
 #define TDL_EXPORT REF_API
 #define TDL_IS_KCF 0

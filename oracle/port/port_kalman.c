@@ -109,3 +109,19 @@ void port_kal_state(void *p, double *x, double *P, double *K)
     if (P) memcpy(P, k->P, sizeof(k->P));
     if (K) memcpy(K, k->K, sizeof(k->K));
 }
+
+/* a whole sequence in one call (stress tests): n tracks x nframes, measurements meas[f][i], predicted boxes out[f][i] */
+__attribute__((visibility("default")))
+void port_kal_run(int n, int nframes, const bbox_t *init, const bbox_t *meas, bbox_t *out)
+{
+    for (int i = 0; i < n; ++i) {
+        void *t = port_kal_new(&init[i]);
+        for (int f = 0; f < nframes; ++f) {
+            bbox_t b = init[i];
+            port_kal_predict(t, 0, &b);
+            out[(long)f * n + i] = b;
+            port_kal_update(t, 0, &meas[(long)f * n + i]);
+        }
+        port_kal_delete(t);
+    }
+}

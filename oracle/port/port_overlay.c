@@ -5,7 +5,7 @@
  *   port_draw_rect     <- drawRect                       top/drawlib.c:97-151
  *   port_overlay       <- the three-rectangle loop       top/td.cpp:647-733
  *   port_hashcolor     <- hashcolor                      top/td.cpp:295-305
- *   port_track_color   <- colormap[hashcolor(tid) & 255] top/td.cpp:620, 652-699
+ *   port_track_color   <- colormap[hashcolor(tid + 1) & 255] top/td.cpp:619-620, 652-699
  * drawRect addresses pixels linearly (PIXEL_AT(y, x) = 3840 y + 3 x for the hard-coded 1280-pixel frame,
  * top/drawlib.c:9-10) and does no clipping; the restatement takes the byte stride and the buffer size and skips bytes
  * that fall outside the buffer (the original would write out of bounds there).  Cross-checked against the compiled
@@ -68,4 +68,5 @@ uint32_t port_colormap(int idx)
 }
 
 __attribute__((visibility("default")))
-uint32_t port_track_color(uint32_t tid) { return port_colormap((int)(port_hashcolor(tid) & 255u)); }   /* top/td.cpp:620, 699 */
+/* top/td.cpp:619-620: tid = tracker_id++; color = hashcolor(tracker_id) & 255 -> the hash of tid + 1; drawn as colormap[color] (:699) */
+uint32_t port_track_color(uint32_t tid) { return port_colormap((int)(port_hashcolor(tid + 1u) & 255u)); }

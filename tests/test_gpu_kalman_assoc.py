@@ -43,6 +43,39 @@ def test_kalman_state_vs_oracle(oracle):
     ctx.close()
 
 
+def test_kalman_truncation_stress(oracle):
+    """trackers/kalman.cpp:112-115 truncates the FP64 state to an int box: >= 10^6 predicts (2048 tracks x 512 frames; moving,
+    jittered, and STATIC targets whose state converges onto integer measurements, the case where the last bits decide) must give
+    the reference's int boxes.  kalman.cu is built with --fmad=false for this."""
+    require_gpu()
+    M = mot()
+    rng = np.random.default_rng(11)
+    n, nf = 2048, 512
+    ctx = M.Context(1920, 1080, max_tracks=n, kind=M.TRACKER_KALMAN)
+    init = random_boxes(rng, n, 1920, 1080, 40, 120)
+    w = (init["r"] - init["l"]).astype(np.int32); hh = (init["b"] - init["t"]).astype(np.int32)
+    pos = np.stack([init["l"], init["t"]], 1).astype(np.float64)
+    vel = rng.uniform(-3, 3, size=(n, 2)); vel[: n // 4] = 0.0                      # a quarter of the targets never move ...
+    noise = np.full(n, 0.5); noise[: n // 8] = 0.0                                  # ... and half of those are measured without jitter
+    meas = np.zeros((nf, n), BBOX_DTYPE)
+    for f in range(nf):
+        pos += vel + rng.normal(0, 1.0, size=pos.shape) * noise[:, None]
+        z = init.copy()
+        z["l"] = pos[:, 0].astype(np.int32); z["t"] = pos[:, 1].astype(np.int32); z["r"] = z["l"] + w; z["b"] = z["t"] + hh
+        meas[f] = z
+    want = np.zeros((nf, n), BBOX_DTYPE)
+    getattr(oracle.kal, oracle.p + "kal_run")(n, nf, init.ctypes.data_as(C.c_void_p), meas.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p))
+    h = ctx.new(init)
+    bad = 0
+    for f in range(nf):
+        out = ctx.predict(h, None, init)
+        for k in "ltbr":
+            bad += int(np.count_nonzero(out[k] != want[f][k]))
+        ctx.update(h, None, meas[f])
+    assert bad == 0, "%d of %d predicted coordinates differ from the reference's truncated state" % (bad, 4 * n * nf)
+    ctx.close()
+
+
 def _oracle_cost(oracle, trk, det, mode, W):
     T, D = len(trk), len(det)
     nr, nc = (T, D) if T < D else (D, T)

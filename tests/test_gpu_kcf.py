@@ -200,3 +200,34 @@ def test_config1_mixed_radix_window_sequence(oracle):
         b = out.copy()
         ctx.update(h, [0], b); oracle.kcf_update(oh, crop_gray(oracle, frame, ob, 120, 160), ob)
     oracle.kcf_delete(oh); ctx.close()
+
+
+@pytest.mark.parametrize("rows,cols", [(128, 128), (64, 64), (64, 128), (130, 67), (35, 34), (35, 66), (66, 33), (129, 34), (34, 131),
+                                       (120, 160), (100, 60), (37, 53)])
+def test_model_state_with_dumps_off(oracle, rows, cols):
+    """The PRODUCTION instantiation (stage dumps compiled out / never enabled): xf_md and alpha read back with mot_debug_state
+    after six predict + update rounds against the compiled reference's model -- all nine fused classes and any-size windows."""
+    require_gpu()
+    M = mot()
+    W, H = 640, 480
+    sc = Scene(900 + rows + cols, W, H, 3, tsize=40, win=64)
+    frame = sc.render()
+    ctx = M.Context(W, H, max_tracks=8, n_frame_slots=1, kind=M.TRACKER_KCF)
+    ctx.upload(0, frame)
+    b = one_box(180, 140, rows, cols)
+    h = ctx.new(b); ob = box_of(b[0]); oh = oracle.kcf_new(ob)
+    ctx.update(h, [0], b); oracle.kcf_update(oh, crop_gray(oracle, frame, ob, rows, cols), ob)
+    hr, wc = rows // 4, cols // 4
+    S = wc * (hr // 2 + 1)
+    for step in range(6):
+        sc.step(); frame = sc.render(); ctx.upload(0, frame)
+        out = ctx.predict(h, [0], b, clamp=1)
+        oracle.kcf_predict(oh, crop_gray(oracle, frame, ob, rows, cols), ob)
+        ob.l, ob.r = min(max(0, ob.l), W - 1), min(max(0, ob.r), W - 1)
+        ob.t, ob.b = min(max(0, ob.t), H - 1), min(max(0, ob.b), H - 1)
+        assert tuple(int(out[0][k]) for k in "ltbr") == ob.tup(), "step %d" % step
+        b = out.copy()
+        ctx.update(h, [0], b); oracle.kcf_update(oh, crop_gray(oracle, frame, ob, rows, cols), ob)
+        assert rel_err(ctx.state(h[0], "alpha"), oracle.kcf_get(oh, "alpha")) < 5e-5, step
+        assert rel_err(ctx.state(h[0], "xf_md").reshape(31, S, 2), oracle.kcf_get(oh, "xf_md").reshape(31, S, 2)) < 5e-6, step
+    oracle.kcf_delete(oh); ctx.close()

@@ -73,6 +73,24 @@ def test_port_equals_compiled_reference(th, tw, ih, iw, nc, nobj, obj, nms):
     assert total > 0, "the synthetic maps must produce detections"
 
 
+@pytest.mark.skipif(not __import__("os").path.exists(__import__("os").path.join(oraclelib.ODIR, "_ref", "libref_yolo.so")), reason="oracle/_ref/libref_yolo.so not built")
+def test_port_equals_compiled_reference_on_overflowing_sizes():
+    """Raw t_w / t_h large enough that expf overflows: the corner conversions are out of the int range, where the x86 (int) of the
+    reference build yields INT_MIN.  The restatement (same compiler, same conversion) must agree with the compiled reference."""
+    import os
+    ref = C.CDLL(os.path.join(oraclelib.ODIR, "_ref", "libref_yolo.so"))
+    port = oraclelib.Oracle("port").kcf
+    rng = np.random.default_rng(99)
+    th, tw, ih, iw, nc = 416, 416, 720, 1280, 3
+    outs = synth_outputs(rng, th, tw, nc, 30)
+    o = outs[1].reshape((th // 32) * 2, (tw // 32) * 2, 3, 5 + nc)
+    for (r_, c_, a_, tw_, th_) in ((1, 1, 0, 95.0, 0.1), (2, 3, 1, 0.2, 120.0), (3, 2, 2, 60.0, 60.0), (4, 4, 0, 30.0, -3.0)):
+        o[r_, c_, a_, 2] = tw_; o[r_, c_, a_, 3] = th_; o[r_, c_, a_, 4] = 6.0; o[r_, c_, a_, 5] = 5.0
+    a = run(ref, "ref_yolo_post", outs, 0.5, 0.45, th, tw, ih, iw, nc)
+    b = run(port, "port_yolo_post", outs, 0.5, 0.45, th, tw, ih, iw, nc)
+    assert a.tobytes() == b.tobytes() and len(a) > 0
+
+
 def test_no_candidates_gives_no_detections():
     port = oraclelib.Oracle("port").kcf
     outs = [np.full(((416 // 32) << k) ** 2 * 3 * 85, -20.0, np.float32) for k in range(3)]
@@ -118,17 +136,27 @@ def test_gpu_yolo_post_equals_oracle(th, tw, ih, iw, nc, nobj, obj, nms):
     require_gpu()
     M = mot()
     ctx = M.Context(iw, ih, max_tracks=4, kind=M.TRACKER_KALMAN)
-    port = oraclelib.Oracle("port").kcf
+    import os
+    # the strongest oracle present: the reference's own functions compiled from their text (oracle/_ref/libref_yolo.so travels to
+    # the GPU box), else the C restatement that a CPU test pins to them bit for bit
+    ref_so = os.path.join(oraclelib.ODIR, "_ref", "libref_yolo.so")
+    port, fn = (C.CDLL(ref_so), "ref_yolo_post") if os.path.exists(ref_so) else (oraclelib.Oracle("port").kcf, "port_yolo_post")
     rng = np.random.default_rng(th * 7 + iw + nc)
     total = 0
-    for rep in range(3):
+    for rep in range(4):
         outs = synth_outputs(rng, th, tw, nc, nobj)
+        if rep == 3:
+            # extreme raw sizes: expf overflows to +inf (and inf * 0 style NaNs downstream), so the corner conversions leave the
+            # int range -- the reference's x86 (int) gives INT_MIN there, which decides whether the box survives the clipping
+            o = outs[1].reshape((th // 32) * 2, (tw // 32) * 2, 3, 5 + nc)
+            for (r_, c_, a_, tw_, th_) in ((1, 1, 0, 95.0, 0.1), (2, 3, 1, 0.2, 120.0), (3, 2, 2, 60.0, 60.0), (4, 4, 0, 30.0, -3.0)):
+                o[r_, c_, a_, 2] = tw_; o[r_, c_, a_, 3] = th_; o[r_, c_, a_, 4] = 6.0; o[r_, c_, a_, 5] = 5.0
         if rep == 2:                                     # exact score ties: the literal exchange sort path
             o = outs[0].reshape(th // 32, tw // 32, 3, 5 + nc)
             o[1, 1, 0, :] = o[2, 2, 1, :] = o[3, 1, 2, :]
             o[1, 1, 0, 4] = o[2, 2, 1, 4] = o[3, 1, 2, 4] = 5.0
             o[1, 1, 0, 5] = o[2, 2, 1, 5] = o[3, 1, 2, 5] = 4.0
-        want = run(port, "port_yolo_post", outs, obj, nms, th, tw, ih, iw, nc)
+        want = run(port, fn, outs, obj, nms, th, tw, ih, iw, nc)
         got = ctx.yolo_post(outs, ANCHORS, obj, nms, th, tw, ih, iw, nc)
         assert len(got) == len(want), (rep, len(got), len(want))
         assert got.tobytes() == want.tobytes(), rep

@@ -54,8 +54,12 @@ def test_palette_and_hash_match_reference_fixture():
     tids, hashes = GOLD["tids"], GOLD["hashes"]
     assert all(L.port_hashcolor(int(t)) == int(h) for t, h in zip(tids, hashes))
     import mot_b200
-    for t, h in zip(tids[::7], hashes[::7]):
-        want = int(GOLD["colormap"][int(h) & 255])
+    # the colour of a track is fixed by the reference's spawn statement (top/td.cpp:619-620), which hashes the id counter
+    # AFTER `tid = tracker_id++`: the fixture holds (tid, colour index) pairs produced by those two lines themselves
+    sp_tid, sp_col = GOLD["spawn_tid"], GOLD["spawn_color"]
+    assert len(sp_tid) >= 4096 and int(sp_tid[0]) == 0
+    for t, ci in zip(sp_tid[::5], sp_col[::5]):
+        want = int(GOLD["colormap"][int(ci)])
         assert L.port_track_color(int(t)) == want
         assert mot_b200.track_color(int(t)) == want                            # the shipped helper (host code, no GPU needed)
 
