@@ -1,0 +1,700 @@
+// kcf_any.cu -- the fused KCF/DCF kernel for ANY window size: everything between the BGR frame bytes and the updated model in
+// one launch, like kcf_fused.cuh, but with the cell grid (hr x wc) a run-time property of each job.
+//
+// The reference plans FFTW for whatever size the detection box has (trackers/kcf.cpp:146-195) and runs, per track and frame,
+//   rgb2Gray + bilinearInterpolationGray      top/drawlib.c:192-240, 542-637   (called top/td.cpp:348-364)
+//   FHoG::extract -> gradMag -> fhog          libhog/fhog.h:16-38, libhog/gradientMex.cpp:59-100, 148-317
+//   kcf_get_features / kcf_fft2_features      trackers/kcf.cpp:245-267 (31 r2c plans of n0 = f_cols, n1 = f_rows)
+//   predict: kcf_linear_correlation_zf + kcf_predict_ifft2 (+ the clamp of top/td.cpp:378-381)   kcf.cpp:306-362, 397-439
+//   update : kcf_linear_correlation_kf + kcf_update_alpha + kcf_update_xf                         kcf.cpp:269-304, 364-395, 441-476
+// Here one persistent CTA runs one job at a time with all intermediates in shared memory (plan: kcf_any.cuh):
+//   P0  frame rows of the crop through the bulk-copy engine; SSE tables; per-N twiddles and Hann vectors
+//   P1  per strip of pixel columns: bytes -> gray (or the reference's scrambled resample) -> gradient magnitude and orientation bin,
+//       table-emulated SSE arithmetic, bit-exact (fhog_common.cuh)
+//   P2  18-bin cell histograms by ordered gather (the reference's summation order), boundary scaling, cell energies
+//   P3  2x2 block normalisers
+//   P4..P6 per tile of channels: features x Hann window -> row transform (two real columns per complex transform) -> split and
+//       transpose -> column transform -> x conj(model) (predict) or |.|^2 and model lerp (update) -> channel sum, in channel order
+//   P7  predict: x alpha x norm -> inverse column transform -> Hermitian rebuild -> inverse row transform -> first-max argmax ->
+//       box shift (float, truncated) -> optional clamp;   update: kf, alpha lerp, tracker_update bookkeeping
+// Transforms are Stockham mixed-radix passes in shared memory (radices 4, 2, 3, 5, 7 in registers; any other prime factor by its
+// definition), driven by a per-length plan, so every length works; the model is read once and written once per update, coalesced.
+#include "kcf_any.cuh"
+#include "fhog_common.cuh"
+#include "copy_async.cuh"
+
+namespace mot {
+
+namespace {
+
+constexpr int ANY_MAX_STAGES = 7;
+
+__device__ __forceinline__ uint32_t magic_of(uint32_t d) { return d <= 1 ? 0u : (0xFFFFFFFFu / d + 1u); }
+// n / d for n * d < 2^32 (m = magic_of(d))
+__device__ __forceinline__ int fdiv(int n, uint32_t m) { return m ? (int)__umulhi((uint32_t)n, m) : n; }
+
+// Everything about the current window size that costs a division: computed by one warp when the size changes between jobs
+struct AnyJobConst {
+    int hr, wc;
+    AnyGeo g;
+    int nst_r, nst_c;                                   // stages of the length-hr / length-wc transforms
+    int rad_r[ANY_MAX_STAGES], ns_r[ANY_MAX_STAGES]; uint32_t mg_m_r[ANY_MAX_STAGES], mg_ns_r[ANY_MAX_STAGES];
+    int rad_c[ANY_MAX_STAGES], ns_c[ANY_MAX_STAGES]; uint32_t mg_m_c[ANY_MAX_STAGES], mg_ns_c[ANY_MAX_STAGES];
+    uint32_t mg_h0, mg_hr, mg_hr1, mg_sk, mg_jp, mg_jphr, mg_skjp;
+    float norm;                                         // feature_norm_ratio, kcf.cpp:197
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+template <int DIR> __device__ __forceinline__ float2 rot90(float2 a) { return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x); }
+
+// R-point DFT in registers, X[q] = sum_r v[r] exp(DIR 2 pi i q r / R)
+template <int R, int DIR> struct Bfly;
+template <int DIR> struct Bfly<2, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[2]) { const float2 a = v[0], b = v[1]; v[0] = cadd(a, b); v[1] = csub(a, b); }
+};
+template <int DIR> struct Bfly<3, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[3])
+    {
+        const float2 t = cadd(v[1], v[2]);
+        const float2 m = make_float2(v[0].x - 0.5f * t.x, v[0].y - 0.5f * t.y);
+        const float2 d = csub(v[1], v[2]);
+        const float2 r = rot90<DIR>(make_float2(0.8660254038f * d.x, 0.8660254038f * d.y));
+        v[0] = cadd(v[0], t); v[1] = cadd(m, r); v[2] = csub(m, r);
+    }
+};
+template <int DIR> struct Bfly<4, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[4])
+    {
+        const float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = rot90<DIR>(csub(v[1], v[3]));
+        v[0] = cadd(a, c); v[2] = csub(a, c); v[1] = cadd(b, d); v[3] = csub(b, d);
+    }
+};
+template <int DIR> struct Bfly<5, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[5])
+    {
+        const float c1 = 0.3090169944f, c2 = -0.8090169944f, s1 = 0.9510565163f, s2 = 0.5877852523f;
+        const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        const float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+        const float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+        const float2 b1 = rot90<DIR>(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+        const float2 b2 = rot90<DIR>(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+        v[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
+        v[1] = cadd(a1, b1); v[4] = csub(a1, b1); v[2] = cadd(a2, b2); v[3] = csub(a2, b2);
+    }
+};
+template <int DIR> struct Bfly<7, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[7])
+    {
+        const float c1 = 0.6234898019f, c2 = -0.2225209340f, c3 = -0.9009688679f, s1 = 0.7818314825f, s2 = 0.9749279122f, s3 = 0.4338837391f;
+        const float2 t1 = cadd(v[1], v[6]), t2 = cadd(v[2], v[5]), t3 = cadd(v[3], v[4]);
+        const float2 u1 = csub(v[1], v[6]), u2 = csub(v[2], v[5]), u3 = csub(v[3], v[4]);
+        const float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x + c3 * t3.x, v[0].y + c1 * t1.y + c2 * t2.y + c3 * t3.y);
+        const float2 a2 = make_float2(v[0].x + c2 * t1.x + c3 * t2.x + c1 * t3.x, v[0].y + c2 * t1.y + c3 * t2.y + c1 * t3.y);
+        const float2 a3 = make_float2(v[0].x + c3 * t1.x + c1 * t2.x + c2 * t3.x, v[0].y + c3 * t1.y + c1 * t2.y + c2 * t3.y);
+        const float2 b1 = rot90<DIR>(make_float2(s1 * u1.x + s2 * u2.x + s3 * u3.x, s1 * u1.y + s2 * u2.y + s3 * u3.y));
+        const float2 b2 = rot90<DIR>(make_float2(s2 * u1.x - s3 * u2.x - s1 * u3.x, s2 * u1.y - s3 * u2.y - s1 * u3.y));
+        const float2 b3 = rot90<DIR>(make_float2(s3 * u1.x - s1 * u2.x + s2 * u3.x, s3 * u1.y - s1 * u2.y + s2 * u3.y));
+        v[0] = make_float2(v[0].x + t1.x + t2.x + t3.x, v[0].y + t1.y + t2.y + t3.y);
+        v[1] = cadd(a1, b1); v[6] = csub(a1, b1); v[2] = cadd(a2, b2); v[5] = csub(a2, b2); v[3] = cadd(a3, b3); v[4] = csub(a3, b3);
+    }
+};
+
+// One Stockham pass of radix R over `nbatch` sequences of length n (stride 1, `pitch` float2 apart): one butterfly per thread
+// iteration.  Ns = product of the radices of the passes before this one; tw[t] = exp(-2 pi i t / n).
+template <int R, int DIR>
+__device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int Ns, uint32_t mg_m, uint32_t mg_ns,
+                                         int nbatch, int pitch, const float2 *__restrict__ tw, int tid, int NT)
+{
+    const int m = n / R, step = m / Ns, total = nbatch * m;
+    for (int t = tid; t < total; t += NT) {
+        const int b = fdiv(t, mg_m), j = t - b * m;
+        const int k = j - fdiv(j, mg_ns) * Ns;
+        const float2 *src = in + b * pitch + j;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = src[r * m];
+        if (Ns > 1) {
+            const int ks = k * step;                      // k r step < n for every r < R
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                float2 w = tw[ks * r];
+                if (DIR > 0) w.y = -w.y;
+                v[r] = cmul(v[r], w);
+            }
+        }
+        Bfly<R, DIR>::run(v);
+        float2 *dst = out + b * pitch + (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) dst[r * Ns] = v[r];
+    }
+}
+
+// The same pass for any other (prime) radix, straight from the definition: one OUTPUT per thread iteration
+template <int DIR>
+__device__ __forceinline__ void fft_pass_prime(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int R, int Ns, int nbatch, int pitch,
+                                               const float2 *__restrict__ tw, int tid, int NT)
+{
+    const int m = n / R, step = m / Ns, total = nbatch * n;
+    const uint32_t mg_n = magic_of(n), mg_ns = magic_of(Ns), mg_R = magic_of(R);
+    for (int t = tid; t < total; t += NT) {
+        const int b = fdiv(t, mg_n), o = t - b * n;
+        const int oq = fdiv(o, mg_ns), k = o - oq * Ns;            // o = (jhi * R + q) * Ns + k
+        const int jhi = fdiv(oq, mg_R), q = oq - jhi * R;
+        const int j = jhi * Ns + k;
+        int inc = k * step + q * m;                                  // phase advance per r, < 2n
+        if (inc >= n) inc -= n;
+        const float2 *src = in + b * pitch + j;
+        float2 acc = src[0];
+        int ph = 0;
+        for (int r = 1; r < R; ++r) {
+            ph += inc; if (ph >= n) ph -= n;
+            float2 w = tw[ph];
+            if (DIR > 0) w.y = -w.y;
+            const float2 x = src[r * m];
+            acc.x = fmaf(x.x, w.x, fmaf(-x.y, w.y, acc.x));
+            acc.y = fmaf(x.x, w.y, fmaf(x.y, w.x, acc.y));
+        }
+        out[b * pitch + o] = acc;
+    }
+}
+
+// All passes of a batch of transforms; ping-pongs between buf0 (input) and buf1; returns the buffer holding the result.
+// Ends with a barrier after every pass (the next pass, or the caller, reads what other threads wrote).
+template <int DIR>
+__device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, int nst, const int *rad, const int *ns, const uint32_t *mg_m, const uint32_t *mg_ns,
+                                             int nbatch, int pitch, const float2 *tw, int tid, int NT)
+{
+    float2 *in = buf0, *out = buf1;
+    for (int s = 0; s < nst; ++s) {
+        const int R = rad[s], Ns = ns[s];
+        switch (R) {
+        case 4: fft_pass<4, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
+        case 2: fft_pass<2, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
+        case 3: fft_pass<3, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
+        case 5: fft_pass<5, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
+        case 7: fft_pass<7, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
+        default: fft_pass_prime<DIR>(in, out, n, R, Ns, nbatch, pitch, tw, tid, NT); break;
+        }
+        __syncthreads();
+        float2 *q = in; in = out; out = q;
+    }
+    return in;
+}
+
+// ordered gather of the 18-bin histograms, CPT cells per thread interleaved (libhog/gradientMex.cpp:183-230, 308-309)
+template <int CPT>
+__device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, const uint32_t *__restrict__ MB, float *__restrict__ R1, float *__restrict__ Es, int tid, int NT)
+{
+    const int OS = g.wc * g.rs, PC = g.pc, PS = g.ps;
+    int ccx[CPT], ccy[CPT]; bool live[CPT]; float *h[CPT]; const uint32_t *mb0[CPT];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u) {
+        const int cell = tid + u * NT;
+        live[u] = cell < g.nb;
+        const int cc = live[u] ? cell : 0;
+        ccx[u] = fdiv(cc, mg_hr); ccy[u] = cc - ccx[u] * g.hr;
+        h[u] = R1 + ccx[u] * g.rs + ccy[u];
+        mb0[u] = MB + (4 * ccx[u]) * PC + ccy[u];
+        if (live[u])
+            for (int o = 0; o < 18; ++o) h[u][o * OS] = 0.f;
+    }
+    if (!live[0]) return;
+#pragma unroll
+    for (int dx = 0; dx < 8; ++dx) {
+        const float wxv = 0.125f + 0.25f * (float)(dx < 4 ? dx : 7 - dx);
+#pragma unroll
+        for (int dy = 0; dy < 8; ++dy) {
+            const float w = wxv * (0.125f + 0.25f * (float)(dy < 4 ? dy : 7 - dy));     // dyadic weights: exact product
+#pragma unroll
+            for (int u = 0; u < CPT; ++u) {
+                if (!live[u]) continue;
+                const uint32_t mb = mb0[u][dx * PC + (dy & 3) * PS + (dy >> 2)];
+                const float v = __fmul_rn(w, __uint_as_float(mb & ~31u));
+                float *const hb = h[u] + (int)(mb & 31u) * OS;
+                *hb = __fadd_rn(*hb, v);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < CPT; ++u) {
+        if (!live[u]) continue;
+        const int cx = ccx[u], cy = ccy[u];
+        // boundary cells x 8/7 per touching side (gradientMex.cpp:226-229): x first, then y; multiplying by 1.0f is the identity
+        const float sx0 = (cx == 0) ? 8.f / 7.f : 1.f, sy0 = (cy == 0) ? 8.f / 7.f : 1.f;
+        const float sx1 = (cx == g.wc - 1) ? 8.f / 7.f : 1.f, sy1 = (cy == g.hr - 1) ? 8.f / 7.f : 1.f;
+        float e = 0.f, r[18];
+#pragma unroll
+        for (int o = 0; o < 18; ++o) {
+            float v = h[u][o * OS];
+            v = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(v, sx0), sy0), sx1), sy1);
+            h[u][o * OS] = v; r[o] = v;
+        }
+#pragma unroll
+        for (int o = 0; o < 9; ++o) { const float r2 = __fadd_rn(r[o], r[o + 9]); e = __fadd_rn(e, __fmul_rn(r2, r2)); }
+        Es[cx * g.hr + cy] = e;
+    }
+}
+
+}  // namespace
+
+template <int MODE, bool DUMP>
+__global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, const AnyTablesDev at, const int lut_floats, const int smem_floats, int *err_flag)
+{
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t mbar_lut, mbar_raw;
+    __shared__ AnyJobConst jc;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    if (tid == 0) { mbar_init(&mbar_lut, 1); mbar_init(&mbar_raw, 1); jc.hr = -1; jc.wc = -1; }
+    __syncthreads();
+    const bool lut_smem = lut_floats > 0;
+    const int n_rs = 2 * (2 << p.tab.rsqrt_bits), n_bn = (2 * p.tab.bin_nseg + 3) & ~3;
+    const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
+    const int n_jobs = p.n_jobs_dev ? min(*p.n_jobs_dev, p.n_jobs) : p.n_jobs;
+    uint32_t phase = 0;
+
+    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        __syncthreads();                                       // the previous job is done with shared memory (and with jc)
+        // ---------------------------------------------------------------- job descriptor (every thread reads the same words: broadcast)
+        const int slot = p.slots[job];
+        KcfMeta *const meta = p.meta + slot;
+        const int bi = p.box_index ? p.box_index[job] : job;
+        const mot_bbox_t box = p.boxes[bi];
+        const int rows = meta->rows, cols = meta->cols, hr = meta->hr, wc = meta->wc;
+        const bool first_update = meta->first_update != 0;
+        const uint8_t *const frame = (p.gray == nullptr) ? p.frame_ptr[p.frames[job]] : nullptr;
+        float2 *const model = meta->model_ptr ? meta->model_ptr : p.model + (long)slot * p.model_stride;
+        float *const alpha = meta->alpha_ptr ? meta->alpha_ptr : p.alpha + (long)slot * p.alpha_stride;
+
+        if (jc.hr != hr || jc.wc != wc) {                      // block-uniform: the window size changed (first job, mixed launches)
+            __syncthreads();
+            if (warp == 0) {
+                if (lane == 0) {
+                    jc.g = any_geo(hr, wc, lut_floats);
+                    jc.norm = (float)(1.0 / (double)((float)(wc * hr * KCF_CHAN)));
+                    jc.mg_h0 = magic_of(4 * hr); jc.mg_hr = magic_of(hr); jc.mg_hr1 = magic_of(hr - 1); jc.mg_sk = magic_of(hr / 2 + 1);
+                    const int jp = (wc + 1) / 2;
+                    jc.mg_jp = magic_of(jp); jc.mg_jphr = magic_of(jp * hr); jc.mg_skjp = magic_of((hr / 2 + 1) * jp);
+                }
+                if (lane == 1 || lane == 2) {
+                    const int n = lane == 1 ? hr : wc;
+                    const AnyPlan pl = at.plan[n];
+                    int *rad = lane == 1 ? jc.rad_r : jc.rad_c, *ns = lane == 1 ? jc.ns_r : jc.ns_c;
+                    uint32_t *mgm = lane == 1 ? jc.mg_m_r : jc.mg_m_c, *mgn = lane == 1 ? jc.mg_ns_r : jc.mg_ns_c;
+                    int acc = 1;
+                    for (int s = 0; s < (int)pl.nf; ++s) { rad[s] = pl.r[s]; ns[s] = acc; mgm[s] = magic_of(n / pl.r[s]); mgn[s] = magic_of(acc); acc *= pl.r[s]; }
+                    if (lane == 1) jc.nst_r = pl.nf; else jc.nst_c = pl.nf;
+                }
+                __syncwarp();
+                if (lane == 0) { jc.hr = hr; jc.wc = wc; }
+            }
+            __syncthreads();
+        }
+        const AnyGeo &g = jc.g;
+        if (g.total > smem_floats || !g.ok) {                  // cannot happen when the host sized the launch; never run out of bounds
+            if (tid == 0 && err_flag) atomicExch(err_flag, 1);
+            continue;
+        }
+        const int H0 = g.h0, W0 = g.w0, SK = g.sk, S = g.S, JP = g.jp, HP = g.hp, WP = g.wp, NB = g.nb;
+        uint32_t *const MB = reinterpret_cast<uint32_t *>(smem);
+        float *const Bf = smem + g.oB;
+        float *const R1 = Bf;
+        unsigned char *const raw = reinterpret_cast<unsigned char *>(Bf + g.lutp);
+        float *const GSB = Bf + g.lutp + (4 * hr + 3) * (g.raw_pitch / 4);
+        float *const Ns = smem + g.oN, *const Es = smem + g.oE;
+        float2 *const ACC = reinterpret_cast<float2 *>(smem + g.oACC);
+        float2 *const TWR = reinterpret_cast<float2 *>(smem + g.oTWR), *const TWC = reinterpret_cast<float2 *>(smem + g.oTWC);
+        float *const wy_s = smem + g.oWY, *const wx_s = smem + g.oWX, *const red = smem + g.oRED;
+
+        // ---------------------------------------------------------------- P0: staging
+        int l = box.l, t = box.t, r = box.r, b = box.b;
+        if (t > b) { const int q = t; t = b; b = q; }          // top/drawlib.c:203-215
+        if (l > r) { const int q = l; l = r; r = q; }
+        const int rows_s = b - t + 1, cols_s = r - l + 1;
+        const bool identity = (p.gray == nullptr) && rows_s == rows && cols_s == cols;
+        const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols_s - 1, 0, Wm);
+        const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;
+        const bool staged = identity && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0 && (a1 - a0) <= g.raw_pitch && rows_s <= 4 * hr + 3;
+        if (warp == 0) {
+            if (lane == 0) {
+                mbar_expect_tx(&mbar_lut, lut_smem ? (uint32_t)(n_rs + n_bn) * 4u : 0u);
+                if (lut_smem) { bulk_g2s(Bf, p.tab.rsrc_tab, n_rs * 4, &mbar_lut); bulk_g2s(Bf + n_rs, p.tab.bin2_tab, n_bn * 4, &mbar_lut); }
+                mbar_expect_tx(&mbar_raw, staged ? (uint32_t)rows_s * (uint32_t)(a1 - a0) : 0u);
+            }
+            __syncwarp();
+            if (staged)
+                for (int y = lane; y < rows_s; y += 32)
+                    bulk_g2s(raw + y * g.raw_pitch, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar_raw);
+        } else if (warp == 1) {
+            // the model is not needed before the spectral phase: pull it (and alpha) into L2 now
+            if (lane == 0 && (MODE == KCF_MODE_PREDICT || !first_update)) prefetch_l2_bulk(model, (uint32_t)(KCF_CHAN * S * 8) & ~15u);
+            if (lane == 1) prefetch_l2_bulk(alpha, (uint32_t)(S * 4) & ~15u);
+        }
+        {
+            const float2 *twr = at.tw + any_off(hr), *twc = at.tw + any_off(wc);
+            const float *hy = at.hann + any_off(hr), *hx = at.hann + any_off(wc);
+            for (int i = tid; i < hr; i += NT) { TWR[i] = twr[i]; wy_s[i] = 0.5f * hy[i]; }     // halved: carries the x0.5 of hogChannels (exact scaling)
+            for (int i = tid; i < wc; i += NT) { TWC[i] = twc[i]; wx_s[i] = hx[i]; }
+        }
+        // zero border of the (M | bin) layout: columns x+2 in {0, 1, W0+2, W0+3} entirely, rows y+2 in {0, 1, H0+2, H0+3} of the others
+        {
+            const int PC = g.pc, PS = g.ps;
+            for (int k = tid; k < 4 * PC; k += NT) { const int cq = k / PC, o = k - cq * PC; MB[(cq < 2 ? cq : W0 + cq) * PC + o] = 0u; }
+            for (int k = tid; k < 4 * W0; k += NT) {
+                const int x2 = 2 + (k >> 2), q = k & 3;
+                MB[x2 * PC + q * PS + (q < 2 ? 0 : hr)] = 0u;            // y+2 = 0, 1 -> (sub 0, 1; idx 0);  y+2 = H0+2, H0+3 -> (sub 2, 3; idx hr)
+            }
+        }
+        if (warp == 0) { mbar_wait(&mbar_raw, phase); mbar_wait(&mbar_lut, phase); }
+        phase ^= 1u;                                               // one arrival per barrier and job, bytes or not
+        __syncthreads();
+
+        // ---------------------------------------------------------------- P1: per strip, gray -> gradient magnitude + orientation bin
+        {
+            const LutConsts lk = make_lut_consts(p.tab);
+            const float2 *const rsrc = lut_smem ? reinterpret_cast<const float2 *>(Bf) : p.tab.rsrc_tab;
+            const uint32_t *const bn = lut_smem ? reinterpret_cast<const uint32_t *>(Bf) + n_rs : p.tab.bin2_tab;
+            const int GS = g.gs, PC = g.pc, PS = g.ps;
+            const float xs_f = __fdiv_rn((float)cols_s, (float)cols), ys_f = __fdiv_rn((float)rows_s, (float)rows);
+            // gray value of template pixel (x, y): staged frame bytes, the caller's gray patch, plain loads (unaligned frames), or
+            // the reference's resample when the crop has another size than the template
+            auto gray_at = [&](int x, int y) -> float {
+                if (staged) return bgr_gray(raw + y * g.raw_pitch + clampi(l + x, 0, Wm) * 3 - a0);
+                if (p.gray != nullptr) return p.gray[(long)job * p.gray_stride + x * rows + y];
+                if (identity) return bgr_gray(frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + clampi(l + x, 0, Wm) * 3);
+                // the reference resamples a column-major crop as if it were row-major height x width; reproduced through
+                // linear indices (top/drawlib.c:542-637, called as (dst, src, rows_s, cols_s, rows_d, cols_d), top/td.cpp:357-364)
+                const int k = x * rows + y;                                  // column-major template element
+                const int ky = k / cols, kx = k - ky * cols;
+                const float sx = __fmul_rn((float)kx, xs_f), sy = __fmul_rn((float)ky, ys_f);
+                const int x0 = __float2int_rz(sx), y0 = __float2int_rz(sy);
+                const float fx = __fsub_rn(sx, (float)x0), fy = __fsub_rn(sy, (float)y0);
+                const float ifx = __fsub_rn(1.0f, fx), ify = __fsub_rn(1.0f, fy);
+                const int x1 = (x0 + 1 >= cols_s) ? x0 : x0 + 1, y1 = (y0 + 1 >= rows_s) ? y0 : y0 + 1;
+                float c[4];
+                const int sidx[4] = { y0 * cols_s + x0, y0 * cols_s + x1, y1 * cols_s + x0, y1 * cols_s + x1 };
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int sc = sidx[q] / rows_s, sr = sidx[q] - sc * rows_s;     // column-major crop element
+                    c[q] = bgr_gray(frame + (long)clampi(t + sr, 0, Hm) * p.frame_stride + clampi(l + sc, 0, Wm) * 3);
+                }
+                const float l0 = __fadd_rn(__fmul_rn(ifx, c[0]), __fmul_rn(fx, c[1]));
+                const float l1 = __fadd_rn(__fmul_rn(ifx, c[2]), __fmul_rn(fx, c[3]));
+                return __fadd_rn(__fmul_rn(ify, l0), __fmul_rn(fy, l1));
+            };
+            if (DUMP && p.dump.gray)                                        // (test hook) the whole rows x cols patch, column-major
+                for (int k = tid; k < rows * cols; k += NT) { const int x = k / rows; p.dump.gray[(long)job * p.dump.stride_px + k] = gray_at(x, k - x * rows); }
+            for (int xs = 0; xs < W0; xs += g.xw) {
+                const int xe = min(xs + g.xw, W0), nx = xe - xs + 2;
+                // gray of template pixels (x, y), x in [xs-1, xe], y in [-1, H0], coordinates clamped into the template: the clamped
+                // apron turns grad1's one-sided border differences (gradientMex.cpp:15-37) into plain differences
+                for (int yy = warp; yy < H0 + 2; yy += nwarps) {
+                    const int y = clampi(yy - 1, 0, rows - 1);
+                    for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = gray_at(clampi(xs - 1 + lx, 0, cols - 1), y);
+                }
+                __syncthreads();
+                // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin)
+                const int npx = (xe - xs) * H0;
+                for (int k = tid; k < npx; k += NT) {
+                    const int lx = fdiv(k, jc.mg_h0), y = k - lx * H0, x = xs + lx;
+                    const float *gp = GSB + (lx + 1) * GS + y + 1;
+                    const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f, ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
+                    const float gx = __fmul_rn(__fsub_rn(gp[GS], gp[-GS]), rx);
+                    const float gy = __fmul_rn(__fsub_rn(gp[1], gp[-1]), ry);
+                    const uint32_t mb = grad_pixel_k(gx, gy, rsrc, bn, lk);
+                    MB[(x + 2) * PC + ((y + 2) & 3) * PS + ((y + 2) >> 2)] = mb;
+                    if (DUMP && p.dump.m0) {
+                        const long idx = (long)job * p.dump.stride_px + x * H0 + y;
+                        p.dump.m0[idx] = __uint_as_float(mb & ~31u); p.dump.bin[idx] = (int)(mb & 31u);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---------------------------------------------------------------- P2: cell histograms (ordered gather)
+        if (NB <= NT) gather_cells<1>(g, jc.mg_hr, MB, R1, Es, tid, NT);
+        else if (NB <= 2 * NT) gather_cells<2>(g, jc.mg_hr, MB, R1, Es, tid, NT);
+        else { if (tid == 0 && err_flag) atomicExch(err_flag, 2); }
+        __syncthreads();
+        const int OS = wc * g.rs, RS = g.rs;
+        if (DUMP && p.dump.r1) {
+            float *d = p.dump.r1 + (long)job * p.dump.stride_cell * 18;
+            for (int i = tid; i < 18 * NB; i += NT) { const int o = i / NB, c2 = i - o * NB, x = c2 / hr, y = c2 - x * hr; d[i] = R1[o * OS + x * RS + y]; }
+        }
+
+        // ---------------------------------------------------------------- P3: 2x2 block normalisers (hogNormMatrix, gradientMex.cpp:236-253)
+        for (int i = tid; i < (wc - 1) * (hr - 1); i += NT) {
+            const int x = fdiv(i, jc.mg_hr1), y = i - x * (hr - 1);
+            const float eps = 1e-4f / 4 / 4 / 4 / 4 / 4;
+            float e = __fadd_rn(Es[x * hr + y], Es[x * hr + y + 1]);
+            e = __fadd_rn(e, Es[(x + 1) * hr + y]);
+            e = __fadd_rn(e, Es[(x + 1) * hr + y + 1]);
+            e = __fadd_rn(e, eps);
+            const float nv = __fdiv_rn(1.0f, __fsqrt_rn(e));
+            float *const q = Ns + (x + 1) * (hr + 1) + y + 1;
+            const bool xl = x == 0, xh = x == wc - 2, yl = y == 0, yh = y == hr - 2;
+            q[0] = nv;
+            if (yl) q[-1] = nv;
+            if (yh) q[1] = nv;
+            if (xl) { q[-(hr + 1)] = nv; if (yl) q[-(hr + 1) - 1] = nv; if (yh) q[-(hr + 1) + 1] = nv; }
+            if (xh) { q[(hr + 1)] = nv; if (yl) q[(hr + 1) - 1] = nv; if (yh) q[(hr + 1) + 1] = nv; }
+        }
+        __syncthreads();
+        if (DUMP && p.dump.nrm) {
+            float *d = p.dump.nrm + (long)job * ((wc + 1) * (hr + 1));
+            for (int i = tid; i < (wc + 1) * (hr + 1); i += NT) d[i] = Ns[i];
+        }
+
+        // ---------------------------------------------------------------- P4..P6: spectral phase, one tile of channels at a time
+        const bool first = (MODE == KCF_MODE_UPDATE) && first_update;
+        const float fac = first ? 1.0f : p.factor;                         // kcf.cpp:443
+        const float omf = __fsub_rn(1.0f, fac);
+        const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
+        float2 *const X0 = reinterpret_cast<float2 *>(smem);
+        float2 *const X1 = X0 + g.tc * g.per_ch;
+        for (int c0 = 0; c0 < KCF_CHAN; c0 += g.tc) {
+            const int c1 = min(KCF_CHAN, c0 + g.tc), nch = c1 - c0;
+            // ---- features of two adjacent cell columns (2jp, 2jp+1) as the real / imaginary part of one sequence along the rows
+            {
+                const int n1 = max(0, min(c1, 27) - c0);                  // type-1 channels of this tile (gradientMex.cpp:266-270)
+                const int per = JP * hr;
+                for (int k = tid; k < n1 * per; k += NT) {
+                    const int cc = fdiv(k, jc.mg_jphr), rem = k - cc * per, jp = fdiv(rem, jc.mg_hr), i = rem - jp * hr;
+                    const int c = c0 + cc;
+                    const float wyi = wy_s[i];
+                    float f[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int j = 2 * jp + q;
+                        f[q] = 0.f;
+                        if (j < wc) {
+                            const float *const n0 = Ns + j * (hr + 1) + i, *const n1p = n0 + (hr + 1);
+                            const float *const ra = R1 + (c < 18 ? c : c - 18) * OS + j * RS + i;
+                            const float rv = (c < 18) ? ra[0] : __fadd_rn(ra[0], ra[9 * OS]);       // R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309)
+                            float hsum = __fadd_rn(fminf(__fmul_rn(rv, n1p[1]), 0.2f), fminf(__fmul_rn(rv, n1p[0]), 0.2f));
+                            hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[1]), 0.2f));
+                            hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[0]), 0.2f));
+                            f[q] = __fmul_rn(hsum, __fmul_rn(wyi, wx_s[j]));                       // (hsum * 0.5) * (wy * wx), kcf.cpp:251-258
+                            if (DUMP && p.dump.feat) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j * hr + i] = f[q];
+                        }
+                    }
+                    X0[(cc * JP + jp) * HP + i] = make_float2(f[0], f[1]);
+                }
+                if (c1 > 27) {
+                    // texture channels 27..30 (hogChannels type 2, gradientMex.cpp:271-275): the 18 orientation loads of a cell are
+                    // shared by its four block normalisers
+                    const int tlo = max(c0, 27);
+                    for (int k = tid; k < per; k += NT) {
+                        const int jp = fdiv(k, jc.mg_hr), i = k - jp * hr;
+                        const float wyi = wy_s[i];
+                        float f[2][4];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int j = 2 * jp + q;
+#pragma unroll
+                            for (int bq = 0; bq < 4; ++bq) f[q][bq] = 0.f;
+                            if (j < wc) {
+                                const float *const n0 = Ns + j * (hr + 1) + i, *const n1p = n0 + (hr + 1);
+                                const float nv0 = n1p[1], nv1 = n1p[0], nv2 = n0[1], nv3 = n0[0];
+                                float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+                                const float *rp = R1 + j * RS + i;
+#pragma unroll 6
+                                for (int o = 0; o < 18; ++o) {
+                                    const float rv = rp[o * OS];
+                                    h0 = __fadd_rn(h0, __fmul_rn(fminf(__fmul_rn(rv, nv0), 0.2f), .2357f));
+                                    h1 = __fadd_rn(h1, __fmul_rn(fminf(__fmul_rn(rv, nv1), 0.2f), .2357f));
+                                    h2 = __fadd_rn(h2, __fmul_rn(fminf(__fmul_rn(rv, nv2), 0.2f), .2357f));
+                                    h3 = __fadd_rn(h3, __fmul_rn(fminf(__fmul_rn(rv, nv3), 0.2f), .2357f));
+                                }
+                                const float w = __fmul_rn(wyi, wx_s[j]);
+                                // doubled (exact) because the window rows are stored halved
+                                f[q][0] = __fmul_rn(h0 + h0, w); f[q][1] = __fmul_rn(h1 + h1, w); f[q][2] = __fmul_rn(h2 + h2, w); f[q][3] = __fmul_rn(h3 + h3, w);
+                                if (DUMP && p.dump.feat) {
+#pragma unroll
+                                    for (int bq = 0; bq < 4; ++bq) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + (27 + bq) * NB + j * hr + i] = f[q][bq];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int bq = 0; bq < 4; ++bq) {
+                            const int c = 27 + bq;
+                            if (c >= tlo && c < c1) X0[((c - c0) * JP + jp) * HP + i] = make_float2(f[0][bq], f[1][bq]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- transform along the rows (length hr), nch * JP sequences
+            float2 *const Zr = fft_batch<-1>(X0, X1, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_m_r, jc.mg_ns_r, nch * JP, HP, TWR, tid, NT);
+            float2 *const Rb = (Zr == X0) ? X1 : X0;
+            // ---- split the two real columns of each sequence and transpose: Rb[(cc * SK + k) * WP + j], j fastest
+            {
+                const int per = SK * JP;
+                for (int q = tid; q < nch * per; q += NT) {
+                    const int cc = fdiv(q, jc.mg_skjp), rem = q - cc * per, k = fdiv(rem, jc.mg_jp), jp = rem - k * JP;
+                    const float2 *z = Zr + (cc * JP + jp) * HP;
+                    const float2 zk = z[k], zn = z[k == 0 ? 0 : hr - k];
+                    // A = (Z[k] + conj(Z[n-k])) / 2,  B = (Z[k] - conj(Z[n-k])) / (2i)
+                    const float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+                    const float2 B = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+                    float2 *d = Rb + (cc * SK + k) * WP + 2 * jp;
+                    d[0] = A;
+                    if (2 * jp + 1 < wc) d[1] = B;
+                }
+            }
+            __syncthreads();
+            // ---- transform along the columns (length wc), nch * SK sequences
+            float2 *const Xf = fft_batch<-1>(Rb, Zr, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_m_c, jc.mg_ns_c, nch * SK, WP, TWC, tid, NT);
+            // ---- spectral products and the channel sum, in channel order; e = j' * SK + k is the FFTW half-spectrum index (kcf.cpp:180-186)
+            for (int e = tid; e < S; e += NT) {
+                const int jq = fdiv(e, jc.mg_sk), k = e - jq * SK;
+                float2 acc = (c0 == 0) ? make_float2(0.f, 0.f) : ACC[e];
+                const float2 *xp = Xf + k * WP + jq;
+                float2 *mp = model + (long)c0 * S + e;
+#pragma unroll 4
+                for (int cc = 0; cc < nch; ++cc) {
+                    const float2 v = xp[cc * SK * WP];
+                    const float2 mv = need_model ? mp[(long)cc * S] : make_float2(0.f, 0.f);
+                    if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + (c0 + cc) * S + e] = v;
+                    float2 o;
+                    if (MODE == KCF_MODE_PREDICT) {
+                        o = make_float2(v.x * mv.x + v.y * mv.y, v.y * mv.x - v.x * mv.y);                 // xf * conj(model), kcf.cpp:306-345
+                    } else {
+                        o = make_float2(v.x * v.x + v.y * v.y, 0.f);                                         // |xf|^2, kcf.cpp:269-293
+                        // model = (1-f) model + f xf, kcf.cpp:380-395 (f = 1 on the first update: the old model drops out)
+                        mp[(long)cc * S] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, mv.x), __fmul_rn(fac, v.x)),
+                                                                   __fadd_rn(__fmul_rn(omf, mv.y), __fmul_rn(fac, v.y)));
+                    }
+                    if (c0 + cc == 0) acc = o; else { acc.x = __fadd_rn(acc.x, o.x); acc.y = __fadd_rn(acc.y, o.y); }
+                }
+                ACC[e] = acc;
+            }
+            __syncthreads();
+        }
+
+        // ---------------------------------------------------------------- P6 / P7
+        if (MODE == KCF_MODE_UPDATE) {
+            const double2 *ly = at.lab + any_off(wc), *lx = at.lab + any_off(hr);
+            for (int e = tid; e < S; e += NT) {
+                const int jq = fdiv(e, jc.mg_sk), k = e - jq * SK;
+                const float kf = __fmul_rn(ACC[e].x, jc.norm);                                   // kcf.cpp:295-303
+                if (DUMP && p.dump.kf) p.dump.kf[(long)job * p.dump.stride_spec + e] = kf;
+                // Re(yf): the label is an outer product of two 1-D Gaussians, so its 2-D transform is the product of their 1-D ones
+                const double2 gy = ly[jq], gx = lx[k];
+                const float yf = (float)(gy.x * gx.x - gy.y * gx.y);
+                const float an = __fdiv_rn(yf, __fadd_rn(kf, p.lamda));                          // kcf.cpp:373
+                alpha[e] = first ? an : __fadd_rn(__fmul_rn(omf, alpha[e]), __fmul_rn(fac, an)); // kcf.cpp:374
+            }
+            if (tid == 0) {
+                // tracker_update, kcf.cpp:462-476
+                meta->pos = box;
+                meta->scale_horiz = __fdiv_rn((float)(box.r - box.l + 1), (float)cols);
+                meta->scale_vert = __fdiv_rn((float)(box.b - box.t + 1), (float)rows);
+                meta->first_update = 0;
+            }
+            continue;
+        }
+        // predict: zf = (sum) * alpha * norm (kcf.cpp:356-357), stored transposed for the inverse column transform
+        for (int e = tid; e < S; e += NT) {
+            const int jq = fdiv(e, jc.mg_sk), k = e - jq * SK;
+            const float al = alpha[e];
+            float2 acc = ACC[e];
+            acc.x = __fmul_rn(__fmul_rn(acc.x, al), jc.norm);
+            acc.y = __fmul_rn(__fmul_rn(acc.y, al), jc.norm);
+            X0[k * WP + jq] = acc;
+            if (DUMP && p.dump.zf) p.dump.zf[(long)job * p.dump.stride_spec + e] = acc;
+        }
+        __syncthreads();
+        float2 *const Yc = fft_batch<+1>(X0, X1, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_m_c, jc.mg_ns_c, SK, WP, TWC, tid, NT);
+        float2 *const Zb = (Yc == X0) ? X1 : X0;
+        // c2r along the rows (kcf.cpp:397-399): rebuild the Hermitian sequences of two columns, A + iB, and transform them together.
+        // FFTW's c2r takes the DC and (even length) Nyquist bins as real.
+        for (int q = tid; q < JP * hr; q += NT) {
+            const int jp = fdiv(q, jc.mg_hr), i = q - jp * hr;
+            const bool up = 2 * i > hr;
+            const int ks = up ? hr - i : i;
+            const bool realbin = (i == 0) || (2 * i == hr);
+            float2 A = Yc[ks * WP + 2 * jp];
+            float2 B = (2 * jp + 1 < wc) ? Yc[ks * WP + 2 * jp + 1] : make_float2(0.f, 0.f);
+            if (up) { A.y = -A.y; B.y = -B.y; }
+            if (realbin) { A.y = 0.f; B.y = 0.f; }
+            Zb[jp * HP + i] = make_float2(A.x - B.y, A.y + B.x);
+        }
+        __syncthreads();
+        float2 *const Rz = fft_batch<+1>(Zb, Yc, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_m_r, jc.mg_ns_r, JP, HP, TWR, tid, NT);
+        // response[j][i] = Re / Im of Rz[(j >> 1)][i]; first maximum in memory order (j outer, i inner), strict '>' from -99999 (kcf.cpp:402-417)
+        float best = -99999.0f; int besti = 0x7FFFFFFF;
+        for (int idx = tid; idx < NB; idx += NT) {
+            const int j = fdiv(idx, jc.mg_hr), i = idx - j * hr;
+            const float2 zz = Rz[(j >> 1) * HP + i];
+            const float v = (j & 1) ? zz.y : zz.x;
+            if (DUMP && p.dump.resp) p.dump.resp[(long)job * p.dump.stride_cell + idx] = v;
+            if (v > best) { best = v; besti = idx; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_down_sync(0xFFFFFFFFu, best, off);
+            const int oi = __shfl_down_sync(0xFFFFFFFFu, besti, off);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        int *const redi = reinterpret_cast<int *>(red) + 32;
+        if (lane == 0) { red[warp] = best; redi[warp] = besti; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < nwarps; ++w) { const float ov = red[w]; const int oi = redi[w]; if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; } }
+            int vd = 1, hd = 1;                                            // the reference leaves these uninitialised when nothing beats -99999
+            if (besti != 0x7FFFFFFF) { hd = besti / hr + 1; vd = besti - (hd - 1) * hr + 1; }
+            if (DUMP && p.dump.peak) { p.dump.peak[2 * job] = vd; p.dump.peak[2 * job + 1] = hd; }
+            if (vd > hr / 2) vd -= hr;                                     // kcf.cpp:419-420
+            if (hd > wc / 2) hd -= wc;
+            mot_bbox_t pos = meta->pos;
+            const float dv = __fmul_rn((float)(KCF_CELL * (vd - 1)), meta->scale_vert);
+            const float dh = __fmul_rn((float)(KCF_CELL * (hd - 1)), meta->scale_horiz);
+            pos.t = __float2int_rz(__fadd_rn((float)pos.t, dv));           // kcf.cpp:423-426 (float math, truncation)
+            pos.b = __float2int_rz(__fadd_rn((float)pos.b, dv));
+            pos.l = __float2int_rz(__fadd_rn((float)pos.l, dh));
+            pos.r = __float2int_rz(__fadd_rn((float)pos.r, dh));
+            meta->pos = pos;
+            if (p.clamp_to_frame) {                                        // top/td.cpp:378-381
+                pos.l = clampi(pos.l, 0, p.frame_w - 1); pos.r = clampi(pos.r, 0, p.frame_w - 1);
+                pos.t = clampi(pos.t, 0, p.frame_h - 1); pos.b = clampi(pos.b, 0, p.frame_h - 1);
+            }
+            p.boxes[bi] = pos;
+        }
+    }
+}
+
+size_t kcf_any_smem_bytes(int hr, int wc, int lut_floats)
+{
+    const AnyGeo g = any_geo(hr, wc, lut_floats);
+    if (!g.ok || g.nb > 2048) return 0;
+    return (size_t)g.total * sizeof(float);
+}
+
+int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, cudaStream_t s)
+{
+    const FhogTablesDev &t = p.tab;
+    int lut_floats = 2 * (2 << t.rsqrt_bits) + ((2 * t.bin_nseg + 3) & ~3);
+    if (lut_floats > 8192) lut_floats = 0;
+    const bool dump = p.dump.gray != nullptr;
+    const void *fn;
+    if (mode == KCF_MODE_PREDICT) fn = dump ? (const void *)kcf_any_kernel<KCF_MODE_PREDICT, true> : (const void *)kcf_any_kernel<KCF_MODE_PREDICT, false>;
+    else                          fn = dump ? (const void *)kcf_any_kernel<KCF_MODE_UPDATE, true> : (const void *)kcf_any_kernel<KCF_MODE_UPDATE, false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int cap = sms * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+    const int grid = p.n_jobs < cap ? p.n_jobs : cap;
+    int smem_floats = (int)(smem_bytes / sizeof(float));
+    int *err = nullptr;
+    void *args[5] = { (void *)&p, (void *)&at, (void *)&lut_floats, (void *)&smem_floats, (void *)&err };
+    e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)threads), args, smem_bytes, s);
+    return (int)e;
+}
+
+}  // namespace mot

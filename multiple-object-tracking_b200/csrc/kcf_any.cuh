@@ -1,0 +1,97 @@
+// kcf_any.cuh -- geometry of the fused any-size KCF kernel (kcf_any.cu), shared with the host layer that sizes its launches.
+#pragma once
+#include "mot_internal.h"
+
+namespace mot {
+
+// Shared-memory plan of one job with an hr x wc cell grid, in floats.  Depends on (hr, wc) only, so that the host can size a
+// launch and the kernel can lay out every job of a mixed-size launch by itself.
+//   A  (M/16 | bin) per pixel in the zero-bordered, y-de-interleaved layout of the gather  ->  spectra of one channel tile (two
+//      ping-pong buffers of the Stockham passes)  ->  zf / response
+//   B  SSE tables + staged frame rows + gray strip (gradient phase)  ->  18-bin cell histograms R1
+//   C  block normalisers, cell energies, channel-sum accumulators, twiddles, Hann vectors, reduction scratch
+struct AnyGeo {
+    int hr, wc, nb, sk, S, h0, w0;
+    int rs;                 // histogram / normaliser column stride (hr + 1)
+    int ps, pc, padm;       // (M | bin) layout: sub-column pitch, column pitch, words
+    int hp, wp, jp;         // spectral pitches (odd, in float2) along rows / columns; column pairs of the two-for-one row pass
+    int per_ch;             // float2 per channel and ping-pong buffer
+    int tc;                 // channels per spectral tile
+    int xw;                 // pixel columns per gradient strip
+    int gs;                 // gray strip column stride (odd)
+    int raw_pitch;          // bytes per staged frame row
+    int lutp;               // floats reserved for the SSE tables
+    int aF, bF;             // region sizes
+    int oB, oN, oE, oACC, oTWR, oTWC, oWY, oWX, oRED, total;   // offsets / total (floats)
+    int ok;                 // fits the budget
+};
+
+constexpr int ANY_SMEM_BUDGET_FLOATS = (227 * 1024 - 2048) / 4;      // dynamic shared memory one CTA may use (static part left out)
+constexpr int ANY_NMAX_DEFAULT = 320;                                 // per-N tables are built for cell-grid sides 2..nmax
+
+__host__ __device__ inline int any_max(int a, int b) { return a > b ? a : b; }
+__host__ __device__ inline int any_min(int a, int b) { return a < b ? a : b; }
+
+__host__ __device__ inline AnyGeo any_geo(int hr, int wc, int lut_floats)
+{
+    AnyGeo g;
+    g.hr = hr; g.wc = wc; g.nb = hr * wc; g.sk = hr / 2 + 1; g.S = wc * g.sk; g.h0 = 4 * hr; g.w0 = 4 * wc;
+    g.rs = hr + 1;
+    g.ps = hr + 1; g.pc = 4 * g.ps + 2; g.padm = (g.w0 + 4) * g.pc;
+    g.hp = hr | 1; g.wp = wc | 1; g.jp = (wc + 1) / 2;
+    g.per_ch = any_max(g.jp * g.hp, g.sk * g.wp);
+    g.gs = (g.h0 + 2) | 1;
+    const int rmax = 4 * hr + 3, cmax = 4 * wc + 3;
+    g.raw_pitch = ((3 * cmax + 30) + 15) & ~15;
+    const int raw_floats = rmax * (g.raw_pitch / 4);
+    g.lutp = (lut_floats + 3) & ~3;
+    g.aF = (any_max(g.padm, 4 * g.per_ch) + 3) & ~3;
+    g.tc = any_min(KCF_CHAN, g.aF / (4 * g.per_ch));
+    const int r1f = 18 * wc * g.rs;
+    // region C, offsets relative to its start
+    int o = 0;
+    const int cN = o;   o += ((wc + 1) * (hr + 1) + 3) & ~3;
+    const int cE = o;   o += (g.nb + 3) & ~3;
+    const int cACC = o; o += (2 * g.S + 3) & ~3;
+    const int cTWR = o; o += (2 * hr + 3) & ~3;
+    const int cTWC = o; o += (2 * wc + 3) & ~3;
+    const int cWY = o;  o += (hr + 3) & ~3;
+    const int cWX = o;  o += (wc + 3) & ~3;
+    const int cRED = o; o += 64;
+    const int cF = o;
+    g.ok = 0; g.xw = 0; g.bF = 0;
+    // gradient strip width: the whole window when it is narrow, else the widest of 64 / 32 / 16 / 8 pixel columns that fits
+    const int cand[4] = { g.w0 <= 64 ? g.w0 : 64, 32, 16, 8 };
+    for (int q = 0; q < 4 && !g.ok; ++q) {
+        const int xw = any_min(cand[q], g.w0);
+        const int bF = (any_max(r1f, g.lutp + raw_floats + (xw + 2) * g.gs) + 3) & ~3;
+        if (g.aF + bF + cF <= ANY_SMEM_BUDGET_FLOATS) { g.xw = xw; g.bF = bF; g.ok = 1; }
+    }
+    if (!g.ok) { g.xw = any_min(8, g.w0); g.bF = (any_max(r1f, g.lutp + raw_floats + (g.xw + 2) * g.gs) + 3) & ~3; }
+    g.oB = g.aF;
+    const int c0 = g.aF + g.bF;
+    g.oN = c0 + cN; g.oE = c0 + cE; g.oACC = c0 + cACC; g.oTWR = c0 + cTWR; g.oTWC = c0 + cTWC; g.oWY = c0 + cWY; g.oWX = c0 + cWX; g.oRED = c0 + cRED;
+    g.total = c0 + cF;
+    if (hr < 2 || wc < 2 || g.S > NB_MAX) g.ok = 0;      // model / alpha live in the slot arena (31 * NB_MAX complex, NB_MAX floats)
+    return g;
+}
+
+// Per-N tables (N = side of a cell grid, 2..nmax), built once per context on the host in the reference's precision:
+//   hann[off(N) + i]  float   0.5 - 0.5 cos(2 pi i / (N - 1))           include/sigpack/window/window.h:34-48, 83-89
+//   tw  [off(N) + t]  float2  exp(-2 pi i t / N)
+//   lab [off(N) + k]  double2 DFT_N of the circularly shifted 1-D Gaussian label   trackers/kcf.cpp:96-122, 78-94
+//   plan[N]           radices of the mixed-radix transform of length N
+// off(N) = N (N - 1) / 2 - 1.  Every (hr, wc) combination is served from them, so a tracker of a never-seen size can be born on
+// the device (the device-resident frame loop) without a host round trip.
+struct AnyPlan { unsigned short nf, r[7]; };
+struct AnyTablesDev {
+    const float *hann; const float2 *tw; const double2 *lab; const AnyPlan *plan; int nmax;
+};
+__host__ __device__ inline int any_off(int N) { return N * (N - 1) / 2 - 1; }
+
+// 0 when the fused any-size kernel cannot hold an hr x wc window (the unfused path kcf_generic.cu serves it then)
+size_t kcf_any_smem_bytes(int hr, int wc, int lut_floats);
+// One launch over jobs of ANY mix of sizes whose plans fit `smem_bytes`; threads = CTA size to use.
+int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, cudaStream_t s);
+
+}  // namespace mot

@@ -103,6 +103,52 @@ static void label_spectrum_re(int hr, int wc, std::vector<float> &yf_re)
         }
 }
 
+// ---- per-N tables of the any-size kernel (kcf_any.cuh): every cell-grid side 2..nmax -------------------------------------------
+static void any_plan(int n, AnyPlan &pl)
+{
+    // radices with a register butterfly first (4, then a single 2, then 3, 5, 7), whatever prime factors remain after them
+    pl = AnyPlan{};
+    int nf = 0;
+    auto push = [&](int r) { if (nf < 7) pl.r[nf++] = (unsigned short)r; };
+    while (n % 4 == 0) { push(4); n /= 4; }
+    if (n % 2 == 0) { push(2); n /= 2; }
+    for (int r : { 3, 5, 7 }) while (n % r == 0) { push(r); n /= r; }
+    for (int r = 11; n > 1; r += 2) while (n % r == 0) { push(r); n /= r; }
+    pl.nf = (unsigned short)nf;
+}
+
+static int build_any_tables(mot_ctx_t *c, int nmax)
+{
+    const long total = any_off(nmax + 1);
+    std::vector<float> hann(total); std::vector<float2> tw(total); std::vector<double2> lab(total); std::vector<AnyPlan> plan(nmax + 1);
+    const double two_pi = 6.283185307179586476925286766559;
+    const float sigma = 0.7289f;                                       // kcf.cpp:205
+    const float sinv = (float)(1.0 / (sigma * sigma));
+    std::vector<float> hn, g; std::vector<double> cs, sn;
+    for (int N = 2; N <= nmax; ++N) {
+        const long o = any_off(N);
+        hann_f(N, hn);
+        cs.resize(N); sn.resize(N);
+        for (int t = 0; t < N; ++t) { cs[t] = std::cos(two_pi * t / N); sn[t] = std::sin(two_pi * t / N); tw[o + t] = make_float2((float)cs[t], (float)-sn[t]); hann[o + t] = hn[t]; }
+        // 1-D label exp(-0.5 x^2 / sigma^2), x = -N/2 + i, circularly shifted so that x = 0 sits at index 0 (kcf.cpp:96-122, 78-94)
+        g.assign(N, 0.f);
+        const int x0 = -N / 2;
+        for (int i = 0; i < N; ++i) { const int x = x0 + i; int ii = (i + x0) % N; if (ii < 0) ii += N; g[ii] = (float)std::exp(-0.5 * x * x * sinv); }
+        for (int k = 0; k < N; ++k) {
+            double sr = 0, si = 0;
+            for (int b = 0; b < N; ++b) { const int tt = (int)((long)k * b % N); sr += g[b] * cs[tt]; si -= g[b] * sn[tt]; }
+            lab[o + k] = make_double2(sr, si);
+        }
+        any_plan(N, plan[N]);
+    }
+    float *d_h; float2 *d_t; double2 *d_l; AnyPlan *d_p;
+    CU(cudaMalloc(&d_h, sizeof(float) * total)); CU(cudaMalloc(&d_t, sizeof(float2) * total)); CU(cudaMalloc(&d_l, sizeof(double2) * total)); CU(cudaMalloc(&d_p, sizeof(AnyPlan) * (nmax + 1)));
+    CU(cudaMemcpy(d_h, hann.data(), sizeof(float) * total, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_t, tw.data(), sizeof(float2) * total, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_l, lab.data(), sizeof(double2) * total, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_p, plan.data(), sizeof(AnyPlan) * (nmax + 1), cudaMemcpyHostToDevice));
+    c->any = AnyTablesDev{ d_h, d_t, d_l, d_p, nmax };
+    return 0;
+}
+
 static int get_class(mot_ctx_t *c, int hr, int wc, int *out)
 {
     for (size_t i = 0; i < c->classes.size(); ++i) if (c->classes[i].hr == hr && c->classes[i].wc == wc) { *out = (int)i; return 0; }
@@ -116,6 +162,7 @@ static int get_class(mot_ctx_t *c, int hr, int wc, int *out)
     CU(cudaMemcpy(sc.d_wx, wx.data(), sizeof(float) * wc, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.d_yf, yf.data(), sizeof(float) * yf.size(), cudaMemcpyHostToDevice));
     sc.fast = kcf_fast_smem_bytes(hr, wc) != 0;
+    sc.any_smem = (!sc.fast && hr <= c->any.nmax && wc <= c->any.nmax) ? kcf_any_smem_bytes(hr, wc, c->lut_floats) : 0;
     {
         // exp(-2 pi i t / n) tables for the any-size DFT path, evaluated in double with exact argument reduction
         const double two_pi = 6.283185307179586476925286766559;
@@ -269,6 +316,10 @@ int mot_ctx_create(mot_ctx_t **out, int device, int frame_w, int frame_h, int ma
         CU(cudaMemcpy(c->d_tab_bin2, ft.bin2_tab.data(), sizeof(uint32_t) * ft.bin2_tab.size(), cudaMemcpyHostToDevice));
         c->tab = FhogTablesDev{ c->d_tab_rsqrt, ft.rsqrt_bits, c->d_tab_rcp, ft.rcp_bits, c->d_tab_bin, ft.bin_shift, ft.bin_nseg,
                                 reinterpret_cast<const float2 *>(c->d_tab_rsrc), ft.rcp_cap, c->d_tab_bin2, ft.u_cap };
+        c->lut_floats = 2 * (2 << ft.rsqrt_bits) + ((2 * ft.bin_nseg + 3) & ~3);
+        if (c->lut_floats > 8192) c->lut_floats = 0;
+        CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+        { const int rc = build_any_tables(c, std::max(32, std::max(frame_w, frame_h) / KCF_CELL)); if (rc) return rc; }
     } else {
         c->kal.cap = max_tracks;
         CU(cudaMalloc(&c->kal.x, sizeof(double) * 6 * max_tracks));
@@ -286,6 +337,7 @@ void mot_ctx_destroy(mot_ctx_t *c)
     for (auto p : c->frame_owned) if (p) cudaFree(p);
     cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
     cudaFree(c->d_tab_rsqrt); cudaFree(c->d_tab_rcp); cudaFree(c->d_tab_rsrc); cudaFree(c->d_tab_bin); cudaFree(c->d_tab_bin2); cudaFree(c->kal.x); cudaFree(c->kal.P);
+    cudaFree((void *)c->any.hann); cudaFree((void *)c->any.tw); cudaFree((void *)c->any.lab); cudaFree((void *)c->any.plan);
     for (auto &sc : c->classes) { cudaFree(sc.d_wy); cudaFree(sc.d_wx); cudaFree(sc.d_yf); cudaFree(sc.d_twh); cudaFree(sc.d_tww); }
     for (auto &m : c->meta_h) { if (m.model_ptr) cudaFree(m.model_ptr); if (m.alpha_ptr) cudaFree(m.alpha_ptr); }
     c->d_scratch.release();
@@ -442,15 +494,15 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
             int cls = 0; const int rc = get_class(c, m.hr, m.wc, &cls); if (rc) return rc;
             m.size_class = cls;
             const long S_ = (long)m.wc * (m.hr / 2 + 1);
-            if (!c->classes[cls].fast) {
-                // sizes without a fused kernel own their model / alpha (they can exceed the fixed slot stride)
+            if (!c->classes[cls].fast && !c->classes[cls].any_smem) {
+                // sizes that no fused kernel holds own their model / alpha (they can exceed the fixed slot stride)
                 CU(cudaMalloc(&m.model_ptr, sizeof(float2) * KCF_CHAN * S_)); CU(cudaMalloc(&m.alpha_ptr, sizeof(float) * S_));
                 CU(cudaMemsetAsync(m.model_ptr, 0, sizeof(float2) * KCF_CHAN * S_, c->stream)); CU(cudaMemsetAsync(m.alpha_ptr, 0, sizeof(float) * S_, c->stream));
             }
             const int slot = c->free_slots.back(); c->free_slots.pop_back();
             c->used[slot] = 1; c->meta_h[slot] = m; c->classes[cls].live++;
             c->h_slots.p[i] = slot; c->h_meta_stage.p[i] = m; handles_out[i] = slot;
-            if (c->classes[cls].fast) { max_model = std::max(max_model, KCF_CHAN * S_); max_alpha = std::max(max_alpha, S_); }
+            if (c->classes[cls].fast || c->classes[cls].any_smem) { max_model = std::max(max_model, KCF_CHAN * S_); max_alpha = std::max(max_alpha, S_); }
         }
         CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_meta_stage.p, c->h_meta_stage.p, sizeof(KcfMeta) * n, cudaMemcpyHostToDevice, c->stream));
@@ -514,6 +566,17 @@ static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, c
     if (c->dumps) L.dump = c->dump;
 }
 
+// CTA size and CTAs per SM of an any-size launch with `smem` bytes of shared memory per CTA over windows of nb cells
+static void any_launch_shape(size_t smem, int nb, int *threads, int *ctas)
+{
+    int k = (int)((227 * 1024) / (smem + 1024));                      // per-CTA reservation included
+    k = std::max(1, std::min(k, 4));
+    int t = std::min(1024, (2048 / k) & ~31);
+    // no more threads than the widest phase can use (16 pixels per cell in the gradient phase: always plenty), but at least 256
+    t = std::max(256, std::min(t, ((16 * nb + 31) & ~31)));
+    *threads = t; *ctas = k;
+}
+
 static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
 {
     if (kcf_fast_smem_bytes(hr, wc) != 0) {
@@ -522,7 +585,18 @@ static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
         c->launches += 1;
         return 0;
     }
-    // any other size: unfused pipeline with per-job scratch, processed in chunks of at most ~1 GB of scratch
+    {
+        // any other size that one CTA can hold: the fused any-size kernel; as many CTAs per SM as its shared memory allows
+        const size_t smem = kcf_any_smem_bytes(hr, wc, c->lut_floats);
+        if (smem && hr <= c->any.nmax && wc <= c->any.nmax) {
+            int threads, ctas; any_launch_shape(smem, hr * wc, &threads, &ctas);
+            const int rc = kcf_launch_any(mode, L, c->any, smem, threads, ctas, c->stream);
+            if (rc) return fail(MOT_ERR_CUDA, "KCF (any-size kernel) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            c->launches += 1;
+            return 0;
+        }
+    }
+    // whatever is left (windows too large for one CTA): unfused pipeline with per-job scratch, processed in chunks of at most ~1 GB of scratch
     const size_t per_job = kcf_generic_scratch_bytes(hr, wc);
     size_t jobs = std::min<size_t>((size_t)L.n_jobs, std::max<size_t>(1, ((size_t)1 << 30) / per_job));
     CU(c->d_scratch.ensure(jobs * per_job));

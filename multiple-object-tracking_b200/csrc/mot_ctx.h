@@ -3,6 +3,7 @@
 #include "mot_internal.h"
 #include "kalman.h"
 #include "assoc.h"
+#include "kcf_any.cuh"
 
 #include <algorithm>
 #include <string>
@@ -14,7 +15,9 @@ int mot_fail(int code, const char *fmt, ...);      // records the message for mo
 
 namespace mot {
 
-struct SizeClass { int hr, wc, live; bool fast; float *d_wy, *d_wx, *d_yf; double2 *d_twh, *d_tww; float norm; };
+// fast: a fixed-size fused kernel exists (kcf_fused.cuh); any_smem > 0: the fused any-size kernel (kcf_any.cu) holds the window in
+// that much shared memory; neither: the unfused path (kcf_generic.cu)
+struct SizeClass { int hr, wc, live; bool fast; size_t any_smem; float *d_wy, *d_wx, *d_yf; double2 *d_twh, *d_tww; float norm; };
 
 template <class T> struct DevBuf {
     T *p = nullptr; size_t n = 0;
@@ -74,6 +77,9 @@ struct mot_ctx_s {
     std::vector<SizeClass> classes;
     KcfClassDev *d_classes = nullptr;
     FhogTablesDev tab{};
+    AnyTablesDev any{};                   // per-N tables of the any-size kernel (Hann, twiddles, label spectra, radix plans)
+    int lut_floats = 0;                   // floats of the SSE tables a fused kernel stages in shared memory
+    int sm_count = 0;
     float *d_tab_rsqrt = nullptr, *d_tab_rcp = nullptr, *d_tab_rsrc = nullptr; uint32_t *d_tab_bin = nullptr, *d_tab_bin2 = nullptr;
     KalmanState kal{};
     // staging
