@@ -18,7 +18,9 @@
 //   P7  predict: x alpha x norm -> inverse column transform -> Hermitian rebuild -> inverse row transform -> first-max argmax ->
 //       box shift (float, truncated) -> optional clamp;   update: kf, alpha lerp, tracker_update bookkeeping
 // Transforms are Stockham mixed-radix passes in shared memory (radices 4, 2, 3, 5, 7 in registers; any other prime factor by its
-// definition), driven by a per-length plan, so every length works; the model is read once and written once per update, coalesced.
+// definition), driven by a per-length plan, so every length works.  Spectra are held batch-major (element e of sequence b at
+// [e * pitch + b]): the 32 lanes of a warp run the SAME butterfly on 32 different sequences, so index arithmetic and twiddles are
+// warp-uniform and every shared-memory access is conflict-free.  The model is read once and written once per update, coalesced.
 #include "kcf_any.cuh"
 #include "fhog_common.cuh"
 #include "copy_async.cuh"
@@ -40,7 +42,7 @@ struct AnyJobConst {
     int nst_r, nst_c;                                   // stages of the length-hr / length-wc transforms
     int rad_r[ANY_MAX_STAGES], ns_r[ANY_MAX_STAGES]; uint32_t mg_m_r[ANY_MAX_STAGES], mg_ns_r[ANY_MAX_STAGES];
     int rad_c[ANY_MAX_STAGES], ns_c[ANY_MAX_STAGES]; uint32_t mg_m_c[ANY_MAX_STAGES], mg_ns_c[ANY_MAX_STAGES];
-    uint32_t mg_h0, mg_hr, mg_hr1, mg_sk, mg_jp, mg_jphr, mg_skjp;
+    uint32_t mg_hr, mg_hr1, mg_sk, mg_jp, mg_nych;
     float norm;                                         // feature_norm_ratio, kcf.cpp:197
 };
 
@@ -102,81 +104,89 @@ template <int DIR> struct Bfly<7, DIR> {
     }
 };
 
-// One Stockham pass of radix R over `nbatch` sequences of length n (stride 1, `pitch` float2 apart): one butterfly per thread
-// iteration.  Ns = product of the radices of the passes before this one; tw[t] = exp(-2 pi i t / n).
+// One Stockham pass of radix R over `nbatch` sequences of length n held batch-major (element e of sequence b at [e * pitch + b]).
+// A warp task = (butterfly j, chunk of 32 sequences): j, its twiddles and every address term are warp-uniform, the lanes differ
+// only in b.  Ns = product of the radices of the passes before this one; tw[t] = exp(-2 pi i t / n).
 template <int R, int DIR>
-__device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int Ns, uint32_t mg_m, uint32_t mg_ns,
-                                         int nbatch, int pitch, const float2 *__restrict__ tw, int tid, int NT)
+__device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int Ns, uint32_t mg_ns,
+                                         int nbatch, int pitch, const float2 *__restrict__ tw, int warp, int lane, int nwarps)
 {
-    const int m = n / R, step = m / Ns, total = nbatch * m;
-    for (int t = tid; t < total; t += NT) {
-        const int b = fdiv(t, mg_m), j = t - b * m;
+    const int m = n / R, step = m / Ns;
+    const int nchunk = (nbatch + 31) >> 5, ntask = m * nchunk;
+    const uint32_t mg_chunk = magic_of(nchunk);
+    const int mp = m * pitch, np = Ns * pitch;
+    for (int task = warp; task < ntask; task += nwarps) {
+        const int j = fdiv(task, mg_chunk), b = ((task - j * nchunk) << 5) + lane;
         const int k = j - fdiv(j, mg_ns) * Ns;
-        const float2 *src = in + b * pitch + j;
+        if (b >= nbatch) continue;
+        const float2 *src = in + j * pitch + b;
         float2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = src[r * m];
+        for (int r = 0; r < R; ++r) v[r] = src[r * mp];
         if (Ns > 1) {
             const int ks = k * step;                      // k r step < n for every r < R
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                float2 w = tw[ks * r];
+                float2 w = tw[ks * r];                    // same word for every lane: broadcast
                 if (DIR > 0) w.y = -w.y;
                 v[r] = cmul(v[r], w);
             }
         }
         Bfly<R, DIR>::run(v);
-        float2 *dst = out + b * pitch + (j - k) * R + k;
+        float2 *dst = out + ((j - k) * R + k) * pitch + b;
 #pragma unroll
-        for (int r = 0; r < R; ++r) dst[r * Ns] = v[r];
+        for (int r = 0; r < R; ++r) dst[r * np] = v[r];
     }
 }
 
-// The same pass for any other (prime) radix, straight from the definition: one OUTPUT per thread iteration
+// The same pass for any other (prime) radix, straight from the definition: a warp task = (output o, chunk of 32 sequences)
 template <int DIR>
 __device__ __forceinline__ void fft_pass_prime(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int R, int Ns, int nbatch, int pitch,
-                                               const float2 *__restrict__ tw, int tid, int NT)
+                                               const float2 *__restrict__ tw, int warp, int lane, int nwarps)
 {
-    const int m = n / R, step = m / Ns, total = nbatch * n;
-    const uint32_t mg_n = magic_of(n), mg_ns = magic_of(Ns), mg_R = magic_of(R);
-    for (int t = tid; t < total; t += NT) {
-        const int b = fdiv(t, mg_n), o = t - b * n;
+    const int m = n / R, step = m / Ns;
+    const int nchunk = (nbatch + 31) >> 5, ntask = n * nchunk;
+    const uint32_t mg_chunk = magic_of(nchunk), mg_ns = magic_of(Ns), mg_R = magic_of(R);
+    const int mp = m * pitch;
+    for (int task = warp; task < ntask; task += nwarps) {
+        const int o = fdiv(task, mg_chunk), b = ((task - o * nchunk) << 5) + lane;
         const int oq = fdiv(o, mg_ns), k = o - oq * Ns;            // o = (jhi * R + q) * Ns + k
         const int jhi = fdiv(oq, mg_R), q = oq - jhi * R;
         const int j = jhi * Ns + k;
         int inc = k * step + q * m;                                  // phase advance per r, < 2n
         if (inc >= n) inc -= n;
-        const float2 *src = in + b * pitch + j;
+        if (b >= nbatch) continue;
+        const float2 *src = in + j * pitch + b;
         float2 acc = src[0];
         int ph = 0;
         for (int r = 1; r < R; ++r) {
             ph += inc; if (ph >= n) ph -= n;
             float2 w = tw[ph];
             if (DIR > 0) w.y = -w.y;
-            const float2 x = src[r * m];
+            const float2 x = src[r * mp];
             acc.x = fmaf(x.x, w.x, fmaf(-x.y, w.y, acc.x));
             acc.y = fmaf(x.x, w.y, fmaf(x.y, w.x, acc.y));
         }
-        out[b * pitch + o] = acc;
+        out[o * pitch + b] = acc;
     }
 }
 
 // All passes of a batch of transforms; ping-pongs between buf0 (input) and buf1; returns the buffer holding the result.
 // Ends with a barrier after every pass (the next pass, or the caller, reads what other threads wrote).
 template <int DIR>
-__device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, int nst, const int *rad, const int *ns, const uint32_t *mg_m, const uint32_t *mg_ns,
-                                             int nbatch, int pitch, const float2 *tw, int tid, int NT)
+__device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, int nst, const int *rad, const int *ns, const uint32_t *mg_ns,
+                                             int nbatch, int pitch, const float2 *tw, int warp, int lane, int nwarps)
 {
     float2 *in = buf0, *out = buf1;
     for (int s = 0; s < nst; ++s) {
         const int R = rad[s], Ns = ns[s];
         switch (R) {
-        case 4: fft_pass<4, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
-        case 2: fft_pass<2, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
-        case 3: fft_pass<3, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
-        case 5: fft_pass<5, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
-        case 7: fft_pass<7, DIR>(in, out, n, Ns, mg_m[s], mg_ns[s], nbatch, pitch, tw, tid, NT); break;
-        default: fft_pass_prime<DIR>(in, out, n, R, Ns, nbatch, pitch, tw, tid, NT); break;
+        case 4: fft_pass<4, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 2: fft_pass<2, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 3: fft_pass<3, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 5: fft_pass<5, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 7: fft_pass<7, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
+        default: fft_pass_prime<DIR>(in, out, n, R, Ns, nbatch, pitch, tw, warp, lane, nwarps); break;
         }
         __syncthreads();
         float2 *q = in; in = out; out = q;
@@ -188,7 +198,7 @@ __device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, 
 template <int CPT>
 __device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, const uint32_t *__restrict__ MB, float *__restrict__ R1, float *__restrict__ Es, int tid, int NT)
 {
-    const int OS = g.wc * g.rs, PC = g.pc, PS = g.ps;
+    const int OS = g.os, PC = g.pc, PS = g.ps;
     int ccx[CPT], ccy[CPT]; bool live[CPT]; float *h[CPT]; const uint32_t *mb0[CPT];
 #pragma unroll
     for (int u = 0; u < CPT; ++u) {
@@ -274,9 +284,8 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
                 if (lane == 0) {
                     jc.g = any_geo(hr, wc, lut_floats);
                     jc.norm = (float)(1.0 / (double)((float)(wc * hr * KCF_CHAN)));
-                    jc.mg_h0 = magic_of(4 * hr); jc.mg_hr = magic_of(hr); jc.mg_hr1 = magic_of(hr - 1); jc.mg_sk = magic_of(hr / 2 + 1);
-                    const int jp = (wc + 1) / 2;
-                    jc.mg_jp = magic_of(jp); jc.mg_jphr = magic_of(jp * hr); jc.mg_skjp = magic_of((hr / 2 + 1) * jp);
+                    jc.mg_hr = magic_of(hr); jc.mg_hr1 = magic_of(hr - 1); jc.mg_sk = magic_of(hr / 2 + 1);
+                    jc.mg_jp = magic_of((wc + 1) / 2); jc.mg_nych = magic_of((4 * hr + 31) >> 5);
                 }
                 if (lane == 1 || lane == 2) {
                     const int n = lane == 1 ? hr : wc;
@@ -285,6 +294,7 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
                     uint32_t *mgm = lane == 1 ? jc.mg_m_r : jc.mg_m_c, *mgn = lane == 1 ? jc.mg_ns_r : jc.mg_ns_c;
                     int acc = 1;
                     for (int s = 0; s < (int)pl.nf; ++s) { rad[s] = pl.r[s]; ns[s] = acc; mgm[s] = magic_of(n / pl.r[s]); mgn[s] = magic_of(acc); acc *= pl.r[s]; }
+                    (void)mgm;
                     if (lane == 1) jc.nst_r = pl.nf; else jc.nst_c = pl.nf;
                 }
                 __syncwarp();
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
             if (tid == 0 && err_flag) atomicExch(err_flag, 1);
             continue;
         }
-        const int H0 = g.h0, W0 = g.w0, SK = g.sk, S = g.S, JP = g.jp, HP = g.hp, WP = g.wp, NB = g.nb;
+        const int H0 = g.h0, W0 = g.w0, SK = g.sk, S = g.S, JP = g.jp, NB = g.nb;
         uint32_t *const MB = reinterpret_cast<uint32_t *>(smem);
         float *const Bf = smem + g.oB;
         float *const R1 = Bf;
@@ -395,10 +405,12 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
                     for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = gray_at(clampi(xs - 1 + lx, 0, cols - 1), y);
                 }
                 __syncthreads();
-                // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin)
-                const int npx = (xe - xs) * H0;
-                for (int k = tid; k < npx; k += NT) {
-                    const int lx = fdiv(k, jc.mg_h0), y = k - lx * H0, x = xs + lx;
+                // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin).
+                // Warp task = (pixel column, chunk of 32 rows): x and its border factor are warp-uniform, the lanes run along y
+                const int nych = (H0 + 31) >> 5, ntask = (xe - xs) * nych;
+                for (int task = warp; task < ntask; task += nwarps) {
+                    const int lx = fdiv(task, jc.mg_nych), y = ((task - lx * nych) << 5) + lane, x = xs + lx;
+                    if (y >= H0) continue;
                     const float *gp = GSB + (lx + 1) * GS + y + 1;
                     const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f, ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
                     const float gx = __fmul_rn(__fsub_rn(gp[GS], gp[-GS]), rx);
@@ -419,10 +431,10 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
         else if (NB <= 2 * NT) gather_cells<2>(g, jc.mg_hr, MB, R1, Es, tid, NT);
         else { if (tid == 0 && err_flag) atomicExch(err_flag, 2); }
         __syncthreads();
-        const int OS = wc * g.rs, RS = g.rs;
+        const int OS = g.os, RS = g.rs;
         if (DUMP && p.dump.r1) {
             float *d = p.dump.r1 + (long)job * p.dump.stride_cell * 18;
-            for (int i = tid; i < 18 * NB; i += NT) { const int o = i / NB, c2 = i - o * NB, x = c2 / hr, y = c2 - x * hr; d[i] = R1[o * OS + x * RS + y]; }
+            for (int i = tid; i < 18 * NB; i += NT) { const int o = i / NB, c2 = i - o * NB; d[i] = R1[o * OS + c2]; }
         }
 
         // ---------------------------------------------------------------- P3: 2x2 block normalisers (hogNormMatrix, gradientMex.cpp:236-253)
@@ -454,121 +466,117 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
         const float omf = __fsub_rn(1.0f, fac);
         const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
         float2 *const X0 = reinterpret_cast<float2 *>(smem);
-        float2 *const X1 = X0 + g.tc * g.per_ch;
+        float2 *const X1 = X0 + g.xbuf;
         for (int c0 = 0; c0 < KCF_CHAN; c0 += g.tc) {
             const int c1 = min(KCF_CHAN, c0 + g.tc), nch = c1 - c0;
-            // ---- features of two adjacent cell columns (2jp, 2jp+1) as the real / imaginary part of one sequence along the rows
-            {
+            const int nbr = nch * JP, BPr = nbr | 1;                      // row pass: sequences (channel, column pair), batch pitch
+            const int nbc = nch * SK, BPc = nbc | 1;                      // column pass: sequences (channel, bin k)
+            // ---- features: two adjacent cell columns (2jp, 2jp+1) as the real / imaginary part of one sequence along the rows.
+            // One thread per (column pair, row) loops over the channels of the tile: the six block normalisers around its two
+            // cells and the window weights stay in registers.
+            for (int item = tid; item < JP * hr; item += NT) {
+                const int jp = fdiv(item, jc.mg_hr), i = item - jp * hr, j0 = 2 * jp;
+                const bool two = j0 + 1 < wc;
+                const float *const np0 = Ns + j0 * (hr + 1) + i;
+                // GETT(0), GETT(1), GETT(hb1), GETT(hb1 + 1) of cell (j, i): N[j+1][i+1], N[j+1][i], N[j][i+1], N[j][i]
+                const float a00 = np0[0], a01 = np0[1], a10 = np0[hr + 1], a11 = np0[hr + 2];
+                const float a20 = two ? np0[2 * (hr + 1)] : 0.f, a21 = two ? np0[2 * (hr + 1) + 1] : 0.f;
+                const float wyi = wy_s[i];
+                const float w0 = __fmul_rn(wyi, wx_s[j0]), w1 = two ? __fmul_rn(wyi, wx_s[j0 + 1]) : 0.f;
+                const float *const r0 = R1 + j0 * RS + i, *const r1p = r0 + (two ? RS : 0);
+                float2 *const dst = X0 + i * BPr + jp;
                 const int n1 = max(0, min(c1, 27) - c0);                  // type-1 channels of this tile (gradientMex.cpp:266-270)
-                const int per = JP * hr;
-                for (int k = tid; k < n1 * per; k += NT) {
-                    const int cc = fdiv(k, jc.mg_jphr), rem = k - cc * per, jp = fdiv(rem, jc.mg_hr), i = rem - jp * hr;
+                for (int cc = 0; cc < n1; ++cc) {
                     const int c = c0 + cc;
-                    const float wyi = wy_s[i];
-                    float f[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int j = 2 * jp + q;
-                        f[q] = 0.f;
-                        if (j < wc) {
-                            const float *const n0 = Ns + j * (hr + 1) + i, *const n1p = n0 + (hr + 1);
-                            const float *const ra = R1 + (c < 18 ? c : c - 18) * OS + j * RS + i;
-                            const float rv = (c < 18) ? ra[0] : __fadd_rn(ra[0], ra[9 * OS]);       // R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309)
-                            float hsum = __fadd_rn(fminf(__fmul_rn(rv, n1p[1]), 0.2f), fminf(__fmul_rn(rv, n1p[0]), 0.2f));
-                            hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[1]), 0.2f));
-                            hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[0]), 0.2f));
-                            f[q] = __fmul_rn(hsum, __fmul_rn(wyi, wx_s[j]));                       // (hsum * 0.5) * (wy * wx), kcf.cpp:251-258
-                            if (DUMP && p.dump.feat) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j * hr + i] = f[q];
-                        }
+                    const int ro = (c < 18 ? c : c - 18) * OS;
+                    float rv0 = r0[ro], rv1 = r1p[ro];
+                    if (c >= 18) { rv0 = __fadd_rn(rv0, r0[ro + 9 * OS]); rv1 = __fadd_rn(rv1, r1p[ro + 9 * OS]); }   // R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309)
+                    float h0 = __fadd_rn(fminf(__fmul_rn(rv0, a11), 0.2f), fminf(__fmul_rn(rv0, a10), 0.2f));
+                    h0 = __fadd_rn(h0, fminf(__fmul_rn(rv0, a01), 0.2f));
+                    h0 = __fadd_rn(h0, fminf(__fmul_rn(rv0, a00), 0.2f));
+                    float h1 = __fadd_rn(fminf(__fmul_rn(rv1, a21), 0.2f), fminf(__fmul_rn(rv1, a20), 0.2f));
+                    h1 = __fadd_rn(h1, fminf(__fmul_rn(rv1, a11), 0.2f));
+                    h1 = __fadd_rn(h1, fminf(__fmul_rn(rv1, a10), 0.2f));
+                    const float f0 = __fmul_rn(h0, w0), f1 = two ? __fmul_rn(h1, w1) : 0.f;       // (hsum * 0.5) * (wy * wx), kcf.cpp:251-258
+                    dst[cc * JP] = make_float2(f0, f1);
+                    if (DUMP && p.dump.feat) {
+                        float *d = p.dump.feat + (long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j0 * hr + i;
+                        d[0] = f0; if (two) d[hr] = f1;
                     }
-                    X0[(cc * JP + jp) * HP + i] = make_float2(f[0], f[1]);
                 }
                 if (c1 > 27) {
                     // texture channels 27..30 (hogChannels type 2, gradientMex.cpp:271-275): the 18 orientation loads of a cell are
-                    // shared by its four block normalisers
-                    const int tlo = max(c0, 27);
-                    for (int k = tid; k < per; k += NT) {
-                        const int jp = fdiv(k, jc.mg_hr), i = k - jp * hr;
-                        const float wyi = wy_s[i];
-                        float f[2][4];
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int j = 2 * jp + q;
-#pragma unroll
-                            for (int bq = 0; bq < 4; ++bq) f[q][bq] = 0.f;
-                            if (j < wc) {
-                                const float *const n0 = Ns + j * (hr + 1) + i, *const n1p = n0 + (hr + 1);
-                                const float nv0 = n1p[1], nv1 = n1p[0], nv2 = n0[1], nv3 = n0[0];
-                                float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
-                                const float *rp = R1 + j * RS + i;
+                    // shared by its four block normalisers; the results are doubled (exact) because the window rows are stored halved
+                    float t0[4] = { 0.f, 0.f, 0.f, 0.f }, t1[4] = { 0.f, 0.f, 0.f, 0.f };
 #pragma unroll 6
-                                for (int o = 0; o < 18; ++o) {
-                                    const float rv = rp[o * OS];
-                                    h0 = __fadd_rn(h0, __fmul_rn(fminf(__fmul_rn(rv, nv0), 0.2f), .2357f));
-                                    h1 = __fadd_rn(h1, __fmul_rn(fminf(__fmul_rn(rv, nv1), 0.2f), .2357f));
-                                    h2 = __fadd_rn(h2, __fmul_rn(fminf(__fmul_rn(rv, nv2), 0.2f), .2357f));
-                                    h3 = __fadd_rn(h3, __fmul_rn(fminf(__fmul_rn(rv, nv3), 0.2f), .2357f));
-                                }
-                                const float w = __fmul_rn(wyi, wx_s[j]);
-                                // doubled (exact) because the window rows are stored halved
-                                f[q][0] = __fmul_rn(h0 + h0, w); f[q][1] = __fmul_rn(h1 + h1, w); f[q][2] = __fmul_rn(h2 + h2, w); f[q][3] = __fmul_rn(h3 + h3, w);
-                                if (DUMP && p.dump.feat) {
+                    for (int o = 0; o < 18; ++o) {
+                        const float rv0 = r0[o * OS], rv1 = r1p[o * OS];
+                        t0[0] = __fadd_rn(t0[0], __fmul_rn(fminf(__fmul_rn(rv0, a11), 0.2f), .2357f));
+                        t0[1] = __fadd_rn(t0[1], __fmul_rn(fminf(__fmul_rn(rv0, a10), 0.2f), .2357f));
+                        t0[2] = __fadd_rn(t0[2], __fmul_rn(fminf(__fmul_rn(rv0, a01), 0.2f), .2357f));
+                        t0[3] = __fadd_rn(t0[3], __fmul_rn(fminf(__fmul_rn(rv0, a00), 0.2f), .2357f));
+                        t1[0] = __fadd_rn(t1[0], __fmul_rn(fminf(__fmul_rn(rv1, a21), 0.2f), .2357f));
+                        t1[1] = __fadd_rn(t1[1], __fmul_rn(fminf(__fmul_rn(rv1, a20), 0.2f), .2357f));
+                        t1[2] = __fadd_rn(t1[2], __fmul_rn(fminf(__fmul_rn(rv1, a11), 0.2f), .2357f));
+                        t1[3] = __fadd_rn(t1[3], __fmul_rn(fminf(__fmul_rn(rv1, a10), 0.2f), .2357f));
+                    }
 #pragma unroll
-                                    for (int bq = 0; bq < 4; ++bq) p.dump.feat[(long)job * p.dump.stride_cell * KCF_CHAN + (27 + bq) * NB + j * hr + i] = f[q][bq];
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int bq = 0; bq < 4; ++bq) {
-                            const int c = 27 + bq;
-                            if (c >= tlo && c < c1) X0[((c - c0) * JP + jp) * HP + i] = make_float2(f[0][bq], f[1][bq]);
+                    for (int bq = 0; bq < 4; ++bq) {
+                        const int c = 27 + bq;
+                        const float f0 = __fmul_rn(t0[bq] + t0[bq], w0), f1 = two ? __fmul_rn(t1[bq] + t1[bq], w1) : 0.f;
+                        if (c >= c0 && c < c1) dst[(c - c0) * JP] = make_float2(f0, f1);
+                        if (DUMP && p.dump.feat && c >= c0 && c < c1) {
+                            float *d = p.dump.feat + (long)job * p.dump.stride_cell * KCF_CHAN + c * NB + j0 * hr + i;
+                            d[0] = f0; if (two) d[hr] = f1;
                         }
                     }
                 }
             }
             __syncthreads();
             // ---- transform along the rows (length hr), nch * JP sequences
-            float2 *const Zr = fft_batch<-1>(X0, X1, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_m_r, jc.mg_ns_r, nch * JP, HP, TWR, tid, NT);
+            float2 *const Zr = fft_batch<-1>(X0, X1, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_ns_r, nbr, BPr, TWR, warp, lane, nwarps);
             float2 *const Rb = (Zr == X0) ? X1 : X0;
-            // ---- split the two real columns of each sequence and transpose: Rb[(cc * SK + k) * WP + j], j fastest
-            {
-                const int per = SK * JP;
-                for (int q = tid; q < nch * per; q += NT) {
-                    const int cc = fdiv(q, jc.mg_skjp), rem = q - cc * per, k = fdiv(rem, jc.mg_jp), jp = rem - k * JP;
-                    const float2 *z = Zr + (cc * JP + jp) * HP;
-                    const float2 zk = z[k], zn = z[k == 0 ? 0 : hr - k];
-                    // A = (Z[k] + conj(Z[n-k])) / 2,  B = (Z[k] - conj(Z[n-k])) / (2i)
-                    const float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-                    const float2 B = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
-                    float2 *d = Rb + (cc * SK + k) * WP + 2 * jp;
-                    d[0] = A;
-                    if (2 * jp + 1 < wc) d[1] = B;
-                }
+            // ---- split the two real columns of each sequence, re-batch for the column pass: Rb[j * BPc + cc * SK + k]
+            for (int q = tid; q < nbr * SK; q += NT) {
+                const int bq = fdiv(q, jc.mg_sk), k = q - bq * SK;        // k fastest: conflict-free on both sides (odd pitches)
+                const int cc = fdiv(bq, jc.mg_jp), jp = bq - cc * JP;
+                const float2 zk = Zr[k * BPr + bq], zn = Zr[(k == 0 ? 0 : hr - k) * BPr + bq];
+                // A = (Z[k] + conj(Z[n-k])) / 2,  B = (Z[k] - conj(Z[n-k])) / (2i)
+                float2 *d = Rb + (2 * jp) * BPc + cc * SK + k;
+                d[0] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+                if (2 * jp + 1 < wc) d[BPc] = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
             }
             __syncthreads();
             // ---- transform along the columns (length wc), nch * SK sequences
-            float2 *const Xf = fft_batch<-1>(Rb, Zr, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_m_c, jc.mg_ns_c, nch * SK, WP, TWC, tid, NT);
+            float2 *const Xf = fft_batch<-1>(Rb, Zr, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_ns_c, nbc, BPc, TWC, warp, lane, nwarps);
             // ---- spectral products and the channel sum, in channel order; e = j' * SK + k is the FFTW half-spectrum index (kcf.cpp:180-186)
             for (int e = tid; e < S; e += NT) {
                 const int jq = fdiv(e, jc.mg_sk), k = e - jq * SK;
                 float2 acc = (c0 == 0) ? make_float2(0.f, 0.f) : ACC[e];
-                const float2 *xp = Xf + k * WP + jq;
+                const float2 *xp = Xf + jq * BPc + k;
                 float2 *mp = model + (long)c0 * S + e;
-#pragma unroll 4
-                for (int cc = 0; cc < nch; ++cc) {
-                    const float2 v = xp[cc * SK * WP];
-                    const float2 mv = need_model ? mp[(long)cc * S] : make_float2(0.f, 0.f);
-                    if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + (c0 + cc) * S + e] = v;
-                    float2 o;
-                    if (MODE == KCF_MODE_PREDICT) {
-                        o = make_float2(v.x * mv.x + v.y * mv.y, v.y * mv.x - v.x * mv.y);                 // xf * conj(model), kcf.cpp:306-345
-                    } else {
-                        o = make_float2(v.x * v.x + v.y * v.y, 0.f);                                         // |xf|^2, kcf.cpp:269-293
-                        // model = (1-f) model + f xf, kcf.cpp:380-395 (f = 1 on the first update: the old model drops out)
-                        mp[(long)cc * S] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, mv.x), __fmul_rn(fac, v.x)),
-                                                                   __fadd_rn(__fmul_rn(omf, mv.y), __fmul_rn(fac, v.y)));
+                for (int cb = 0; cb < nch; cb += 8) {
+                    // up to eight model values in flight per thread before the first one is used
+                    float2 mv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) mv[u] = (need_model && cb + u < nch) ? mp[(long)(cb + u) * S] : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int cc = cb + u;
+                        if (cc >= nch) break;
+                        const float2 v = xp[cc * SK];
+                        if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + (c0 + cc) * S + e] = v;
+                        float2 o;
+                        if (MODE == KCF_MODE_PREDICT) {
+                            o = make_float2(v.x * mv[u].x + v.y * mv[u].y, v.y * mv[u].x - v.x * mv[u].y);       // xf * conj(model), kcf.cpp:306-345
+                        } else {
+                            o = make_float2(v.x * v.x + v.y * v.y, 0.f);                                         // |xf|^2, kcf.cpp:269-293
+                            // model = (1-f) model + f xf, kcf.cpp:380-395 (f = 1 on the first update: the old model drops out)
+                            mp[(long)cc * S] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, mv[u].x), __fmul_rn(fac, v.x)),
+                                                                       __fadd_rn(__fmul_rn(omf, mv[u].y), __fmul_rn(fac, v.y)));
+                        }
+                        if (c0 + cc == 0) acc = o; else { acc.x = __fadd_rn(acc.x, o.x); acc.y = __fadd_rn(acc.y, o.y); }
                     }
-                    if (c0 + cc == 0) acc = o; else { acc.x = __fadd_rn(acc.x, o.x); acc.y = __fadd_rn(acc.y, o.y); }
                 }
                 ACC[e] = acc;
             }
@@ -597,18 +605,19 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
             }
             continue;
         }
-        // predict: zf = (sum) * alpha * norm (kcf.cpp:356-357), stored transposed for the inverse column transform
+        // predict: zf = (sum) * alpha * norm (kcf.cpp:356-357), batch-major for the inverse column transform: [j' * BPk + k]
+        const int BPk = SK | 1, BPj = JP | 1;
         for (int e = tid; e < S; e += NT) {
             const int jq = fdiv(e, jc.mg_sk), k = e - jq * SK;
             const float al = alpha[e];
             float2 acc = ACC[e];
             acc.x = __fmul_rn(__fmul_rn(acc.x, al), jc.norm);
             acc.y = __fmul_rn(__fmul_rn(acc.y, al), jc.norm);
-            X0[k * WP + jq] = acc;
+            X0[jq * BPk + k] = acc;
             if (DUMP && p.dump.zf) p.dump.zf[(long)job * p.dump.stride_spec + e] = acc;
         }
         __syncthreads();
-        float2 *const Yc = fft_batch<+1>(X0, X1, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_m_c, jc.mg_ns_c, SK, WP, TWC, tid, NT);
+        float2 *const Yc = fft_batch<+1>(X0, X1, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_ns_c, SK, BPk, TWC, warp, lane, nwarps);
         float2 *const Zb = (Yc == X0) ? X1 : X0;
         // c2r along the rows (kcf.cpp:397-399): rebuild the Hermitian sequences of two columns, A + iB, and transform them together.
         // FFTW's c2r takes the DC and (even length) Nyquist bins as real.
@@ -617,19 +626,19 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
             const bool up = 2 * i > hr;
             const int ks = up ? hr - i : i;
             const bool realbin = (i == 0) || (2 * i == hr);
-            float2 A = Yc[ks * WP + 2 * jp];
-            float2 B = (2 * jp + 1 < wc) ? Yc[ks * WP + 2 * jp + 1] : make_float2(0.f, 0.f);
+            float2 A = Yc[(2 * jp) * BPk + ks];
+            float2 B = (2 * jp + 1 < wc) ? Yc[(2 * jp + 1) * BPk + ks] : make_float2(0.f, 0.f);
             if (up) { A.y = -A.y; B.y = -B.y; }
             if (realbin) { A.y = 0.f; B.y = 0.f; }
-            Zb[jp * HP + i] = make_float2(A.x - B.y, A.y + B.x);
+            Zb[i * BPj + jp] = make_float2(A.x - B.y, A.y + B.x);
         }
         __syncthreads();
-        float2 *const Rz = fft_batch<+1>(Zb, Yc, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_m_r, jc.mg_ns_r, JP, HP, TWR, tid, NT);
-        // response[j][i] = Re / Im of Rz[(j >> 1)][i]; first maximum in memory order (j outer, i inner), strict '>' from -99999 (kcf.cpp:402-417)
+        float2 *const Rz = fft_batch<+1>(Zb, Yc, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_ns_r, JP, BPj, TWR, warp, lane, nwarps);
+        // response[j][i] = Re / Im of Rz[i][j >> 1]; first maximum in memory order (j outer, i inner), strict '>' from -99999 (kcf.cpp:402-417)
         float best = -99999.0f; int besti = 0x7FFFFFFF;
         for (int idx = tid; idx < NB; idx += NT) {
             const int j = fdiv(idx, jc.mg_hr), i = idx - j * hr;
-            const float2 zz = Rz[(j >> 1) * HP + i];
+            const float2 zz = Rz[i * BPj + (j >> 1)];
             const float v = (j & 1) ? zz.y : zz.x;
             if (DUMP && p.dump.resp) p.dump.resp[(long)job * p.dump.stride_cell + idx] = v;
             if (v > best) { best = v; besti = idx; }

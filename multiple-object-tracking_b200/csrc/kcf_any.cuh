@@ -7,16 +7,15 @@ namespace mot {
 // Shared-memory plan of one job with an hr x wc cell grid, in floats.  Depends on (hr, wc) only, so that the host can size a
 // launch and the kernel can lay out every job of a mixed-size launch by itself.
 //   A  (M/16 | bin) per pixel in the zero-bordered, y-de-interleaved layout of the gather  ->  spectra of one channel tile (two
-//      ping-pong buffers of the Stockham passes)  ->  zf / response
+//      ping-pong buffers of the Stockham passes, batch-major)  ->  zf / response
 //   B  SSE tables + staged frame rows + gray strip (gradient phase)  ->  18-bin cell histograms R1
 //   C  block normalisers, cell energies, channel-sum accumulators, twiddles, Hann vectors, reduction scratch
 struct AnyGeo {
     int hr, wc, nb, sk, S, h0, w0;
-    int rs;                 // histogram / normaliser column stride (hr + 1)
+    int rs, os;             // cell-histogram strides: column (hr) and orientation plane (multiple of 32: the gather's updates are conflict-free)
     int ps, pc, padm;       // (M | bin) layout: sub-column pitch, column pitch, words
-    int hp, wp, jp;         // spectral pitches (odd, in float2) along rows / columns; column pairs of the two-for-one row pass
-    int per_ch;             // float2 per channel and ping-pong buffer
-    int tc;                 // channels per spectral tile
+    int jp;                 // column pairs of the two-for-one row pass
+    int tc, xbuf;           // channels per spectral tile; float2 per ping-pong buffer
     int xw;                 // pixel columns per gradient strip
     int gs;                 // gray strip column stride (odd)
     int raw_pitch;          // bytes per staged frame row
@@ -27,27 +26,27 @@ struct AnyGeo {
 };
 
 constexpr int ANY_SMEM_BUDGET_FLOATS = (227 * 1024 - 2048) / 4;      // dynamic shared memory one CTA may use (static part left out)
-constexpr int ANY_NMAX_DEFAULT = 320;                                 // per-N tables are built for cell-grid sides 2..nmax
 
 __host__ __device__ inline int any_max(int a, int b) { return a > b ? a : b; }
 __host__ __device__ inline int any_min(int a, int b) { return a < b ? a : b; }
+
+// Spectra of a tile of `tc` channels are held batch-major: element e of sequence b at [e * pitch + b], pitch odd, so that the 32
+// lanes of a warp run the same butterfly on 32 different sequences (conflict-free, warp-uniform twiddles).  Row pass: hr elements x
+// (tc * jp) sequences; column pass: wc elements x (tc * sk) sequences.
+__host__ __device__ inline int any_xbuf(int hr, int wc, int jp, int sk, int tc) { return any_max(hr * ((tc * jp) | 1), wc * ((tc * sk) | 1)); }
 
 __host__ __device__ inline AnyGeo any_geo(int hr, int wc, int lut_floats)
 {
     AnyGeo g;
     g.hr = hr; g.wc = wc; g.nb = hr * wc; g.sk = hr / 2 + 1; g.S = wc * g.sk; g.h0 = 4 * hr; g.w0 = 4 * wc;
-    g.rs = hr + 1;
-    g.ps = hr + 1; g.pc = 4 * g.ps + 2; g.padm = (g.w0 + 4) * g.pc;
-    g.hp = hr | 1; g.wp = wc | 1; g.jp = (wc + 1) / 2;
-    g.per_ch = any_max(g.jp * g.hp, g.sk * g.wp);
+    g.rs = hr; g.os = (g.nb + 31) & ~31;
+    g.jp = (wc + 1) / 2;
     g.gs = (g.h0 + 2) | 1;
     const int rmax = 4 * hr + 3, cmax = 4 * wc + 3;
     g.raw_pitch = ((3 * cmax + 30) + 15) & ~15;
     const int raw_floats = rmax * (g.raw_pitch / 4);
     g.lutp = (lut_floats + 3) & ~3;
-    g.aF = (any_max(g.padm, 4 * g.per_ch) + 3) & ~3;
-    g.tc = any_min(KCF_CHAN, g.aF / (4 * g.per_ch));
-    const int r1f = 18 * wc * g.rs;
+    const int r1f = 18 * g.os;
     // region C, offsets relative to its start
     int o = 0;
     const int cN = o;   o += ((wc + 1) * (hr + 1) + 3) & ~3;
@@ -59,15 +58,27 @@ __host__ __device__ inline AnyGeo any_geo(int hr, int wc, int lut_floats)
     const int cWX = o;  o += (wc + 3) & ~3;
     const int cRED = o; o += 64;
     const int cF = o;
-    g.ok = 0; g.xw = 0; g.bF = 0;
-    // gradient strip width: the whole window when it is narrow, else the widest of 64 / 32 / 16 / 8 pixel columns that fits
-    const int cand[4] = { g.w0 <= 64 ? g.w0 : 64, 32, 16, 8 };
-    for (int q = 0; q < 4 && !g.ok; ++q) {
-        const int xw = any_min(cand[q], g.w0);
-        const int bF = (any_max(r1f, g.lutp + raw_floats + (xw + 2) * g.gs) + 3) & ~3;
-        if (g.aF + bF + cF <= ANY_SMEM_BUDGET_FLOATS) { g.xw = xw; g.bF = bF; g.ok = 1; }
+    g.ok = 0; g.xw = 0; g.bF = 0; g.aF = 0; g.ps = 0; g.pc = 0; g.padm = 0;
+    // Two choices, most comfortable first: the sub-column pitch of the (M | bin) layout = 8 (mod 16), which makes the gradient phase's
+    // stores conflict-free, or the bare minimum hr + 1; the gradient strip as wide as fits (whole window when narrow, else 64 / 32 / 16 / 8).
+    for (int pad = 1; pad >= 0 && !g.ok; --pad) {
+        const int ps = pad ? (((hr + 1 - 8 + 15) / 16) * 16 + 8) : hr + 1;
+        const int pc = 4 * ps + 2, padm = (g.w0 + 4) * pc;
+        const int aF = (any_max(padm, 4 * any_xbuf(hr, wc, g.jp, g.sk, 1)) + 3) & ~3;
+        const int cand[4] = { g.w0 <= 64 ? g.w0 : 64, 32, 16, 8 };
+        for (int q = 0; q < 4 && !g.ok; ++q) {
+            const int xw = any_min(cand[q], g.w0);
+            const int bF = (any_max(r1f, g.lutp + raw_floats + (xw + 2) * g.gs) + 3) & ~3;
+            g.ps = ps; g.pc = pc; g.padm = padm; g.aF = aF; g.xw = xw; g.bF = bF;      // the last one tried stays when nothing fits
+            g.ok = aF + bF + cF <= ANY_SMEM_BUDGET_FLOATS;
+        }
     }
-    if (!g.ok) { g.xw = any_min(8, g.w0); g.bF = (any_max(r1f, g.lutp + raw_floats + (g.xw + 2) * g.gs) + 3) & ~3; }
+    // channels per tile: as many as two ping-pong buffers in region A hold, then balanced over the resulting number of tiles
+    int tcmax = 1;
+    for (int tc = 2; tc <= KCF_CHAN; ++tc) if (4 * any_xbuf(hr, wc, g.jp, g.sk, tc) <= g.aF) tcmax = tc;
+    const int ntiles = (KCF_CHAN + tcmax - 1) / tcmax;
+    g.tc = (KCF_CHAN + ntiles - 1) / ntiles;
+    g.xbuf = any_xbuf(hr, wc, g.jp, g.sk, g.tc);
     g.oB = g.aF;
     const int c0 = g.aF + g.bF;
     g.oN = c0 + cN; g.oE = c0 + cE; g.oACC = c0 + cACC; g.oTWR = c0 + cTWR; g.oTWC = c0 + cTWC; g.oWY = c0 + cWY; g.oWX = c0 + cWX; g.oRED = c0 + cRED;
