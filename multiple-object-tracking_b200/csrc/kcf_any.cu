@@ -24,6 +24,7 @@
 #include "kcf_any.cuh"
 #include "fhog_common.cuh"
 #include "copy_async.cuh"
+#include <cstdlib>
 
 namespace mot {
 
@@ -40,8 +41,9 @@ struct AnyJobConst {
     int hr, wc;
     AnyGeo g;
     int nst_r, nst_c;                                   // stages of the length-hr / length-wc transforms
-    int rad_r[ANY_MAX_STAGES], ns_r[ANY_MAX_STAGES]; uint32_t mg_m_r[ANY_MAX_STAGES], mg_ns_r[ANY_MAX_STAGES];
-    int rad_c[ANY_MAX_STAGES], ns_c[ANY_MAX_STAGES]; uint32_t mg_m_c[ANY_MAX_STAGES], mg_ns_c[ANY_MAX_STAGES];
+    int rad_r[ANY_MAX_STAGES], ns_r[ANY_MAX_STAGES]; uint32_t mg_ns_r[ANY_MAX_STAGES];
+    int rad_c[ANY_MAX_STAGES], ns_c[ANY_MAX_STAGES]; uint32_t mg_ns_c[ANY_MAX_STAGES];
+    uint32_t mg_small[64];                              // magic_of(d), d < 64 (chunk counts of the passes)
     uint32_t mg_hr, mg_hr1, mg_sk, mg_jp, mg_nych;
     float norm;                                         // feature_norm_ratio, kcf.cpp:197
 };
@@ -108,12 +110,12 @@ template <int DIR> struct Bfly<7, DIR> {
 // A warp task = (butterfly j, chunk of 32 sequences): j, its twiddles and every address term are warp-uniform, the lanes differ
 // only in b.  Ns = product of the radices of the passes before this one; tw[t] = exp(-2 pi i t / n).
 template <int R, int DIR>
-__device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int Ns, uint32_t mg_ns,
+__device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int Ns, uint32_t mg_ns, const uint32_t *mg_small,
                                          int nbatch, int pitch, const float2 *__restrict__ tw, int warp, int lane, int nwarps)
 {
-    const int m = n / R, step = m / Ns;
+    const int m = n / R, step = fdiv(m, mg_ns);
     const int nchunk = (nbatch + 31) >> 5, ntask = m * nchunk;
-    const uint32_t mg_chunk = magic_of(nchunk);
+    const uint32_t mg_chunk = mg_small[nchunk & 63];
     const int mp = m * pitch, np = Ns * pitch;
     for (int task = warp; task < ntask; task += nwarps) {
         const int j = fdiv(task, mg_chunk), b = ((task - j * nchunk) << 5) + lane;
@@ -141,12 +143,13 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ in, float2 *
 
 // The same pass for any other (prime) radix, straight from the definition: a warp task = (output o, chunk of 32 sequences)
 template <int DIR>
-__device__ __forceinline__ void fft_pass_prime(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int R, int Ns, int nbatch, int pitch,
-                                               const float2 *__restrict__ tw, int warp, int lane, int nwarps)
+__device__ __forceinline__ void fft_pass_prime(const float2 *__restrict__ in, float2 *__restrict__ out, int n, int R, int Ns, uint32_t mg_ns, const uint32_t *mg_small,
+                                               int nbatch, int pitch, const float2 *__restrict__ tw, int warp, int lane, int nwarps)
 {
-    const int m = n / R, step = m / Ns;
+    const uint32_t mg_R = magic_of(R);
+    const int m = fdiv(n, mg_R), step = fdiv(m, mg_ns);
     const int nchunk = (nbatch + 31) >> 5, ntask = n * nchunk;
-    const uint32_t mg_chunk = magic_of(nchunk), mg_ns = magic_of(Ns), mg_R = magic_of(R);
+    const uint32_t mg_chunk = mg_small[nchunk & 63];
     const int mp = m * pitch;
     for (int task = warp; task < ntask; task += nwarps) {
         const int o = fdiv(task, mg_chunk), b = ((task - o * nchunk) << 5) + lane;
@@ -174,19 +177,19 @@ __device__ __forceinline__ void fft_pass_prime(const float2 *__restrict__ in, fl
 // All passes of a batch of transforms; ping-pongs between buf0 (input) and buf1; returns the buffer holding the result.
 // Ends with a barrier after every pass (the next pass, or the caller, reads what other threads wrote).
 template <int DIR>
-__device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, int nst, const int *rad, const int *ns, const uint32_t *mg_ns,
+__device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, int nst, const int *rad, const int *ns, const uint32_t *mg_ns, const uint32_t *mg_small,
                                              int nbatch, int pitch, const float2 *tw, int warp, int lane, int nwarps)
 {
     float2 *in = buf0, *out = buf1;
     for (int s = 0; s < nst; ++s) {
         const int R = rad[s], Ns = ns[s];
         switch (R) {
-        case 4: fft_pass<4, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
-        case 2: fft_pass<2, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
-        case 3: fft_pass<3, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
-        case 5: fft_pass<5, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
-        case 7: fft_pass<7, DIR>(in, out, n, Ns, mg_ns[s], nbatch, pitch, tw, warp, lane, nwarps); break;
-        default: fft_pass_prime<DIR>(in, out, n, R, Ns, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 4: fft_pass<4, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 2: fft_pass<2, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 3: fft_pass<3, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 5: fft_pass<5, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 7: fft_pass<7, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        default: fft_pass_prime<DIR>(in, out, n, R, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
         }
         __syncthreads();
         float2 *q = in; in = out; out = q;
@@ -196,13 +199,13 @@ __device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, 
 
 // ordered gather of the 18-bin histograms, CPT cells per thread interleaved (libhog/gradientMex.cpp:183-230, 308-309)
 template <int CPT>
-__device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, const uint32_t *__restrict__ MB, float *__restrict__ R1, float *__restrict__ Es, int tid, int NT)
+__device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, const uint32_t *__restrict__ MB, float *__restrict__ R1, float *__restrict__ Es, int cell0, int NT)
 {
     const int OS = g.os, PC = g.pc, PS = g.ps;
     int ccx[CPT], ccy[CPT]; bool live[CPT]; float *h[CPT]; const uint32_t *mb0[CPT];
 #pragma unroll
     for (int u = 0; u < CPT; ++u) {
-        const int cell = tid + u * NT;
+        const int cell = cell0 + u * NT;
         live[u] = cell < g.nb;
         const int cc = live[u] ? cell : 0;
         ccx[u] = fdiv(cc, mg_hr); ccy[u] = cc - ccx[u] * g.hr;
@@ -250,14 +253,15 @@ __device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, co
 
 }  // namespace
 
-template <int MODE, bool DUMP>
-__global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, const AnyTablesDev at, const int lut_floats, const int smem_floats, int *err_flag)
+template <int MODE, bool DUMP, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, const AnyTablesDev at, const int lut_floats, const int smem_floats, int *err_flag)
 {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t mbar_lut, mbar_raw;
     __shared__ AnyJobConst jc;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     if (tid == 0) { mbar_init(&mbar_lut, 1); mbar_init(&mbar_raw, 1); jc.hr = -1; jc.wc = -1; }
+    if (tid < 64) jc.mg_small[tid] = magic_of(tid);
     __syncthreads();
     const bool lut_smem = lut_floats > 0;
     const int n_rs = 2 * (2 << p.tab.rsqrt_bits), n_bn = (2 * p.tab.bin_nseg + 3) & ~3;
@@ -291,10 +295,9 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
                     const int n = lane == 1 ? hr : wc;
                     const AnyPlan pl = at.plan[n];
                     int *rad = lane == 1 ? jc.rad_r : jc.rad_c, *ns = lane == 1 ? jc.ns_r : jc.ns_c;
-                    uint32_t *mgm = lane == 1 ? jc.mg_m_r : jc.mg_m_c, *mgn = lane == 1 ? jc.mg_ns_r : jc.mg_ns_c;
+                    uint32_t *mgn = lane == 1 ? jc.mg_ns_r : jc.mg_ns_c;
                     int acc = 1;
-                    for (int s = 0; s < (int)pl.nf; ++s) { rad[s] = pl.r[s]; ns[s] = acc; mgm[s] = magic_of(n / pl.r[s]); mgn[s] = magic_of(acc); acc *= pl.r[s]; }
-                    (void)mgm;
+                    for (int s = 0; s < (int)pl.nf; ++s) { rad[s] = pl.r[s]; ns[s] = acc; mgn[s] = magic_of(acc); acc *= pl.r[s]; }
                     if (lane == 1) jc.nst_r = pl.nf; else jc.nst_c = pl.nf;
                 }
                 __syncwarp();
@@ -427,9 +430,14 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
         }
 
         // ---------------------------------------------------------------- P2: cell histograms (ordered gather)
-        if (NB <= NT) gather_cells<1>(g, jc.mg_hr, MB, R1, Es, tid, NT);
-        else if (NB <= 2 * NT) gather_cells<2>(g, jc.mg_hr, MB, R1, Es, tid, NT);
-        else { if (tid == 0 && err_flag) atomicExch(err_flag, 2); }
+        // up to four cells per thread interleaved (independent dependency chains); larger windows go round again
+        for (int cb = 0; cb < NB; cb += 4 * NT) {
+            const int left = NB - cb;
+            if (left <= NT) gather_cells<1>(g, jc.mg_hr, MB, R1, Es, cb + tid, NT);
+            else if (left <= 2 * NT) gather_cells<2>(g, jc.mg_hr, MB, R1, Es, cb + tid, NT);
+            else if (left <= 3 * NT) gather_cells<3>(g, jc.mg_hr, MB, R1, Es, cb + tid, NT);
+            else gather_cells<4>(g, jc.mg_hr, MB, R1, Es, cb + tid, NT);
+        }
         __syncthreads();
         const int OS = g.os, RS = g.rs;
         if (DUMP && p.dump.r1) {
@@ -534,7 +542,7 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
             }
             __syncthreads();
             // ---- transform along the rows (length hr), nch * JP sequences
-            float2 *const Zr = fft_batch<-1>(X0, X1, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_ns_r, nbr, BPr, TWR, warp, lane, nwarps);
+            float2 *const Zr = fft_batch<-1>(X0, X1, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_ns_r, jc.mg_small, nbr, BPr, TWR, warp, lane, nwarps);
             float2 *const Rb = (Zr == X0) ? X1 : X0;
             // ---- split the two real columns of each sequence, re-batch for the column pass: Rb[j * BPc + cc * SK + k]
             for (int q = tid; q < nbr * SK; q += NT) {
@@ -548,7 +556,7 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
             }
             __syncthreads();
             // ---- transform along the columns (length wc), nch * SK sequences
-            float2 *const Xf = fft_batch<-1>(Rb, Zr, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_ns_c, nbc, BPc, TWC, warp, lane, nwarps);
+            float2 *const Xf = fft_batch<-1>(Rb, Zr, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_ns_c, jc.mg_small, nbc, BPc, TWC, warp, lane, nwarps);
             // ---- spectral products and the channel sum, in channel order; e = j' * SK + k is the FFTW half-spectrum index (kcf.cpp:180-186)
             for (int e = tid; e < S; e += NT) {
                 const int jq = fdiv(e, jc.mg_sk), k = e - jq * SK;
@@ -617,7 +625,7 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
             if (DUMP && p.dump.zf) p.dump.zf[(long)job * p.dump.stride_spec + e] = acc;
         }
         __syncthreads();
-        float2 *const Yc = fft_batch<+1>(X0, X1, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_ns_c, SK, BPk, TWC, warp, lane, nwarps);
+        float2 *const Yc = fft_batch<+1>(X0, X1, wc, jc.nst_c, jc.rad_c, jc.ns_c, jc.mg_ns_c, jc.mg_small, SK, BPk, TWC, warp, lane, nwarps);
         float2 *const Zb = (Yc == X0) ? X1 : X0;
         // c2r along the rows (kcf.cpp:397-399): rebuild the Hermitian sequences of two columns, A + iB, and transform them together.
         // FFTW's c2r takes the DC and (even length) Nyquist bins as real.
@@ -633,7 +641,7 @@ __global__ void __launch_bounds__(1024, 1) kcf_any_kernel(const KcfLaunch p, con
             Zb[i * BPj + jp] = make_float2(A.x - B.y, A.y + B.x);
         }
         __syncthreads();
-        float2 *const Rz = fft_batch<+1>(Zb, Yc, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_ns_r, JP, BPj, TWR, warp, lane, nwarps);
+        float2 *const Rz = fft_batch<+1>(Zb, Yc, hr, jc.nst_r, jc.rad_r, jc.ns_r, jc.mg_ns_r, jc.mg_small, JP, BPj, TWR, warp, lane, nwarps);
         // response[j][i] = Re / Im of Rz[i][j >> 1]; first maximum in memory order (j outer, i inner), strict '>' from -99999 (kcf.cpp:402-417)
         float best = -99999.0f; int besti = 0x7FFFFFFF;
         for (int idx = tid; idx < NB; idx += NT) {
@@ -690,8 +698,14 @@ int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t 
     if (lut_floats > 8192) lut_floats = 0;
     const bool dump = p.dump.gray != nullptr;
     const void *fn;
-    if (mode == KCF_MODE_PREDICT) fn = dump ? (const void *)kcf_any_kernel<KCF_MODE_PREDICT, true> : (const void *)kcf_any_kernel<KCF_MODE_PREDICT, false>;
-    else                          fn = dump ? (const void *)kcf_any_kernel<KCF_MODE_UPDATE, true> : (const void *)kcf_any_kernel<KCF_MODE_UPDATE, false>;
+    // two register budgets: 128 registers per thread (at most 512 threads per SM in total) or 64 (1024 threads per SM)
+    bool r128 = threads * (ctas_per_sm < 1 ? 1 : ctas_per_sm) <= 512;
+    if (getenv("MOT_ANY_THREADS")) threads = atoi(getenv("MOT_ANY_THREADS"));
+    if (getenv("MOT_ANY_CTAS")) ctas_per_sm = atoi(getenv("MOT_ANY_CTAS"));
+    if (getenv("MOT_ANY_R128")) r128 = atoi(getenv("MOT_ANY_R128")) != 0;
+    if (r128 && threads > 512) threads = 512;
+    if (mode == KCF_MODE_PREDICT) fn = dump ? (const void *)kcf_any_kernel<KCF_MODE_PREDICT, true, 1024> : r128 ? (const void *)kcf_any_kernel<KCF_MODE_PREDICT, false, 512> : (const void *)kcf_any_kernel<KCF_MODE_PREDICT, false, 1024>;
+    else                          fn = dump ? (const void *)kcf_any_kernel<KCF_MODE_UPDATE, true, 1024> : r128 ? (const void *)kcf_any_kernel<KCF_MODE_UPDATE, false, 512> : (const void *)kcf_any_kernel<KCF_MODE_UPDATE, false, 1024>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 0;

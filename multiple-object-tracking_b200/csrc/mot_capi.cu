@@ -566,15 +566,16 @@ static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, c
     if (c->dumps) L.dump = c->dump;
 }
 
-// CTA size and CTAs per SM of an any-size launch with `smem` bytes of shared memory per CTA over windows of nb cells
-static void any_launch_shape(size_t smem, int nb, int *threads, int *ctas)
+// CTA size and CTAs per SM of an any-size launch with `smem` bytes of shared memory per CTA.  The register file (64 K) allows 1024
+// threads per SM at 64 registers or 512 at 128; the kernel is much shorter with 128 (no spills, nothing rematerialised), and two
+// or more CTAs per SM hide each other's barriers.  Measured on B200 (profiles/ab_any.sh): one CTA per SM -> 512 threads x 128
+// registers; two or three -> 2 x 256 x 128; four or more (small windows) -> 4 x 256 x 64.
+static void any_launch_shape(size_t smem, int *threads, int *ctas)
 {
-    int k = (int)((227 * 1024) / (smem + 1024));                      // per-CTA reservation included
-    k = std::max(1, std::min(k, 4));
-    int t = std::min(1024, (2048 / k) & ~31);
-    // no more threads than the widest phase can use (16 pixels per cell in the gradient phase: always plenty), but at least 256
-    t = std::max(256, std::min(t, ((16 * nb + 31) & ~31)));
-    *threads = t; *ctas = k;
+    const int k = (int)((227 * 1024) / (smem + 1024));                // per-CTA reservation included
+    if (k >= 4) { *threads = 256; *ctas = 4; }
+    else if (k >= 2) { *threads = 256; *ctas = 2; }
+    else { *threads = 512; *ctas = 1; }
 }
 
 static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
@@ -589,7 +590,7 @@ static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
         // any other size that one CTA can hold: the fused any-size kernel; as many CTAs per SM as its shared memory allows
         const size_t smem = kcf_any_smem_bytes(hr, wc, c->lut_floats);
         if (smem && hr <= c->any.nmax && wc <= c->any.nmax) {
-            int threads, ctas; any_launch_shape(smem, hr * wc, &threads, &ctas);
+            int threads, ctas; any_launch_shape(smem, &threads, &ctas);
             const int rc = kcf_launch_any(mode, L, c->any, smem, threads, ctas, c->stream);
             if (rc) return fail(MOT_ERR_CUDA, "KCF (any-size kernel) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
             c->launches += 1;
