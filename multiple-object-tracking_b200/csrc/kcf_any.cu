@@ -106,6 +106,70 @@ template <int DIR> struct Bfly<7, DIR> {
     }
 };
 
+// composite radices (decimation in time over the smaller factor): fewer passes through shared memory
+template <int DIR> struct Bfly<6, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[6])
+    {
+        float2 e[3] = { v[0], v[2], v[4] }, o[3] = { v[1], v[3], v[5] };
+        Bfly<3, DIR>::run(e); Bfly<3, DIR>::run(o);
+        const float sg = DIR < 0 ? -1.f : 1.f;
+        const float2 t1 = cmul(o[1], make_float2(0.5f, sg * 0.8660254038f)), t2 = cmul(o[2], make_float2(-0.5f, sg * 0.8660254038f));
+        v[0] = cadd(e[0], o[0]); v[3] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], t1);   v[4] = csub(e[1], t1);
+        v[2] = cadd(e[2], t2);   v[5] = csub(e[2], t2);
+    }
+};
+template <int DIR> struct Bfly<8, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[8])
+    {
+        float2 e[4] = { v[0], v[2], v[4], v[6] }, o[4] = { v[1], v[3], v[5], v[7] };
+        Bfly<4, DIR>::run(e); Bfly<4, DIR>::run(o);
+        const float h = 0.7071067812f;
+        // w8^1 = h (1 -+ i), w8^2 = -+ i, w8^3 = h (-1 -+ i)   (upper sign: forward)
+        const float2 r1 = rot90<DIR>(o[1]), r3 = rot90<DIR>(o[3]);
+        const float2 t1 = make_float2(h * (o[1].x + r1.x), h * (o[1].y + r1.y));
+        const float2 t2 = rot90<DIR>(o[2]);
+        const float2 t3 = make_float2(h * (r3.x - o[3].x), h * (r3.y - o[3].y));
+        v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], t1);   v[5] = csub(e[1], t1);
+        v[2] = cadd(e[2], t2);   v[6] = csub(e[2], t2);
+        v[3] = cadd(e[3], t3);   v[7] = csub(e[3], t3);
+    }
+};
+template <int DIR> struct Bfly<9, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[9])
+    {
+        float2 a0[3] = { v[0], v[3], v[6] }, a1[3] = { v[1], v[4], v[7] }, a2[3] = { v[2], v[5], v[8] };
+        Bfly<3, DIR>::run(a0); Bfly<3, DIR>::run(a1); Bfly<3, DIR>::run(a2);
+        const float sg = DIR < 0 ? -1.f : 1.f;
+        const float2 w1 = make_float2(0.7660444431f, sg * 0.6427876097f), w2 = make_float2(0.1736481777f, sg * 0.9848077530f),
+                     w4 = make_float2(-0.9396926208f, sg * 0.3420201433f);
+        // X[k1 + 3 k2] = DFT3 over j of w9^(j k1) A_j[k1]
+        float2 b0[3] = { a0[0], a1[0], a2[0] };
+        float2 b1[3] = { a0[1], cmul(a1[1], w1), cmul(a2[1], w2) };
+        float2 b2[3] = { a0[2], cmul(a1[2], w2), cmul(a2[2], w4) };
+        Bfly<3, DIR>::run(b0); Bfly<3, DIR>::run(b1); Bfly<3, DIR>::run(b2);
+        v[0] = b0[0]; v[3] = b0[1]; v[6] = b0[2];
+        v[1] = b1[0]; v[4] = b1[1]; v[7] = b1[2];
+        v[2] = b2[0]; v[5] = b2[1]; v[8] = b2[2];
+    }
+};
+template <int DIR> struct Bfly<10, DIR> {
+    static __device__ __forceinline__ void run(float2 (&v)[10])
+    {
+        float2 e[5] = { v[0], v[2], v[4], v[6], v[8] }, o[5] = { v[1], v[3], v[5], v[7], v[9] };
+        Bfly<5, DIR>::run(e); Bfly<5, DIR>::run(o);
+        const float sg = DIR < 0 ? -1.f : 1.f;
+        const float2 t1 = cmul(o[1], make_float2(0.8090169944f, sg * 0.5877852523f)), t2 = cmul(o[2], make_float2(0.3090169944f, sg * 0.9510565163f));
+        const float2 t3 = cmul(o[3], make_float2(-0.3090169944f, sg * 0.9510565163f)), t4 = cmul(o[4], make_float2(-0.8090169944f, sg * 0.5877852523f));
+        v[0] = cadd(e[0], o[0]); v[5] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], t1);   v[6] = csub(e[1], t1);
+        v[2] = cadd(e[2], t2);   v[7] = csub(e[2], t2);
+        v[3] = cadd(e[3], t3);   v[8] = csub(e[3], t3);
+        v[4] = cadd(e[4], t4);   v[9] = csub(e[4], t4);
+    }
+};
+
 // One Stockham pass of radix R over `nbatch` sequences of length n held batch-major (element e of sequence b at [e * pitch + b]).
 // A warp task = (butterfly j, chunk of 32 sequences): j, its twiddles and every address term are warp-uniform, the lanes differ
 // only in b.  Ns = product of the radices of the passes before this one; tw[t] = exp(-2 pi i t / n).
@@ -189,6 +253,10 @@ __device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, 
         case 3: fft_pass<3, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
         case 5: fft_pass<5, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
         case 7: fft_pass<7, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 8: fft_pass<8, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 6: fft_pass<6, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 10: fft_pass<10, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
+        case 9: fft_pass<9, DIR>(in, out, n, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
         default: fft_pass_prime<DIR>(in, out, n, R, Ns, mg_ns[s], mg_small, nbatch, pitch, tw, warp, lane, nwarps); break;
         }
         __syncthreads();
@@ -399,32 +467,47 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
             };
             if (DUMP && p.dump.gray)                                        // (test hook) the whole rows x cols patch, column-major
                 for (int k = tid; k < rows * cols; k += NT) { const int x = k / rows; p.dump.gray[(long)job * p.dump.stride_px + k] = gray_at(x, k - x * rows); }
+            const bool inside = l >= 0 && l + cols - 1 <= Wm;               // no horizontal clamping needed (the common case)
+            // gradient mapping: a warp keeps one chunk of 32 rows (its y, border factor and the y part of the store address are fixed)
+            // and walks over pixel columns; with fewer warps than chunks it takes several chunks in turn
+            const int nych = (H0 + 31) >> 5;
+            const int ywarps = min(nwarps, nych), ngrp = max(1, fdiv(nwarps, jc.mg_nych));
+            const int wyc = nwarps >= nych ? warp - fdiv(warp, jc.mg_nych) * nych : warp, xg = nwarps >= nych ? fdiv(warp, jc.mg_nych) : 0;
             for (int xs = 0; xs < W0; xs += g.xw) {
                 const int xe = min(xs + g.xw, W0), nx = xe - xs + 2;
                 // gray of template pixels (x, y), x in [xs-1, xe], y in [-1, H0], coordinates clamped into the template: the clamped
                 // apron turns grad1's one-sided border differences (gradientMex.cpp:15-37) into plain differences
                 for (int yy = warp; yy < H0 + 2; yy += nwarps) {
                     const int y = clampi(yy - 1, 0, rows - 1);
-                    for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = gray_at(clampi(xs - 1 + lx, 0, cols - 1), y);
-                }
-                __syncthreads();
-                // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin).
-                // Warp task = (pixel column, chunk of 32 rows): x and its border factor are warp-uniform, the lanes run along y
-                const int nych = (H0 + 31) >> 5, ntask = (xe - xs) * nych;
-                for (int task = warp; task < ntask; task += nwarps) {
-                    const int lx = fdiv(task, jc.mg_nych), y = ((task - lx * nych) << 5) + lane, x = xs + lx;
-                    if (y >= H0) continue;
-                    const float *gp = GSB + (lx + 1) * GS + y + 1;
-                    const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f, ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
-                    const float gx = __fmul_rn(__fsub_rn(gp[GS], gp[-GS]), rx);
-                    const float gy = __fmul_rn(__fsub_rn(gp[1], gp[-1]), ry);
-                    const uint32_t mb = grad_pixel_k(gx, gy, rsrc, bn, lk);
-                    MB[(x + 2) * PC + ((y + 2) & 3) * PS + ((y + 2) >> 2)] = mb;
-                    if (DUMP && p.dump.m0) {
-                        const long idx = (long)job * p.dump.stride_px + x * H0 + y;
-                        p.dump.m0[idx] = __uint_as_float(mb & ~31u); p.dump.bin[idx] = (int)(mb & 31u);
+                    if (staged && inside) {
+                        const unsigned char *rrow = raw + y * g.raw_pitch + l * 3 - a0;
+                        for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = bgr_gray(rrow + clampi(xs - 1 + lx, 0, cols - 1) * 3);
+                    } else {
+                        for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = gray_at(clampi(xs - 1 + lx, 0, cols - 1), y);
                     }
                 }
+                __syncthreads();
+                // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin)
+                if (xg < ngrp)
+                    for (int yc = wyc; yc < nych; yc += ywarps) {
+                        const int y = (yc << 5) + lane;
+                        if (y >= H0) continue;
+                        const float ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
+                        const float *gp = GSB + (xg + 1) * GS + y + 1;
+                        uint32_t *mp = MB + (xs + xg + 2) * PC + ((y + 2) & 3) * PS + ((y + 2) >> 2);
+                        for (int lx = xg; lx < xe - xs; lx += ngrp, gp += ngrp * GS, mp += ngrp * PC) {
+                            const int x = xs + lx;
+                            const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f;
+                            const float gx = __fmul_rn(__fsub_rn(gp[GS], gp[-GS]), rx);
+                            const float gy = __fmul_rn(__fsub_rn(gp[1], gp[-1]), ry);
+                            const uint32_t mb = grad_pixel_k(gx, gy, rsrc, bn, lk);
+                            *mp = mb;
+                            if (DUMP && p.dump.m0) {
+                                const long idx = (long)job * p.dump.stride_px + x * H0 + y;
+                                p.dump.m0[idx] = __uint_as_float(mb & ~31u); p.dump.bin[idx] = (int)(mb & 31u);
+                            }
+                        }
+                    }
                 __syncthreads();
             }
         }

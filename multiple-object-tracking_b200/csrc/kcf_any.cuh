@@ -60,12 +60,12 @@ __host__ __device__ inline AnyGeo any_geo(int hr, int wc, int lut_floats)
     const int cF = o;
     g.ok = 0; g.xw = 0; g.bF = 0; g.aF = 0; g.ps = 0; g.pc = 0; g.padm = 0;
     // Two choices, most comfortable first: the sub-column pitch of the (M | bin) layout = 8 (mod 16), which makes the gradient phase's
-    // stores conflict-free, or the bare minimum hr + 1; the gradient strip as wide as fits (whole window when narrow, else 64 / 32 / 16 / 8).
+    // stores conflict-free, or the bare minimum hr + 1; the gradient strip as wide as fits (whole window when narrow, else 62 / 30 / 14 / 6 pixel columns).
     for (int pad = 1; pad >= 0 && !g.ok; --pad) {
         const int ps = pad ? (((hr + 1 - 8 + 15) / 16) * 16 + 8) : hr + 1;
         const int pc = 4 * ps + 2, padm = (g.w0 + 4) * pc;
         const int aF = (any_max(padm, 4 * any_xbuf(hr, wc, g.jp, g.sk, 1)) + 3) & ~3;
-        const int cand[4] = { g.w0 <= 64 ? g.w0 : 64, 32, 16, 8 };
+        const int cand[4] = { g.w0 <= 64 ? g.w0 : 62, 30, 14, 6 };      // + 2 apron columns = whole warps of the gray conversion
         for (int q = 0; q < 4 && !g.ok; ++q) {
             const int xw = any_min(cand[q], g.w0);
             const int bF = (any_max(r1f, g.lutp + raw_floats + (xw + 2) * g.gs) + 3) & ~3;

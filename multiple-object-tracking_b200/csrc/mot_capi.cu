@@ -106,15 +106,28 @@ static void label_spectrum_re(int hr, int wc, std::vector<float> &yf_re)
 // ---- per-N tables of the any-size kernel (kcf_any.cuh): every cell-grid side 2..nmax -------------------------------------------
 static void any_plan(int n, AnyPlan &pl)
 {
-    // radices with a register butterfly first (4, then a single 2, then 3, 5, 7), whatever prime factors remain after them
+    // fewest passes over the radices that have a register butterfly (2..10); a prime factor above 10 becomes a pass of its own,
+    // evaluated from the definition.  Largest radix first: the first pass needs no twiddles.
+    static const int allowed[] = { 10, 9, 8, 7, 6, 5, 4, 3, 2 };
+    std::vector<int> best(n + 1, 1 << 20), pick(n + 1, 0);
+    best[1] = 0;
+    for (int v = 2; v <= n; ++v) {
+        if (n % v) continue;
+        for (int r : allowed) if (v % r == 0 && best[v / r] + 1 < best[v]) { best[v] = best[v / r] + 1; pick[v] = r; }
+        if (!pick[v] || best[v] >= (1 << 20)) {
+            int pr = 0;
+            for (int q = 11; q <= v; q += 2) if (v % q == 0) { pr = q; break; }
+            if (pr && best[v / pr] + 1 < best[v]) { best[v] = best[v / pr] + 1; pick[v] = pr; }
+        }
+    }
     pl = AnyPlan{};
-    int nf = 0;
-    auto push = [&](int r) { if (nf < 7) pl.r[nf++] = (unsigned short)r; };
-    while (n % 4 == 0) { push(4); n /= 4; }
-    if (n % 2 == 0) { push(2); n /= 2; }
-    for (int r : { 3, 5, 7 }) while (n % r == 0) { push(r); n /= r; }
-    for (int r = 11; n > 1; r += 2) while (n % r == 0) { push(r); n /= r; }
-    pl.nf = (unsigned short)nf;
+    int nf = 0, fac[16];
+    for (int v = n; v > 1 && pick[v] && nf < 16; v /= pick[v]) fac[nf++] = pick[v];
+    std::sort(fac, fac + nf, [](int a, int b) { return a > b; });
+    // a prime radix (> 10) goes last so that the passes before it stay cheap; keep at most 7 passes (n <= 2^14 always fits)
+    std::stable_partition(fac, fac + nf, [](int r) { return r <= 10; });
+    for (int i = 0; i < nf && i < 7; ++i) pl.r[i] = (unsigned short)fac[i];
+    pl.nf = (unsigned short)std::min(nf, 7);
 }
 
 static int build_any_tables(mot_ctx_t *c, int nmax)

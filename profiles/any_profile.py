@@ -34,7 +34,8 @@ def main():
             shdr = r; continue
         if cur is not None and shdr and len(r) == len(shdr):
             cur.append(dict(zip(shdr, r)))
-    insts = parse_disasm(dis, "kcf_any_kernelILi%dELb0E" % mode)
+    ntmax = int(sys.argv[4]) if len(sys.argv) > 4 else 512
+    insts = parse_disasm(dis, "kcf_any_kernelILi%dELb0ELi%dE" % (mode, ntmax))
     sect = next(s for k, s in sects if len(s) == len(insts))
 
     def phase_of(line):
