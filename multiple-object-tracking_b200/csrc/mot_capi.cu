@@ -267,6 +267,31 @@ int mot_ctx_associate_dev(mot_ctx_t *c, int n_mat, const int *d_T, const int *d_
     return 0;
 }
 
+// CTA size and CTAs per SM of an any-size launch with `smem` bytes of shared memory per CTA.  The register file (64 K) allows 1024
+// threads per SM at 64 registers or 512 at 128; the kernel is much shorter with 128 (no spills, nothing rematerialised), and two
+// or more CTAs per SM hide each other's barriers.  Measured on B200 (profiles/ab_any.sh): one CTA per SM -> 512 threads x 128
+// registers; two or three -> 2 x 256 x 128; four or more (small windows) -> 4 x 256 x 64.
+static void any_launch_shape(size_t smem, int *threads, int *ctas)
+{
+    const int k = (int)((227 * 1024) / (smem + 1024));                // per-CTA reservation included
+    if (k >= 4) { *threads = 256; *ctas = 4; }
+    else if (k >= 2) { *threads = 256; *ctas = 2; }
+    else { *threads = 512; *ctas = 1; }
+}
+
+
+int mot_ctx_kcf_launch_any(mot_ctx_t *c, int mode, size_t smem_bytes, int n_max, const int *n_dev, const int *slots, const int *frames,
+                           mot_bbox_t *boxes, const int *box_index, int clamp)
+{
+    KcfLaunch L; fill_launch(c, L, n_max, slots, frames, boxes, clamp);
+    L.n_jobs_dev = n_dev; L.box_index = box_index; L.dump = KcfDump{};
+    int threads, ctas; any_launch_shape(smem_bytes, &threads, &ctas);
+    const int rc = kcf_launch_any(mode, L, c->any, smem_bytes, threads, ctas, c->stream);
+    if (rc) return fail(MOT_ERR_CUDA, "KCF (any-size kernel) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
+}
+
 // =====================================================================================================================
 extern "C" {
 
@@ -577,18 +602,6 @@ static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, c
     L.classes = c->d_classes; L.tab = c->tab; L.clamp_to_frame = clamp;
     L.factor = 0.05f; L.lamda = 0.0001f;                                 // kcf.cpp:211-212
     if (c->dumps) L.dump = c->dump;
-}
-
-// CTA size and CTAs per SM of an any-size launch with `smem` bytes of shared memory per CTA.  The register file (64 K) allows 1024
-// threads per SM at 64 registers or 512 at 128; the kernel is much shorter with 128 (no spills, nothing rematerialised), and two
-// or more CTAs per SM hide each other's barriers.  Measured on B200 (profiles/ab_any.sh): one CTA per SM -> 512 threads x 128
-// registers; two or three -> 2 x 256 x 128; four or more (small windows) -> 4 x 256 x 64.
-static void any_launch_shape(size_t smem, int *threads, int *ctas)
-{
-    const int k = (int)((227 * 1024) / (smem + 1024));                // per-CTA reservation included
-    if (k >= 4) { *threads = 256; *ctas = 4; }
-    else if (k >= 2) { *threads = 256; *ctas = 2; }
-    else { *threads = 512; *ctas = 1; }
 }
 
 static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)

@@ -8,13 +8,17 @@
 // Stream s owns the tracker slots [s*cap, (s+1)*cap).
 //
 // KCF kind: the same loop with the fused KCF kernels in place of the Kalman ones.  The track table does not say which
-// window class a track has in a form the host could read without synchronising, so every frame a small kernel sorts the
-// live tracks into one job list per fused window class (cell grids with sides 8/16/32); the fused kernels take their job
-// count from the device and exit at once when their list is empty.  tracker_new (trackers/kcf.cpp:484-491, :139-213) runs
+// window size a track has in a form the host could read without synchronising, so every frame a small kernel sorts the
+// live tracks into job lists: one per fixed-size fused kernel (cell grids with sides 8/16/32) and three for the fused
+// any-size kernel (kcf_any.cu), by the shared memory a window needs (four, two or one CTA per SM); the kernels take their
+// job count from the device and exit at once when their list is empty.  A tracker of ANY size a CTA can hold is therefore
+// born on the device: its constants come from the per-N tables, nothing is computed on the host.  tracker_new (trackers/kcf.cpp:484-491, :139-213) runs
 // inside the lifecycle kernel (metadata only: model and alpha are fully written by the first update), followed by one
 // more update launch over the tracks spawned in this frame (the reference's first update, top/td.cpp:629-641).  Stream s
-// reads frame slot frame_base + s (mot_tdd_frame_base: alternate two bases to upload frame k+1 under the kernels of frame k).  Detections whose window has no fused kernel cannot spawn here and are counted (mot_tdd_dropped);
-// the host-side loop (host/td_loop.cpp) serves those through the any-size path.
+// reads frame slot frame_base + s (mot_tdd_frame_base: alternate two bases to upload frame k+1 under the kernels of frame k).
+// Only detections no tracker can be built for (smaller than 2x2 cells, larger than the frame, or too large for one CTA's shared
+// memory -- about 1400 cells) are skipped and counted (mot_tdd_dropped); the host-side loop (host/td_loop.cpp) serves the last kind
+// through the unfused path.
 #include "mot_ctx.h"
 
 namespace mot {
@@ -30,11 +34,18 @@ struct TddState {
     int kcf, frame_w, frame_h;
     int frame_base;                              // stream s reads frame slot frame_base + s
     int cls_id[9];                               // context class index of fused class 3*hi + wi (cell sides 8, 16, 32); -1: disabled
+    int any_on[3];                               // any-size job lists (list 9 + b) enabled
+    int lut_floats;                              // what any_geo needs to size a window's shared memory
     KcfMeta *meta;
-    int *jl_slot, *jl_frame, *jl_box, *jl_count; // [9][S*cap] x 3, [9]: live tracks grouped by window class
+    int *jl_slot, *jl_frame, *jl_box, *jl_count; // [TDD_LISTS][S*cap] x 3, [TDD_LISTS]: live tracks grouped by kernel
     int *sp_slot, *sp_frame, *sp_box, *sp_count; // the same for the tracks spawned in this frame
     int *dropped;                                // [S] detections that could not spawn (no fused kernel for their window)
 };
+
+constexpr int TDD_LISTS = 12;                    // 9 fixed-size fused classes + 3 any-size lists
+
+// any-size list of a window that needs `floats` of shared memory: 0 -> four CTAs per SM, 1 -> two, 2 -> one (mot_capi.cu: any_launch_shape)
+__host__ __device__ inline size_t tdd_any_list_bytes(int b) { return b == 0 ? (size_t)(227 * 1024) / 4 - 1024 : b == 1 ? (size_t)(227 * 1024) / 2 - 1024 : (size_t)ANY_SMEM_BUDGET_FLOATS * 4; }
 
 __device__ __forceinline__ int fused_side(int cells) { return cells == 8 ? 0 : cells == 16 ? 1 : cells == 32 ? 2 : -1; }
 __device__ __forceinline__ int fused_class_of(const TddState &st, int rows, int cols)
@@ -43,6 +54,19 @@ __device__ __forceinline__ int fused_class_of(const TddState &st, int rows, int 
     const int hi = fused_side(rows / KCF_CELL), wi = fused_side(cols / KCF_CELL);
     if (hi < 0 || wi < 0) return -1;
     return st.cls_id[3 * hi + wi] >= 0 ? 3 * hi + wi : -1;
+}
+// job list of a window: a fixed-size fused class, else the any-size list its shared-memory plan falls into, else -1 (no tracker)
+__device__ __forceinline__ int kcf_list_of(const TddState &st, int rows, int cols)
+{
+    if (rows > st.frame_h || cols > st.frame_w || rows / KCF_CELL < 2 || cols / KCF_CELL < 2) return -1;
+    const int k = fused_class_of(st, rows, cols);
+    if (k >= 0) return k;
+    if (fused_side(rows / KCF_CELL) >= 0 && fused_side(cols / KCF_CELL) >= 0) return -1;      // a fixed-size class that was switched off
+    const AnyGeo g = any_geo(rows / KCF_CELL, cols / KCF_CELL, st.lut_floats);
+    if (!g.ok) return -1;
+    const size_t bytes = (size_t)g.total * 4;
+    const int b = bytes <= tdd_any_list_bytes(0) ? 0 : bytes <= tdd_any_list_bytes(1) ? 1 : 2;
+    return st.any_on[b] ? 9 + b : -1;
 }
 
 // live tracks -> one job list per window class (order inside a list is irrelevant: jobs are independent)
@@ -54,7 +78,7 @@ __global__ void td_joblist_kernel(TddState st)
         const long e = (long)s * st.cap + i;
         const int slot = st.slot[e];
         const KcfMeta *m = st.meta + slot;
-        const int k = 3 * fused_side(m->hr) + fused_side(m->wc);
+        const int k = m->size_class >= 1000 ? 9 + (m->size_class - 1000) : 3 * fused_side(m->hr) + fused_side(m->wc);
         const int at = atomicAdd(&st.jl_count[k], 1);
         st.jl_slot[k * N + at] = slot; st.jl_frame[k * N + at] = st.frame_base + s; st.jl_box[k * N + at] = (int)e;
     }
@@ -155,7 +179,7 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
         bool cand = st.assigned_detected[(long)s * st.max_det + j] < 0;
         if (cand && st.kcf) {
             const mot_bbox_t b = dets[(long)s * st.max_det + j];
-            if (fused_class_of(st, b.b - b.t + 1, b.r - b.l + 1) < 0) { cand = false; atomicAdd(&st.dropped[s], 1); }
+            if (kcf_list_of(st, b.b - b.t + 1, b.r - b.l + 1) < 0) { cand = false; atomicAdd(&st.dropped[s], 1); }
         }
         pos[j] = cand ? 1 : 0;
     }
@@ -194,8 +218,9 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
             KcfMeta m{};
             m.rows = b.b - b.t + 1; m.cols = b.r - b.l + 1; m.hr = m.rows / KCF_CELL; m.wc = m.cols / KCF_CELL;
             m.pos = b; m.scale_horiz = 1.0f; m.scale_vert = 1.0f; m.first_update = 1;
-            const int k = fused_class_of(st, m.rows, m.cols);
-            m.size_class = st.cls_id[k]; m.model_ptr = nullptr; m.alpha_ptr = nullptr;
+            const int k = kcf_list_of(st, m.rows, m.cols);
+            m.size_class = k < 9 ? st.cls_id[k] : 1000 + (k - 9);        // any-size tracks remember their list, not a class
+            m.model_ptr = nullptr; m.alpha_ptr = nullptr;
             st.meta[sl] = m;
             const long N = (long)st.S * cap;
             const int at = atomicAdd(&st.sp_count[k], 1);
@@ -261,13 +286,15 @@ static int tdd_alloc(mot_tdd_t *t, mot_ctx_t *c, int n_streams, int cap, int max
     CU(cudaMemsetAsync(st.bbox, 0, sizeof(mot_bbox_t) * n, c->stream)); CU(cudaMemsetAsync(st.tid, 0, sizeof(uint32_t) * n, c->stream));
     st.kcf = kcf ? 1 : 0; st.frame_w = c->W; st.frame_h = c->H; st.meta = c->d_meta; st.frame_base = 0;
     for (int k = 0; k < 9; ++k) st.cls_id[k] = -1;
+    for (int b = 0; b < 3; ++b) st.any_on[b] = kcf ? 1 : 0;
+    st.lut_floats = c->lut_floats;
     if (kcf) {
         static const int side[3] = { 8, 16, 32 };
         for (int hi = 0; hi < 3; ++hi)
             for (int wi = 0; wi < 3; ++wi) { const int rc = mot_ctx_kcf_class(c, side[hi], side[wi], &st.cls_id[3 * hi + wi]); if (rc) return rc; }
-        CU(cudaMalloc(&st.jl_slot, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.jl_frame, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.jl_box, sizeof(int) * 9 * n));
-        CU(cudaMalloc(&st.sp_slot, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.sp_frame, sizeof(int) * 9 * n)); CU(cudaMalloc(&st.sp_box, sizeof(int) * 9 * n));
-        CU(cudaMalloc(&st.jl_count, sizeof(int) * 18)); st.sp_count = st.jl_count + 9;
+        CU(cudaMalloc(&st.jl_slot, sizeof(int) * TDD_LISTS * n)); CU(cudaMalloc(&st.jl_frame, sizeof(int) * TDD_LISTS * n)); CU(cudaMalloc(&st.jl_box, sizeof(int) * TDD_LISTS * n));
+        CU(cudaMalloc(&st.sp_slot, sizeof(int) * TDD_LISTS * n)); CU(cudaMalloc(&st.sp_frame, sizeof(int) * TDD_LISTS * n)); CU(cudaMalloc(&st.sp_box, sizeof(int) * TDD_LISTS * n));
+        CU(cudaMalloc(&st.jl_count, sizeof(int) * 2 * TDD_LISTS)); st.sp_count = st.jl_count + TDD_LISTS;
         CU(cudaMalloc(&st.dropped, sizeof(int) * n_streams));
         CU(cudaMemsetAsync(st.dropped, 0, sizeof(int) * n_streams, c->stream));
     }
@@ -308,12 +335,18 @@ static int tdd_step_kcf(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_nde
     mot_ctx_t *c = t->ctx; TddState &st = t->st;
     const int n = st.S * st.cap;
     int rc = mot_ctx_frames_ready(c); if (rc) return rc;
-    CU(cudaMemsetAsync(st.jl_count, 0, sizeof(int) * 18, c->stream));
+    CU(cudaMemsetAsync(st.jl_count, 0, sizeof(int) * 2 * TDD_LISTS, c->stream));
     td_joblist_kernel<<<st.S, 256, 0, c->stream>>>(st);
     auto per_class = [&](int mode, const int *count, const int *slot, const int *frame, const int *box, int clamp) {
         for (int k = 0; k < 9; ++k) {
             if (st.cls_id[k] < 0) continue;
             const int r = mot_ctx_kcf_launch(c, mode, st.cls_id[k], n, count + k, slot + (long)k * n, frame + (long)k * n, st.bbox, box + (long)k * n, clamp);
+            if (r) return r;
+        }
+        for (int b = 0; b < 3; ++b) {
+            if (!st.any_on[b]) continue;
+            const int k = 9 + b;
+            const int r = mot_ctx_kcf_launch_any(c, mode, tdd_any_list_bytes(b), n, count + k, slot + (long)k * n, frame + (long)k * n, st.bbox, box + (long)k * n, clamp);
             if (r) return r;
         }
         return 0;
@@ -406,18 +439,23 @@ int mot_tdd_frame_base(mot_tdd_t *t, int base)
     return 0;
 }
 
-/* KCF kind: restrict the loop to the listed window sizes (pixels); detections of any other size are counted as dropped */
+/* KCF kind: restrict the loop to the listed window sizes (pixels): the kernels of all other job lists are not launched, and
+ * detections of any other kind of size are counted as dropped */
 int mot_tdd_kcf_windows(mot_tdd_t *t, int n, const int *rows, const int *cols)
 {
     if (!t || n < 0 || (n && (!rows || !cols))) return mot_fail(MOT_ERR_ARG, "mot_tdd_kcf_windows: bad argument");
     if (!t->st.kcf) return mot_fail(MOT_ERR_KIND, "not a KCF frame loop");
     static const int side[3] = { 8, 16, 32 };
-    int keep[9] = { 0 };
+    int keep[9] = { 0 }, any_keep[3] = { 0 };
     for (int i = 0; i < n; ++i) {
+        const int hr = rows[i] / KCF_CELL, wc = cols[i] / KCF_CELL;
         int hi = -1, wi = -1;
-        for (int q = 0; q < 3; ++q) { if (rows[i] / KCF_CELL == side[q]) hi = q; if (cols[i] / KCF_CELL == side[q]) wi = q; }
-        if (hi < 0 || wi < 0) return mot_fail(MOT_ERR_SHAPE, "window %dx%d px has no fused kernel (cell sides 8, 16, 32)", rows[i], cols[i]);
-        keep[3 * hi + wi] = 1;
+        for (int q = 0; q < 3; ++q) { if (hr == side[q]) hi = q; if (wc == side[q]) wi = q; }
+        if (hi >= 0 && wi >= 0) { keep[3 * hi + wi] = 1; continue; }
+        const AnyGeo g = (hr >= 2 && wc >= 2) ? any_geo(hr, wc, t->st.lut_floats) : AnyGeo{};
+        if (hr < 2 || wc < 2 || !g.ok) return mot_fail(MOT_ERR_SHAPE, "window %dx%d px: no fused kernel holds it (2x2 cells up to about 1400 cells)", rows[i], cols[i]);
+        const size_t bytes = (size_t)g.total * 4;
+        any_keep[bytes <= tdd_any_list_bytes(0) ? 0 : bytes <= tdd_any_list_bytes(1) ? 1 : 2] = 1;
     }
     for (int hi = 0; hi < 3; ++hi)
         for (int wi = 0; wi < 3; ++wi) {
@@ -425,6 +463,7 @@ int mot_tdd_kcf_windows(mot_tdd_t *t, int n, const int *rows, const int *cols)
             if (!keep[3 * hi + wi]) id = -1;
             else if (id < 0) { const int rc = mot_ctx_kcf_class(t->ctx, side[hi], side[wi], &id); if (rc) return rc; }
         }
+    for (int b = 0; b < 3; ++b) t->st.any_on[b] = any_keep[b];
     return 0;
 }
 

@@ -183,3 +183,48 @@ def test_device_resident_kcf_loop_trace(oracle):
     for r in refs:
         r.close()
     ctx.close()
+
+
+def test_device_resident_kcf_loop_with_detections_of_any_size(oracle):
+    """The device-resident KCF loop with detections of ARBITRARY sizes that change from frame to frame: every tracker is born on the
+    device whatever its window (fixed-size fused classes and the any-size kernel's job lists side by side), its constants come
+    from the per-N tables, and every update whose box differs from the template goes through the reference's scrambled resize.
+    Trace-identical to the oracle's loop; nothing is dropped."""
+    require_gpu()
+    M = mot()
+    W, H, ns, cap = 1280, 720, 2, 32
+    scs = [Scene(77 + 5 * s, W, H, 8, tsize=40, win=64) for s in range(ns)]
+    ctx = M.Context(W, H, max_tracks=ns * cap, n_frame_slots=2 * ns, kind=M.TRACKER_KCF)
+    loop = M.DeviceLoop(ctx, ns, cap=cap, max_det=32, cost_mode=0)
+    refs = [oracle.td_new("kcf", W, H, cap, 0) for _ in range(ns)]
+    rng = np.random.default_rng(8)
+    grow = [rng.integers(-6, 90, size=(8, 2)) for _ in range(ns)]            # windows from 58 to 154 px: fused 64/128 classes, small and large any-size ones
+    for f in range(14):
+        dets, frames = [], []
+        for s, sc in enumerate(scs):
+            sc.step()
+            frames.append(sc.render())
+            d = sc.windows(jitter=1)
+            jig = rng.integers(-2, 3, size=(8, 2))
+            d["r"] = np.clip(d["r"] + grow[s][:, 0] + jig[:, 0], d["l"] + 16, W - 1)
+            d["b"] = np.clip(d["b"] + grow[s][:, 1] + jig[:, 1], d["t"] + 16, H - 1)
+            if f in (4, 5) and s == 0:
+                d = d[:5]                                                       # misses
+            dets.append(np.ascontiguousarray(d))
+        base = (f & 1) * ns
+        for s in range(ns):
+            ctx.upload(base + s, frames[s])
+        loop.frame_base(base)
+        loop.step(dets)
+        for s in range(ns):
+            refs[s].step(frames[s], dets[s])
+            a, b = loop.tracks(s), refs[s].tracks()
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (f, s, k)
+    assert all(loop.dropped(s) == 0 for s in range(ns))
+    sizes = {(int(b["b"] - b["t"] + 1) // 4, int(b["r"] - b["l"] + 1) // 4) for d in dets for b in d}
+    assert len(sizes) >= 6, "the test must really mix window sizes"
+    loop.close()
+    for r in refs:
+        r.close()
+    ctx.close()
