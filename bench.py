@@ -7,8 +7,13 @@ branch, top/td.cpp:550-582), crop + gray + resize included.  Workload = BASELINE
 64 independent 1080p streams x 128 KCF tracks with 128x128-px windows (32x32 cells).  Streams are independent, so
 ranks share nothing: no data-path collective, weak scaling (every GPU gets its own 64 streams).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            the CUDA path (this repo)
+  python bench.py [--gpus N] [--steps K] [--warmup W]            the CUDA path (this repo), BASELINE config 4 (the headline)
   python bench.py --impl reference ...                            the reference's CPU path on the host cores
+  python bench.py --config C1|C2|C3|C5                            the other BASELINE configs (one JSON line each, CPU oracle beside;
+                                                                  single GPU; C4 is the default and the only multi-GPU one)
+The default line also carries `strong` (config 4 as BASELINE words it: 64 streams IN TOTAL sharded over the N GPUs), `full_loop`
+(the device-resident frame loop: the same tracks with association + lifecycle every frame) and, in `e2e`, the all-ranks-concurrent
+H2D rate and the NUMA placement that explain the end-to-end number.
 
 `value`     device-timed (CUDA events on the launching stream), frames + boxes + models resident in HBM
 `e2e`       the same metric through the host-array C ABI: frames copied from pinned host memory every step,
@@ -63,6 +68,37 @@ def make_streams(n_streams, n_tracks, ring, seed0):
             frames[s, r] = sc.render()
             sc.step()
     return frames, boxes
+
+
+def numa_info(gpu_index):
+    """Where the GPU and this process's pinned memory live: the NUMA node of the GPU's PCIe function, the node(s) of the CPUs this
+    process may run on, the number of nodes of the box."""
+    out = {}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(gpu_index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(bus, "pci_domain_id", 0), bus.pci_bus_id, bus.pci_device_id)
+        out["gpu_pci"] = bdf
+        out["gpu_numa_node"] = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+    except Exception as e:
+        out["gpu_numa_node"] = "unknown (%s)" % type(e).__name__
+    try:
+        nodes = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        out["numa_nodes"] = len(nodes)
+        mine = os.sched_getaffinity(0)
+        on = []
+        for d in nodes:
+            cpus = set()
+            for part in open("/sys/devices/system/node/%s/cpulist" % d).read().strip().split(","):
+                if part:
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            if cpus & mine:
+                on.append(int(d[4:]))
+        out["process_cpu_nodes"] = on
+    except Exception as e:
+        out["numa_nodes"] = "unknown (%s)" % type(e).__name__
+    return out
 
 
 class ClockSampler:
@@ -149,6 +185,12 @@ def cpu_reference(n_threads, tracks_per_thread, warmup, steps, want_mkl=True):
             "kind": "reference" if kind == "ref" else "port",
             "sample": "%d threads x %d KCF tracks (128x128 px) x %d frames of one 1080p stream; FFT provider %s; %.1f s" %
                       (n_threads, tracks_per_thread, steps, provider, dt)}, dt
+
+
+def cpu_single_core(frames=12):
+    """The "host-core" figure of the north-star target: one thread, 32 KCF tracks, same loop."""
+    cb, _ = cpu_reference(1, 32, 1, frames)
+    return cb["value"]
 
 
 def run_reference(args):
@@ -251,6 +293,62 @@ def run_b200(args):
     final = d_boxes.cpu().numpy().view(M.BBOX_DTYPE).reshape(n)
     drift = float(np.abs((final["l"] + final["r"]) / 2.0 - (all_boxes["l"] + all_boxes["r"]) / 2.0).max())
 
+    # ---- strong scaling (BASELINE config 4 as worded: 64 streams in total, sharded s mod G): this rank's share of the streams -------
+    strong = None
+    if NS % world == 0:
+        ns_s = NS // world
+        n_s = ns_s * NT
+        with torch.cuda.stream(stream):
+            for k in range(2):
+                fr = d_frames[k % RING].data_ptr()
+                ctx.predict_dev(n_s, d_handles.data_ptr(), fr, d_boxes.data_ptr(), clamp=1); ctx.update_dev(n_s, d_handles.data_ptr(), fr, d_boxes.data_ptr())
+            stream.synchronize(); barrier()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for k in range(args.steps):
+                fr = d_frames[k % RING].data_ptr()
+                ctx.predict_dev(n_s, d_handles.data_ptr(), fr, d_boxes.data_ptr(), clamp=1); ctx.update_dev(n_s, d_handles.data_ptr(), fr, d_boxes.data_ptr())
+            e1.record(stream); stream.synchronize()
+        ms_s = max_over_ranks(e0.elapsed_time(e1), dev)
+        strong = {"value": world * n_s * args.steps / (ms_s * 1e-3), "unit": "track-updates/s", "streams_total": NS, "streams_per_gpu": ns_s,
+                  "tracks_per_gpu": n_s, "ms_per_step": ms_s / args.steps, "scaling": "strong"}
+
+    # ---- the whole frame loop on the device (association + bookkeeping + lifecycle every frame; detections = the tracks' own boxes) ----
+    full_loop = None
+    if not args.no_loop:
+        ctx3 = M.Context(W, H, max_tracks=n, n_frame_slots=NS * RING, kind=M.TRACKER_KCF, device=local)
+        ctx3.set_stream(stream.cuda_stream)
+        for i in range(NS * RING):
+            ctx3.bind_device(i, frames_d[i].data_ptr(), W * 3)
+        loop = M.DeviceLoop(ctx3, NS, cap=NT, max_det=NT, cost_mode=0)
+        loop.kcf_windows([(WIN, WIN)])
+        det_buf = np.zeros((NS, NT), M.BBOX_DTYPE)
+        for s_ in range(NS):
+            det_buf[s_] = boxes0[s_]
+        d_det = torch.from_numpy(det_buf.view(np.uint8).reshape(NS, NT * 24)).to(dev)
+        d_nd = torch.full((NS,), NT, dtype=torch.int32, device=dev)
+        with torch.cuda.stream(stream):
+            # the frame ring is [stream][ring]; the loop reads slot base + s, so bind ring frame r of stream s to slot r * NS + s
+            for s_ in range(NS):
+                for r in range(RING):
+                    ctx3.bind_device(r * NS + s_, frames_d[s_ * RING + r].data_ptr(), W * 3)
+            for k in range(3):
+                loop.frame_base((k % RING) * NS); loop.step_dev(d_det.data_ptr(), d_nd.data_ptr())
+            stream.synchronize(); barrier()
+            l3 = ctx3.launches()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            kl = max(3, min(args.steps, 10))
+            for k in range(kl):
+                loop.frame_base(((k + 1) % RING) * NS); loop.step_dev(d_det.data_ptr(), d_nd.data_ptr())
+            e1.record(stream); stream.synchronize()
+        ms_l = max_over_ranks(e0.elapsed_time(e1), dev)
+        ntr = sum(len(loop.tracks(s_)["tid"]) for s_ in (0, NS - 1))
+        full_loop = {"value": world * n * kl / (ms_l * 1e-3), "unit": "track-updates/s", "ms_per_step": ms_l / kl, "launches_per_step": (ctx3.launches() - l3) / kl,
+                     "what": "mot_tdd_step_dev: job lists, fused predict, 64 x (128x128) cost matrices + Munkres, scatter, fused update, lifecycle",
+                     "tracks_alive_in_first_and_last_stream": ntr}
+        loop.close(); ctx3.close()
+
     # ---- e2e: host arrays through the C ABI, frames from pinned host memory every step ------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -279,7 +377,12 @@ def run_b200(args):
 
         upload(0); upload(1)                 # both slot sets exist (the first upload of a slot allocates it)
         ctx2.sync()
-        t0 = time.perf_counter(); upload(1); ctx2.sync(); h2d_s = time.perf_counter() - t0      # PCIe alone, for context
+        t0 = time.perf_counter(); upload(1); ctx2.sync(); h2d_s = time.perf_counter() - t0      # PCIe alone (this rank; the others may be busy)
+        # every rank uploads at the same moment: what one GPU gets when all of the box's GPUs pull frames from the host at once
+        barrier()
+        t0 = time.perf_counter(); upload(0); upload(1); ctx2.sync(); h2d_all_s = (time.perf_counter() - t0) / 2
+        h2d_all_s = max_over_ranks(h2d_all_s, dev)
+        barrier()
         upload(0)
         for k in range(2):
             e2e_step(k)
@@ -293,7 +396,10 @@ def run_b200(args):
         dt = max_over_ranks(dt, dev)
         e2e = {"value": world * n * ke / dt, "unit": "track-updates/s", "h2d_bytes_per_step": NS * H * W * 3 + 2 * n * (24 + 8),
                "d2h_bytes_per_step": n * 24, "steps": ke, "ms_per_step": 1e3 * dt / ke,
-               "h2d_alone_ms": 1e3 * h2d_s, "h2d_alone_gbs": NS * H * W * 3 / h2d_s / 1e9}
+               "h2d_alone_ms": 1e3 * h2d_s, "h2d_alone_gbs": NS * H * W * 3 / h2d_s / 1e9,
+               "h2d_all_ranks_gbs": NS * H * W * 3 / h2d_all_s / 1e9, "h2d_all_ranks_ms": 1e3 * h2d_all_s,
+               "h2d_bound": "a step cannot be faster than its frame upload: %.2f ms at the all-ranks rate vs %.2f ms measured" % (1e3 * h2d_all_s, 1e3 * dt / ke),
+               "numa": numa_info(local)}
         ctx2.close()
 
     if rank == 0:
@@ -320,18 +426,53 @@ def run_b200(args):
         cb = None
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_reference(os.cpu_count() or 1, 32, 2, 24)
+            cb["single_core"] = {"value": cpu_single_core(), "unit": "track-updates/s", "cores": 1,
+                                 "note": "the host-core figure of the north-star target (>= 100x on one B200)"}
+            cb["times"] = "td.step of the oracle loop (predict + association of 32 tracks + update + lifecycle); the association is ~1 % of it"
         line = {"metric": "KCF track-updates/sec", "value": value, "unit": "track-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "C4: %d independent 1080p streams x %d KCF tracks (128x128 px windows, 32x32 cells) per GPU" % (NS, NT),
                            "streams_per_gpu": NS, "tracks_per_stream": NT, "frame": "1920x1080 BGR u8", "parallelism": "streams sharded, no collective",
                            "l2": "working set per step (%.0f MB of models + frames) exceeds the 126 MB L2" % ((31 * S * 8 + S * 4) * n / 1e6 + NS * H * W * 3 / 1e6),
-                           "max_center_drift_px": drift},
-                "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+                           "max_center_drift_px": drift,
+                           "reference_arm": "--impl reference times td.step of the compiled reference (predict + update per track, plus the association and lifecycle of its 32-track loops: ~1 % extra work on the reference's side)"},
+                "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                "strong": strong, "full_loop": full_loop}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_other_config(args):
+    """BASELINE configs 1, 2, 3, 5 (bench_assoc.py holds the workloads): one JSON line in the bench schema, the CPU oracle timed beside."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import bench_assoc as B
+    B.use_mkl_fft_for_the_cpu_side()
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "config": {"workload": args.config}, "note": "the CPU oracle is timed inside the --config line itself (cpu_baseline)"}))
+        return
+    if args.config == "C1":
+        r = B.config1(args)
+        line = {"metric": "single-target KCF frames/sec (host-array API, one sync per call)", "value": r["gpu_frames_per_s_host_api"], "unit": "frames/s",
+                "cpu_baseline": {"value": r["cpu_frames_per_s_one_core"], "unit": "frames/s", "cores": 1, "kind": "reference", "sample": "the same 300-frame sequence, FFT " + r["cpu_fft"]}}
+    elif args.config == "C2":
+        r = B.config2(args)
+        line = {"metric": "Kalman + Hungarian frames/sec, 64 tracks x 64 detections, one stream (device-resident loop)", "value": r["device_resident_1_stream"]["gpu_stream_frames_per_s"],
+                "unit": "frames/s", "cpu_baseline": {"value": r["ref_centroid"]["cpu_frames_per_s_one_core"], "unit": "frames/s", "cores": 1, "kind": "reference", "sample": "the same 300 frames through the oracle loop"}}
+    elif args.config == "C3":
+        r = B.config3(args)
+        line = {"metric": "multi-target KCF frames/sec, 256 tracks in one 1080p stream, whole frame loop (device-resident)", "value": r["gpu_frames_per_s_device_loop"], "unit": "frames/s",
+                "cpu_baseline": {"value": r["cpu_frames_per_s_one_core"], "unit": "frames/s", "cores": 1, "kind": "reference", "sample": "the same 10 frames through the oracle loop"}}
+    else:
+        r = B.config5(args)
+        line = {"metric": "association problems/sec, %d x (%dx%d) cost matrix + Munkres (REF_CENTROID costs)" % (args.matrices, args.dim, args.dim), "value": r["ref_centroid"]["gpu_matrices_per_s"],
+                "unit": "matrices/s", "cpu_baseline": {"value": 1.0 / r["ref_centroid"]["cpu_s_per_matrix_one_core"], "unit": "matrices/s", "cores": 1, "kind": "reference",
+                                                       "sample": "%d of the matrices through assignmentoptimal, assignments compared bit for bit" % r["ref_centroid"]["checked"]}}
+    line.update({"n_gpus": 1, "higher_is_better": True, "scaling": "none (single GPU config)", "vs_baseline": None, "data": "synthetic", "config": {"workload": r["config"]}, "details": r})
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -344,7 +485,14 @@ def main():
     ap.add_argument("--tracks", type=int, default=128)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-loop", action="store_true")
+    ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--matrices", type=int, default=1024)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--cpu-matrices", type=int, default=2)
     args = ap.parse_args()
+    if args.config != "C4":
+        return run_other_config(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
         }
         const AnyGeo &g = jc.g;
         if (g.total > smem_floats || !g.ok) {                  // cannot happen when the host sized the launch; never run out of bounds
-            if (tid == 0 && err_flag) atomicExch(err_flag, 1);
+            if (tid == 0 && err_flag) *reinterpret_cast<volatile int *>(err_flag) = 1;
             continue;
         }
         const int H0 = g.h0, W0 = g.w0, SK = g.sk, S = g.S, JP = g.jp, NB = g.nb;
@@ -774,7 +774,7 @@ size_t kcf_any_smem_bytes(int hr, int wc, int lut_floats)
     return (size_t)g.total * sizeof(float);
 }
 
-int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, cudaStream_t s)
+int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, int *err_flag, cudaStream_t s)
 {
     const FhogTablesDev &t = p.tab;
     int lut_floats = 2 * (2 << t.rsqrt_bits) + ((2 * t.bin_nseg + 3) & ~3);
@@ -797,7 +797,7 @@ int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t 
     const int cap = sms * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
     const int grid = p.n_jobs < cap ? p.n_jobs : cap;
     int smem_floats = (int)(smem_bytes / sizeof(float));
-    int *err = nullptr;
+    int *err = err_flag;
     void *args[5] = { (void *)&p, (void *)&at, (void *)&lut_floats, (void *)&smem_floats, (void *)&err };
     e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)threads), args, smem_bytes, s);
     return (int)e;

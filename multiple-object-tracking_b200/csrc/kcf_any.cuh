@@ -102,7 +102,8 @@ __host__ __device__ inline int any_off(int N) { return N * (N - 1) / 2 - 1; }
 
 // 0 when the fused any-size kernel cannot hold an hr x wc window (the unfused path kcf_generic.cu serves it then)
 size_t kcf_any_smem_bytes(int hr, int wc, int lut_floats);
-// One launch over jobs of ANY mix of sizes whose plans fit `smem_bytes`; threads = CTA size to use.
-int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, cudaStream_t s);
+// One launch over jobs of ANY mix of sizes whose plans fit `smem_bytes`; threads = CTA size to use.  A job whose plan does not fit
+// (a host-side sizing bug) is skipped and *err_flag (device-visible, may be null) set, never run out of bounds.
+int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, int *err_flag, cudaStream_t s);
 
 }  // namespace mot

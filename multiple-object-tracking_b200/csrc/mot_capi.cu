@@ -286,7 +286,7 @@ int mot_ctx_kcf_launch_any(mot_ctx_t *c, int mode, size_t smem_bytes, int n_max,
     KcfLaunch L; fill_launch(c, L, n_max, slots, frames, boxes, clamp);
     L.n_jobs_dev = n_dev; L.box_index = box_index; L.dump = KcfDump{};
     int threads, ctas; any_launch_shape(smem_bytes, &threads, &ctas);
-    const int rc = kcf_launch_any(mode, L, c->any, smem_bytes, threads, ctas, c->stream);
+    const int rc = kcf_launch_any(mode, L, c->any, smem_bytes, threads, ctas, c->d_any_err, c->stream);
     if (rc) return fail(MOT_ERR_CUDA, "KCF (any-size kernel) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     c->launches += 1;
     return 0;
@@ -358,6 +358,8 @@ int mot_ctx_create(mot_ctx_t **out, int device, int frame_w, int frame_h, int ma
         if (c->lut_floats > 8192) c->lut_floats = 0;
         CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         { const int rc = build_any_tables(c, std::max(32, std::max(frame_w, frame_h) / KCF_CELL)); if (rc) return rc; }
+        CU(cudaHostAlloc(&c->h_any_err, sizeof(int), cudaHostAllocMapped)); *c->h_any_err = 0;
+        CU(cudaHostGetDevicePointer(&c->d_any_err, c->h_any_err, 0));
     } else {
         c->kal.cap = max_tracks;
         CU(cudaMalloc(&c->kal.x, sizeof(double) * 6 * max_tracks));
@@ -375,6 +377,7 @@ void mot_ctx_destroy(mot_ctx_t *c)
     for (auto p : c->frame_owned) if (p) cudaFree(p);
     cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
     cudaFree(c->d_tab_rsqrt); cudaFree(c->d_tab_rcp); cudaFree(c->d_tab_rsrc); cudaFree(c->d_tab_bin); cudaFree(c->d_tab_bin2); cudaFree(c->kal.x); cudaFree(c->kal.P);
+    if (c->h_any_err) cudaFreeHost(c->h_any_err);
     cudaFree((void *)c->any.hann); cudaFree((void *)c->any.tw); cudaFree((void *)c->any.lab); cudaFree((void *)c->any.plan);
     for (auto &sc : c->classes) { cudaFree(sc.d_wy); cudaFree(sc.d_wx); cudaFree(sc.d_yf); cudaFree(sc.d_twh); cudaFree(sc.d_tww); }
     for (auto &m : c->meta_h) { if (m.model_ptr) cudaFree(m.model_ptr); if (m.alpha_ptr) cudaFree(m.alpha_ptr); }
@@ -391,7 +394,13 @@ void mot_ctx_destroy(mot_ctx_t *c)
 }
 
 int mot_ctx_set_stream(mot_ctx_t *c, void *s) { if (!c) return fail(MOT_ERR_ARG, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
-int mot_sync(mot_ctx_t *c) { if (!c) return fail(MOT_ERR_ARG, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->copy_stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+int mot_sync(mot_ctx_t *c)
+{
+    if (!c) return fail(MOT_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->copy_stream)); CU(cudaStreamSynchronize(c->stream));
+    if (c->h_any_err && *c->h_any_err) { *c->h_any_err = 0; return fail(MOT_ERR_SHAPE, "a KCF job did not fit the shared memory of its launch and was skipped (internal sizing error)"); }
+    return 0;
+}
 long mot_launch_count(mot_ctx_t *c) { return c ? c->launches : 0; }
 int mot_ctx_kind(mot_ctx_t *c) { return c ? c->kind : MOT_ERR_ARG; }
 
@@ -617,7 +626,7 @@ static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
         const size_t smem = kcf_any_smem_bytes(hr, wc, c->lut_floats);
         if (smem && hr <= c->any.nmax && wc <= c->any.nmax) {
             int threads, ctas; any_launch_shape(smem, &threads, &ctas);
-            const int rc = kcf_launch_any(mode, L, c->any, smem, threads, ctas, c->stream);
+            const int rc = kcf_launch_any(mode, L, c->any, smem, threads, ctas, c->d_any_err, c->stream);
             if (rc) return fail(MOT_ERR_CUDA, "KCF (any-size kernel) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
             c->launches += 1;
             return 0;
@@ -672,6 +681,7 @@ static int kcf_batch_host(mot_ctx_t *c, int mode, int n, const int *handles, con
     } else {
         CU(cudaStreamSynchronize(c->stream));     // staging buffers are reused by the next call
     }
+    if (c->h_any_err && *c->h_any_err) { *c->h_any_err = 0; return fail(MOT_ERR_SHAPE, "a KCF job did not fit the shared memory of its launch and was skipped (internal sizing error)"); }
     return 0;
 }
 
