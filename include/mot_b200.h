@@ -162,6 +162,11 @@ int mot_td_create(mot_td_t **out, mot_ctx_t *ctx, int frame_slot, int cap, int c
 void mot_td_destroy(mot_td_t *td);
 /* host_bgr may be NULL when the frame slot was already filled (or for the Kalman kind, which never reads pixels). */
 int mot_td_step(mot_td_t *td, const uint8_t *host_bgr, int stride_bytes, const mot_bbox_t *dets, int ndet);
+/* The same step fed with the detector's wire format: one bbox_chain_t per frame (top/cnntype.h:43-47; the tracking thread reads
+ * pdetected->nbox and ->bbox[], top/td.cpp:326-335), and a detector batch as tensorRunB delivers it (top/td.cpp:178-204: up to
+ * MAX_GPU_BATCH = 4 frames, one chain each), consumed frame by frame in queue order. */
+int mot_td_step_chain(mot_td_t *td, const uint8_t *host_bgr, int stride_bytes, const mot_bbox_chain_t *chain);
+int mot_td_step_chain_batch(mot_td_t *td, int nbatch, const uint8_t *const *host_bgr, int stride_bytes, const mot_bbox_chain_t *const *chains);
 /* Lock-step over several streams: one batched predict / associate / update per frame instead of one per stream. */
 int mot_td_step_multi(mot_td_t **tds, int n_streams, const uint8_t *const *host_bgr, int stride_bytes,
                       const mot_bbox_t *const *dets, const int *ndet);
@@ -190,6 +195,8 @@ void mot_tdd_destroy(mot_tdd_t *tdd);
 int mot_tdd_step_dev(mot_tdd_t *tdd, const mot_bbox_t *d_dets, const int *d_ndet);
 /* detections in host arrays (dets[s] points at ndet[s] boxes); staged, uploaded and stepped; asynchronous */
 int mot_tdd_step(mot_tdd_t *tdd, const mot_bbox_t *const *dets, const int *ndet);
+/* one bbox_chain_t per stream (NULL = no detections): the detector's wire format; max_det must cover the chains' nbox */
+int mot_tdd_step_chains(mot_tdd_t *tdd, const mot_bbox_chain_t *const *chains);
 /* KCF kind: from the next step on, stream s reads frame slot base + s (default 0).  Steps are asynchronous: do not upload
  * into a slot that a step still in flight reads -- alternate two bases (2 * n_streams frame slots) or call mot_sync first. */
 int mot_tdd_frame_base(mot_tdd_t *tdd, int base);
@@ -211,6 +218,11 @@ long mot_debug_state(mot_ctx_t *ctx, int handle, int which, void *host_out, long
  * 4 orientation-bin step table (u32 bits) | 5 the same with the wrap folded in (u32 bits) | 6 {saturation threshold bits, rcp(1e10f)};
  * info[0..3] = rsqrt_bits, rcp_bits, bin_shift, bin_nseg */
 long mot_debug_tables(int which, float *out, long max_floats, int *info);
+
+/* How the fused any-size kernel would run an hr x wc cell grid (host-only, no GPU needed): out[16] = ok, strip mode, shared-memory
+ * bytes, channels per tile, gradient strip width, cell columns per strip, spectral buffer (complex), region A / B floats, scratch bytes
+ * per CTA, CTAs per SM, threads per CTA, passes of the length-hr / length-wc transforms; radices[14] = their radices (7 slots each). */
+int mot_debug_any_plan(int hr, int wc, int *out, int *radices);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -267,17 +267,20 @@ __device__ __forceinline__ float2 *fft_batch(float2 *buf0, float2 *buf1, int n, 
 
 // ordered gather of the 18-bin histograms, CPT cells per thread interleaved (libhog/gradientMex.cpp:183-230, 308-309)
 template <int CPT>
-__device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, const uint32_t *__restrict__ MB, float *__restrict__ R1, float *__restrict__ Es, int cell0, int NT)
+// Cells are numbered column-major inside the strip (ncell of them, first cell column cx0 of the window); MB is the strip's map
+// (local pixel column 0 = window pixel 4 cx0 - 2), R1 its histograms with plane stride OS.
+__device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, const uint32_t *__restrict__ MB, float *__restrict__ R1, int OS, float *__restrict__ Es,
+                                             int cell0, int ncell, int cx0, int NT)
 {
-    const int OS = g.os, PC = g.pc, PS = g.ps;
+    const int PC = g.pc, PS = g.ps;
     int ccx[CPT], ccy[CPT]; bool live[CPT]; float *h[CPT]; const uint32_t *mb0[CPT];
 #pragma unroll
     for (int u = 0; u < CPT; ++u) {
         const int cell = cell0 + u * NT;
-        live[u] = cell < g.nb;
+        live[u] = cell < ncell;
         const int cc = live[u] ? cell : 0;
         ccx[u] = fdiv(cc, mg_hr); ccy[u] = cc - ccx[u] * g.hr;
-        h[u] = R1 + ccx[u] * g.rs + ccy[u];
+        h[u] = R1 + cc;
         mb0[u] = MB + (4 * ccx[u]) * PC + ccy[u];
         if (live[u])
             for (int o = 0; o < 18; ++o) h[u][o * OS] = 0.f;
@@ -302,7 +305,7 @@ __device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, co
 #pragma unroll
     for (int u = 0; u < CPT; ++u) {
         if (!live[u]) continue;
-        const int cx = ccx[u], cy = ccy[u];
+        const int cx = ccx[u] + cx0, cy = ccy[u];
         // boundary cells x 8/7 per touching side (gradientMex.cpp:226-229): x first, then y; multiplying by 1.0f is the identity
         const float sx0 = (cx == 0) ? 8.f / 7.f : 1.f, sy0 = (cy == 0) ? 8.f / 7.f : 1.f;
         const float sx1 = (cx == g.wc - 1) ? 8.f / 7.f : 1.f, sy1 = (cy == g.hr - 1) ? 8.f / 7.f : 1.f;
@@ -321,8 +324,9 @@ __device__ __forceinline__ void gather_cells(const AnyGeo &g, uint32_t mg_hr, co
 
 }  // namespace
 
-template <int MODE, bool DUMP, int NTMAX>
-__global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, const AnyTablesDev at, const int lut_floats, const int smem_floats, int *err_flag)
+template <int MODE, bool DUMP, int NTMAX, bool STRIPS>
+__global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, const AnyTablesDev at, const int lut_floats, const int smem_floats, int *err_flag,
+                                                           float *r1g_base, long r1g_stride)
 {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t mbar_lut, mbar_raw;
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
     const int n_rs = 2 * (2 << p.tab.rsqrt_bits), n_bn = (2 * p.tab.bin_nseg + 3) & ~3;
     const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
     const int n_jobs = p.n_jobs_dev ? min(*p.n_jobs_dev, p.n_jobs) : p.n_jobs;
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase_raw = 0;
 
     for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         __syncthreads();                                       // the previous job is done with shared memory (and with jc)
@@ -374,14 +378,17 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
             __syncthreads();
         }
         const AnyGeo &g = jc.g;
-        if (g.total > smem_floats || !g.ok) {                  // cannot happen when the host sized the launch; never run out of bounds
+        if (g.total > smem_floats || !g.ok || (g.strips != 0) != STRIPS) {     // cannot happen when the host sized the launch; never run out of bounds
             if (tid == 0 && err_flag) *reinterpret_cast<volatile int *>(err_flag) = 1;
             continue;
         }
         const int H0 = g.h0, W0 = g.w0, SK = g.sk, S = g.S, JP = g.jp, NB = g.nb;
         uint32_t *const MB = reinterpret_cast<uint32_t *>(smem);
         float *const Bf = smem + g.oB;
-        float *const R1 = Bf;
+        // histograms: all in shared memory (on top of the tables and the staging area, dead by then), or -- strip mode -- one strip
+        // at a time behind the tables, parked in this CTA's global scratch from which the spectral phase reads them
+        float *const R1s = STRIPS ? Bf + g.lutp : Bf;
+        const float *const R1 = STRIPS ? r1g_base + (long)blockIdx.x * r1g_stride : Bf;
         unsigned char *const raw = reinterpret_cast<unsigned char *>(Bf + g.lutp);
         float *const GSB = Bf + g.lutp + (4 * hr + 3) * (g.raw_pitch / 4);
         float *const Ns = smem + g.oN, *const Es = smem + g.oE;
@@ -395,19 +402,12 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
         if (l > r) { const int q = l; l = r; r = q; }
         const int rows_s = b - t + 1, cols_s = r - l + 1;
         const bool identity = (p.gray == nullptr) && rows_s == rows && cols_s == cols;
-        const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols_s - 1, 0, Wm);
-        const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;
-        const bool staged = identity && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0 && (a1 - a0) <= g.raw_pitch && rows_s <= 4 * hr + 3;
+        const bool can_stage = identity && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0 && rows_s <= 4 * hr + 3;
         if (warp == 0) {
             if (lane == 0) {
                 mbar_expect_tx(&mbar_lut, lut_smem ? (uint32_t)(n_rs + n_bn) * 4u : 0u);
                 if (lut_smem) { bulk_g2s(Bf, p.tab.rsrc_tab, n_rs * 4, &mbar_lut); bulk_g2s(Bf + n_rs, p.tab.bin2_tab, n_bn * 4, &mbar_lut); }
-                mbar_expect_tx(&mbar_raw, staged ? (uint32_t)rows_s * (uint32_t)(a1 - a0) : 0u);
             }
-            __syncwarp();
-            if (staged)
-                for (int y = lane; y < rows_s; y += 32)
-                    bulk_g2s(raw + y * g.raw_pitch, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar_raw);
         } else if (warp == 1) {
             // the model is not needed before the spectral phase: pull it (and alpha) into L2 now
             if (lane == 0 && (MODE == KCF_MODE_PREDICT || !first_update)) prefetch_l2_bulk(model, (uint32_t)(KCF_CHAN * S * 8) & ~15u);
@@ -419,30 +419,19 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
             for (int i = tid; i < hr; i += NT) { TWR[i] = twr[i]; wy_s[i] = 0.5f * hy[i]; }     // halved: carries the x0.5 of hogChannels (exact scaling)
             for (int i = tid; i < wc; i += NT) { TWC[i] = twc[i]; wx_s[i] = hx[i]; }
         }
-        // zero border of the (M | bin) layout: columns x+2 in {0, 1, W0+2, W0+3} entirely, rows y+2 in {0, 1, H0+2, H0+3} of the others
-        {
-            const int PC = g.pc, PS = g.ps;
-            for (int k = tid; k < 4 * PC; k += NT) { const int cq = k / PC, o = k - cq * PC; MB[(cq < 2 ? cq : W0 + cq) * PC + o] = 0u; }
-            for (int k = tid; k < 4 * W0; k += NT) {
-                const int x2 = 2 + (k >> 2), q = k & 3;
-                MB[x2 * PC + q * PS + (q < 2 ? 0 : hr)] = 0u;            // y+2 = 0, 1 -> (sub 0, 1; idx 0);  y+2 = H0+2, H0+3 -> (sub 2, 3; idx hr)
-            }
-        }
-        if (warp == 0) { mbar_wait(&mbar_raw, phase); mbar_wait(&mbar_lut, phase); }
-        phase ^= 1u;                                               // one arrival per barrier and job, bytes or not
-        __syncthreads();
 
-        // ---------------------------------------------------------------- P1: per strip, gray -> gradient magnitude + orientation bin
+        // ---------------------------------------------------------------- P1 + P2, per strip of cell columns (one strip = the whole window unless STRIPS)
         {
             const LutConsts lk = make_lut_consts(p.tab);
             const float2 *const rsrc = lut_smem ? reinterpret_cast<const float2 *>(Bf) : p.tab.rsrc_tab;
             const uint32_t *const bn = lut_smem ? reinterpret_cast<const uint32_t *>(Bf) + n_rs : p.tab.bin2_tab;
             const int GS = g.gs, PC = g.pc, PS = g.ps;
             const float xs_f = __fdiv_rn((float)cols_s, (float)cols), ys_f = __fdiv_rn((float)rows_s, (float)rows);
+            int a0 = 0;                                                     // frame-row byte offset of the staged span of the current strip
             // gray value of template pixel (x, y): staged frame bytes, the caller's gray patch, plain loads (unaligned frames), or
             // the reference's resample when the crop has another size than the template
-            auto gray_at = [&](int x, int y) -> float {
-                if (staged) return bgr_gray(raw + y * g.raw_pitch + clampi(l + x, 0, Wm) * 3 - a0);
+            auto gray_at = [&](int x, int y, bool from_stage) -> float {
+                if (from_stage) return bgr_gray(raw + y * g.raw_pitch + clampi(l + x, 0, Wm) * 3 - a0);
                 if (p.gray != nullptr) return p.gray[(long)job * p.gray_stride + x * rows + y];
                 if (identity) return bgr_gray(frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + clampi(l + x, 0, Wm) * 3);
                 // the reference resamples a column-major crop as if it were row-major height x width; reproduced through
@@ -466,60 +455,104 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
                 return __fadd_rn(__fmul_rn(ify, l0), __fmul_rn(fy, l1));
             };
             if (DUMP && p.dump.gray)                                        // (test hook) the whole rows x cols patch, column-major
-                for (int k = tid; k < rows * cols; k += NT) { const int x = k / rows; p.dump.gray[(long)job * p.dump.stride_px + k] = gray_at(x, k - x * rows); }
+                for (int k = tid; k < rows * cols; k += NT) { const int x = k / rows; p.dump.gray[(long)job * p.dump.stride_px + k] = gray_at(x, k - x * rows, false); }
             const bool inside = l >= 0 && l + cols - 1 <= Wm;               // no horizontal clamping needed (the common case)
             // gradient mapping: a warp keeps one chunk of 32 rows (its y, border factor and the y part of the store address are fixed)
             // and walks over pixel columns; with fewer warps than chunks it takes several chunks in turn
             const int nych = (H0 + 31) >> 5;
             const int ywarps = min(nwarps, nych), ngrp = max(1, fdiv(nwarps, jc.mg_nych));
             const int wyc = nwarps >= nych ? warp - fdiv(warp, jc.mg_nych) * nych : warp, xg = nwarps >= nych ? fdiv(warp, jc.mg_nych) : 0;
-            for (int xs = 0; xs < W0; xs += g.xw) {
-                const int xe = min(xs + g.xw, W0), nx = xe - xs + 2;
-                // gray of template pixels (x, y), x in [xs-1, xe], y in [-1, H0], coordinates clamped into the template: the clamped
-                // apron turns grad1's one-sided border differences (gradientMex.cpp:15-37) into plain differences
-                for (int yy = warp; yy < H0 + 2; yy += nwarps) {
-                    const int y = clampi(yy - 1, 0, rows - 1);
-                    if (staged && inside) {
-                        const unsigned char *rrow = raw + y * g.raw_pitch + l * 3 - a0;
-                        for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = bgr_gray(rrow + clampi(xs - 1 + lx, 0, cols - 1) * 3);
-                    } else {
-                        for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = gray_at(clampi(xs - 1 + lx, 0, cols - 1), y);
+            const int CSW = STRIPS ? g.cs : wc, OSS = STRIPS ? g.oss : g.os;
+            for (int cs0v = 0; cs0v < (STRIPS ? wc : 1); cs0v += CSW) {
+                const int cs0 = STRIPS ? cs0v : 0, cs1 = STRIPS ? min(wc, cs0v + CSW) : wc;      // compile-time 0 / wc without strips
+                // pixel columns [pxb, pxe) of the window live in the strip's (M | bin) map, local column x - pxb; [gxb, gxe) of them exist
+                const int pxb = 4 * cs0 - 2, pxe = 4 * cs1 + 2, gxb = max(pxb, 0), gxe = min(pxe, W0);
+                // template columns whose gray the strip needs (one more on each side for the gradient), and their bytes in a frame row
+                const int ta = max(gxb - 1, 0), tb = min(gxe, cols - 1);
+                const int xa = clampi(l + ta, 0, Wm), xb = clampi(l + tb, 0, Wm);
+                const int a1 = ((xb + 1) * 3 + 15) & ~15;
+                a0 = (xa * 3) & ~15;
+                const bool staged = can_stage && (a1 - a0) <= g.raw_pitch;
+                if (STRIPS) __syncthreads();                           // the previous strip is done with the staging area, its histograms and its map
+                if (warp == 0) {
+                    if (lane == 0) mbar_expect_tx(&mbar_raw, staged ? (uint32_t)rows_s * (uint32_t)(a1 - a0) : 0u);
+                    __syncwarp();
+                    if (staged)
+                        for (int y = lane; y < rows_s; y += 32)
+                            bulk_g2s(raw + y * g.raw_pitch, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar_raw);
+                }
+                // zero border of the map: the columns outside the window entirely, rows y+2 in {0, 1, H0+2, H0+3} of the others
+                {
+                    const int ncol = pxe - pxb;
+                    for (int k = tid; k < 4 * PC; k += NT) {
+                        const int cq = k / PC, o = k - cq * PC, lc = cq < 2 ? cq : ncol - 4 + cq;      // local columns 0, 1, ncol-2, ncol-1
+                        const int x = pxb + lc;
+                        if (x < 0 || x >= W0) MB[lc * PC + o] = 0u;
+                    }
+                    for (int k = tid; k < 4 * (gxe - gxb); k += NT) {
+                        const int lc = gxb - pxb + (k >> 2), q = k & 3;
+                        MB[lc * PC + q * PS + (q < 2 ? 0 : hr)] = 0u;        // y+2 = 0, 1 -> (sub 0, 1; idx 0);  y+2 = H0+2, H0+3 -> (sub 2, 3; idx hr)
                     }
                 }
+                if (warp == 0) { mbar_wait(&mbar_raw, phase_raw); if (cs0 == 0) mbar_wait(&mbar_lut, phase); }
+                phase_raw ^= 1u;                                       // one arrival per strip, bytes or not
                 __syncthreads();
-                // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin)
-                if (xg < ngrp)
-                    for (int yc = wyc; yc < nych; yc += ywarps) {
-                        const int y = (yc << 5) + lane;
-                        if (y >= H0) continue;
-                        const float ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
-                        const float *gp = GSB + (xg + 1) * GS + y + 1;
-                        uint32_t *mp = MB + (xs + xg + 2) * PC + ((y + 2) & 3) * PS + ((y + 2) >> 2);
-                        for (int lx = xg; lx < xe - xs; lx += ngrp, gp += ngrp * GS, mp += ngrp * PC) {
-                            const int x = xs + lx;
-                            const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f;
-                            const float gx = __fmul_rn(__fsub_rn(gp[GS], gp[-GS]), rx);
-                            const float gy = __fmul_rn(__fsub_rn(gp[1], gp[-1]), ry);
-                            const uint32_t mb = grad_pixel_k(gx, gy, rsrc, bn, lk);
-                            *mp = mb;
-                            if (DUMP && p.dump.m0) {
-                                const long idx = (long)job * p.dump.stride_px + x * H0 + y;
-                                p.dump.m0[idx] = __uint_as_float(mb & ~31u); p.dump.bin[idx] = (int)(mb & 31u);
-                            }
+                for (int xs = gxb; xs < gxe; xs += g.xw) {
+                    const int xe = min(xs + g.xw, gxe), nx = xe - xs + 2;
+                    // gray of template pixels (x, y), x in [xs-1, xe], y in [-1, H0], coordinates clamped into the template: the clamped
+                    // apron turns grad1's one-sided border differences (gradientMex.cpp:15-37) into plain differences
+                    for (int yy = warp; yy < H0 + 2; yy += nwarps) {
+                        const int y = clampi(yy - 1, 0, rows - 1);
+                        if (staged && inside) {
+                            const unsigned char *rrow = raw + y * g.raw_pitch + l * 3 - a0;
+                            for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = bgr_gray(rrow + clampi(xs - 1 + lx, 0, cols - 1) * 3);
+                        } else {
+                            for (int lx = lane; lx < nx; lx += 32) GSB[lx * GS + yy] = gray_at(clampi(xs - 1 + lx, 0, cols - 1), y, staged);
                         }
                     }
-                __syncthreads();
+                    __syncthreads();
+                    // libhog/gradientMex.cpp:15-37 (grad1), :59-100 (gradMag, d=1, full=true), :112-145 (gradQuantize, nearest bin)
+                    if (xg < ngrp)
+                        for (int yc = wyc; yc < nych; yc += ywarps) {
+                            const int y = (yc << 5) + lane;
+                            if (y >= H0) continue;
+                            const float ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
+                            const float *gp = GSB + (xg + 1) * GS + y + 1;
+                            uint32_t *mp = MB + (xs + xg - pxb) * PC + ((y + 2) & 3) * PS + ((y + 2) >> 2);
+                            for (int lx = xg; lx < xe - xs; lx += ngrp, gp += ngrp * GS, mp += ngrp * PC) {
+                                const int x = xs + lx;
+                                const float rx = (x == 0 || x == cols - 1) ? 1.f : .5f;
+                                const float gx = __fmul_rn(__fsub_rn(gp[GS], gp[-GS]), rx);
+                                const float gy = __fmul_rn(__fsub_rn(gp[1], gp[-1]), ry);
+                                const uint32_t mb = grad_pixel_k(gx, gy, rsrc, bn, lk);
+                                *mp = mb;
+                                if (DUMP && p.dump.m0) {
+                                    const long idx = (long)job * p.dump.stride_px + x * H0 + y;
+                                    p.dump.m0[idx] = __uint_as_float(mb & ~31u); p.dump.bin[idx] = (int)(mb & 31u);
+                                }
+                            }
+                        }
+                    __syncthreads();
+                }
+                // ---- P2: cell histograms of the strip (ordered gather); up to four cells per thread interleaved (independent
+                // dependency chains), larger strips go round again
+                const int ncell = (cs1 - cs0) * hr;
+                for (int cb = 0; cb < ncell; cb += 4 * NT) {
+                    const int left = ncell - cb;
+                    if (left <= NT) gather_cells<1>(g, jc.mg_hr, MB, R1s, OSS, Es, cb + tid, ncell, cs0, NT);
+                    else if (left <= 2 * NT) gather_cells<2>(g, jc.mg_hr, MB, R1s, OSS, Es, cb + tid, ncell, cs0, NT);
+                    else if (left <= 3 * NT) gather_cells<3>(g, jc.mg_hr, MB, R1s, OSS, Es, cb + tid, ncell, cs0, NT);
+                    else gather_cells<4>(g, jc.mg_hr, MB, R1s, OSS, Es, cb + tid, ncell, cs0, NT);
+                }
+                if (STRIPS) {
+                    // park the strip's histograms in the CTA's global scratch: plane o of the window at o * g.os, cells column-major
+                    __syncthreads();
+                    float *const R1w = r1g_base + (long)blockIdx.x * r1g_stride + cs0 * hr;
+                    for (int o = warp; o < 18; o += nwarps)
+                        for (int c2 = lane; c2 < ncell; c2 += 32) R1w[o * g.os + c2] = R1s[o * OSS + c2];
+                }
             }
-        }
-
-        // ---------------------------------------------------------------- P2: cell histograms (ordered gather)
-        // up to four cells per thread interleaved (independent dependency chains); larger windows go round again
-        for (int cb = 0; cb < NB; cb += 4 * NT) {
-            const int left = NB - cb;
-            if (left <= NT) gather_cells<1>(g, jc.mg_hr, MB, R1, Es, cb + tid, NT);
-            else if (left <= 2 * NT) gather_cells<2>(g, jc.mg_hr, MB, R1, Es, cb + tid, NT);
-            else if (left <= 3 * NT) gather_cells<3>(g, jc.mg_hr, MB, R1, Es, cb + tid, NT);
-            else gather_cells<4>(g, jc.mg_hr, MB, R1, Es, cb + tid, NT);
+            phase ^= 1u;                                                   // the tables arrive once per job
         }
         __syncthreads();
         const int OS = g.os, RS = g.rs;
@@ -770,35 +803,48 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
 size_t kcf_any_smem_bytes(int hr, int wc, int lut_floats)
 {
     const AnyGeo g = any_geo(hr, wc, lut_floats);
-    if (!g.ok || g.nb > 2048) return 0;
-    return (size_t)g.total * sizeof(float);
+    return g.ok ? (size_t)g.total * sizeof(float) : 0;
 }
 
-int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, int *err_flag, cudaStream_t s)
+size_t kcf_any_scratch_bytes(int hr, int wc, int lut_floats)
+{
+    const AnyGeo g = any_geo(hr, wc, lut_floats);
+    return (g.ok && g.strips) ? (size_t)18 * g.os * sizeof(float) : 0;
+}
+
+int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, int *err_flag,
+                   float *scratch, long scratch_stride_floats, int max_ctas, cudaStream_t s)
 {
     const FhogTablesDev &t = p.tab;
     int lut_floats = 2 * (2 << t.rsqrt_bits) + ((2 * t.bin_nseg + 3) & ~3);
     if (lut_floats > 8192) lut_floats = 0;
-    const bool dump = p.dump.gray != nullptr;
-    const void *fn;
+    const bool dump = p.dump.gray != nullptr, strips = scratch != nullptr;
     // two register budgets: 128 registers per thread (at most 512 threads per SM in total) or 64 (1024 threads per SM)
     bool r128 = threads * (ctas_per_sm < 1 ? 1 : ctas_per_sm) <= 512;
     if (getenv("MOT_ANY_THREADS")) threads = atoi(getenv("MOT_ANY_THREADS"));
     if (getenv("MOT_ANY_CTAS")) ctas_per_sm = atoi(getenv("MOT_ANY_CTAS"));
     if (getenv("MOT_ANY_R128")) r128 = atoi(getenv("MOT_ANY_R128")) != 0;
     if (r128 && threads > 512) threads = 512;
-    if (mode == KCF_MODE_PREDICT) fn = dump ? (const void *)kcf_any_kernel<KCF_MODE_PREDICT, true, 1024> : r128 ? (const void *)kcf_any_kernel<KCF_MODE_PREDICT, false, 512> : (const void *)kcf_any_kernel<KCF_MODE_PREDICT, false, 1024>;
-    else                          fn = dump ? (const void *)kcf_any_kernel<KCF_MODE_UPDATE, true, 1024> : r128 ? (const void *)kcf_any_kernel<KCF_MODE_UPDATE, false, 512> : (const void *)kcf_any_kernel<KCF_MODE_UPDATE, false, 1024>;
+    const int pm = mode == KCF_MODE_PREDICT ? 0 : 1, v = dump ? 0 : r128 ? 1 : 2;
+#define ANY_FN(M, D, N, S) (const void *)kcf_any_kernel<M, D, N, S>
+    static const void *const fns[2][2][3] = {
+        { { ANY_FN(KCF_MODE_PREDICT, true, 1024, false), ANY_FN(KCF_MODE_PREDICT, false, 512, false), ANY_FN(KCF_MODE_PREDICT, false, 1024, false) },
+          { ANY_FN(KCF_MODE_PREDICT, true, 1024, true), ANY_FN(KCF_MODE_PREDICT, false, 512, true), ANY_FN(KCF_MODE_PREDICT, false, 1024, true) } },
+        { { ANY_FN(KCF_MODE_UPDATE, true, 1024, false), ANY_FN(KCF_MODE_UPDATE, false, 512, false), ANY_FN(KCF_MODE_UPDATE, false, 1024, false) },
+          { ANY_FN(KCF_MODE_UPDATE, true, 1024, true), ANY_FN(KCF_MODE_UPDATE, false, 512, true), ANY_FN(KCF_MODE_UPDATE, false, 1024, true) } } };
+#undef ANY_FN
+    const void *fn = fns[pm][strips ? 1 : 0][v];
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int cap = sms * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+    int cap = sms * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+    if (max_ctas > 0 && cap > max_ctas) cap = max_ctas;
     const int grid = p.n_jobs < cap ? p.n_jobs : cap;
     int smem_floats = (int)(smem_bytes / sizeof(float));
     int *err = err_flag;
-    void *args[5] = { (void *)&p, (void *)&at, (void *)&lut_floats, (void *)&smem_floats, (void *)&err };
+    void *args[7] = { (void *)&p, (void *)&at, (void *)&lut_floats, (void *)&smem_floats, (void *)&err, (void *)&scratch, (void *)&scratch_stride_floats };
     e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)threads), args, smem_bytes, s);
     return (int)e;
 }

@@ -23,6 +23,10 @@ struct AnyGeo {
     int aF, bF;             // region sizes
     int oB, oN, oE, oACC, oTWR, oTWC, oWY, oWX, oRED, total;   // offsets / total (floats)
     int ok;                 // fits the budget
+    // Windows whose (M | bin) map and cell histograms do not fit one CTA's shared memory together run in STRIPS of `cs` cell columns:
+    // frame rows, gray, (M | bin) and the histograms of one strip at a time in shared memory, the finished histograms parked in a
+    // per-CTA scratch area in global memory (L2-resident), from which the spectral phase generates the channels.
+    int strips, cs, oss;    // strip mode; cell columns per strip; orientation-plane stride of the strip's histograms (multiple of 32)
 };
 
 constexpr int ANY_SMEM_BUDGET_FLOATS = (227 * 1024 - 2048) / 4;      // dynamic shared memory one CTA may use (static part left out)
@@ -73,6 +77,26 @@ __host__ __device__ inline AnyGeo any_geo(int hr, int wc, int lut_floats)
             g.ok = aF + bF + cF <= ANY_SMEM_BUDGET_FLOATS;
         }
     }
+    g.strips = 0; g.cs = wc; g.oss = g.os;
+    if (!g.ok) {
+        // strip mode: the widest strip that still leaves room for tiles of >= 4 channels, else >= 2, else 1
+        const int ps = hr + 1, pc = 4 * ps + 2;
+        for (int want_tc = 4; want_tc >= 1 && !g.ok; want_tc = want_tc > 2 ? 2 : want_tc - 1) {
+            for (int cs = 16; cs >= 1 && !g.ok; cs >>= 1) {
+                if (cs > wc) continue;
+                const int pxw = 4 * cs + 6;                                   // gray columns of a strip: its pixels, +-2 for the gather, +-1 for the gradient
+                const int pitch = ((3 * pxw + 30) + 15) & ~15;
+                const int raw_s = rmax * (pitch / 4), oss = (cs * hr + 31) & ~31;
+                const int bF = (g.lutp + any_max(raw_s + pxw * g.gs, 18 * oss) + 3) & ~3;
+                const int a_min = any_max((4 * cs + 4) * pc, 4 * any_xbuf(hr, wc, g.jp, g.sk, want_tc));
+                const int left = ANY_SMEM_BUDGET_FLOATS - bF - cF;
+                if (left < a_min) continue;
+                g.strips = 1; g.cs = cs; g.oss = oss; g.ps = ps; g.pc = pc; g.padm = (4 * cs + 4) * pc; g.raw_pitch = pitch; g.xw = 4 * cs + 4;
+                g.bF = bF; g.aF = any_min(left & ~3, (any_max(g.padm, 4 * any_xbuf(hr, wc, g.jp, g.sk, KCF_CHAN)) + 3) & ~3);
+                g.ok = 1;
+            }
+        }
+    }
     // channels per tile: as many as two ping-pong buffers in region A hold, then balanced over the resulting number of tiles
     int tcmax = 1;
     for (int tc = 2; tc <= KCF_CHAN; ++tc) if (4 * any_xbuf(hr, wc, g.jp, g.sk, tc) <= g.aF) tcmax = tc;
@@ -83,7 +107,7 @@ __host__ __device__ inline AnyGeo any_geo(int hr, int wc, int lut_floats)
     const int c0 = g.aF + g.bF;
     g.oN = c0 + cN; g.oE = c0 + cE; g.oACC = c0 + cACC; g.oTWR = c0 + cTWR; g.oTWC = c0 + cTWC; g.oWY = c0 + cWY; g.oWX = c0 + cWX; g.oRED = c0 + cRED;
     g.total = c0 + cF;
-    if (hr < 2 || wc < 2 || g.S > NB_MAX) g.ok = 0;      // model / alpha live in the slot arena (31 * NB_MAX complex, NB_MAX floats)
+    if (hr < 2 || wc < 2) g.ok = 0;
     return g;
 }
 
@@ -100,10 +124,14 @@ struct AnyTablesDev {
 };
 __host__ __device__ inline int any_off(int N) { return N * (N - 1) / 2 - 1; }
 
-// 0 when the fused any-size kernel cannot hold an hr x wc window (the unfused path kcf_generic.cu serves it then)
+// 0 when the fused any-size kernel cannot hold an hr x wc window even in strips (the unfused path kcf_generic.cu serves it then)
 size_t kcf_any_smem_bytes(int hr, int wc, int lut_floats);
+// bytes of global scratch one CTA needs for this window (0: everything stays in shared memory)
+size_t kcf_any_scratch_bytes(int hr, int wc, int lut_floats);
 // One launch over jobs of ANY mix of sizes whose plans fit `smem_bytes`; threads = CTA size to use.  A job whose plan does not fit
 // (a host-side sizing bug) is skipped and *err_flag (device-visible, may be null) set, never run out of bounds.
-int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, int *err_flag, cudaStream_t s);
+// scratch / scratch_stride: per-CTA global scratch for strip-mode windows (null: the launch holds none; such jobs are skipped and flagged).
+int kcf_launch_any(int mode, const KcfLaunch &p, const AnyTablesDev &at, size_t smem_bytes, int threads, int ctas_per_sm, int *err_flag,
+                   float *scratch, long scratch_stride_floats, int max_ctas, cudaStream_t s);
 
 }  // namespace mot

@@ -286,7 +286,7 @@ int mot_ctx_kcf_launch_any(mot_ctx_t *c, int mode, size_t smem_bytes, int n_max,
     KcfLaunch L; fill_launch(c, L, n_max, slots, frames, boxes, clamp);
     L.n_jobs_dev = n_dev; L.box_index = box_index; L.dump = KcfDump{};
     int threads, ctas; any_launch_shape(smem_bytes, &threads, &ctas);
-    const int rc = kcf_launch_any(mode, L, c->any, smem_bytes, threads, ctas, c->d_any_err, c->stream);
+    const int rc = kcf_launch_any(mode, L, c->any, smem_bytes, threads, ctas, c->d_any_err, nullptr, 0, 0, c->stream);
     if (rc) return fail(MOT_ERR_CUDA, "KCF (any-size kernel) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     c->launches += 1;
     return 0;
@@ -541,7 +541,7 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
             int cls = 0; const int rc = get_class(c, m.hr, m.wc, &cls); if (rc) return rc;
             m.size_class = cls;
             const long S_ = (long)m.wc * (m.hr / 2 + 1);
-            if (!c->classes[cls].fast && !c->classes[cls].any_smem) {
+            if (!c->classes[cls].fast && (!c->classes[cls].any_smem || S_ > NB_MAX)) {
                 // sizes that no fused kernel holds own their model / alpha (they can exceed the fixed slot stride)
                 CU(cudaMalloc(&m.model_ptr, sizeof(float2) * KCF_CHAN * S_)); CU(cudaMalloc(&m.alpha_ptr, sizeof(float) * S_));
                 CU(cudaMemsetAsync(m.model_ptr, 0, sizeof(float2) * KCF_CHAN * S_, c->stream)); CU(cudaMemsetAsync(m.alpha_ptr, 0, sizeof(float) * S_, c->stream));
@@ -549,7 +549,7 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
             const int slot = c->free_slots.back(); c->free_slots.pop_back();
             c->used[slot] = 1; c->meta_h[slot] = m; c->classes[cls].live++;
             c->h_slots.p[i] = slot; c->h_meta_stage.p[i] = m; handles_out[i] = slot;
-            if (c->classes[cls].fast || c->classes[cls].any_smem) { max_model = std::max(max_model, KCF_CHAN * S_); max_alpha = std::max(max_alpha, S_); }
+            if (c->classes[cls].fast || (c->classes[cls].any_smem && S_ <= NB_MAX)) { max_model = std::max(max_model, KCF_CHAN * S_); max_alpha = std::max(max_alpha, S_); }
         }
         CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_meta_stage.p, c->h_meta_stage.p, sizeof(KcfMeta) * n, cudaMemcpyHostToDevice, c->stream));
@@ -626,7 +626,12 @@ static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
         const size_t smem = kcf_any_smem_bytes(hr, wc, c->lut_floats);
         if (smem && hr <= c->any.nmax && wc <= c->any.nmax) {
             int threads, ctas; any_launch_shape(smem, &threads, &ctas);
-            const int rc = kcf_launch_any(mode, L, c->any, smem, threads, ctas, c->d_any_err, c->stream);
+            // windows that run in strips park their cell histograms in a per-CTA scratch area (L2-resident: 18 planes of the cell grid)
+            const size_t scr = kcf_any_scratch_bytes(hr, wc, c->lut_floats);
+            float *scratch = nullptr;
+            const int grid_cap = c->sm_count * ctas;
+            if (scr) { CU(c->d_scratch.ensure(scr * (size_t)grid_cap)); scratch = reinterpret_cast<float *>(c->d_scratch.p); }
+            const int rc = kcf_launch_any(mode, L, c->any, smem, threads, ctas, c->d_any_err, scratch, (long)(scr / sizeof(float)), grid_cap, c->stream);
             if (rc) return fail(MOT_ERR_CUDA, "KCF (any-size kernel) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
             c->launches += 1;
             return 0;
@@ -968,6 +973,28 @@ long mot_debug_state(mot_ctx_t *c, int handle, int which, void *host_out, long m
         return e == cudaSuccess ? (long)sizeof(double) * n : fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
     }
     return fail(MOT_ERR_ARG, "unknown state %d for a Kalman context", which);
+}
+
+// Host-only view of how the any-size kernel would run an hr x wc window (no GPU needed): out[0..15] = ok, strips, total shared-memory
+// bytes, channels per tile, gradient strip width (pixel columns), cell columns per strip, spectral buffer (float2), A / B region floats,
+// scratch bytes per CTA, CTAs per SM, threads per CTA, passes of the length-hr / length-wc transforms, reserved;
+// radices[0..13] = the radices of the two transforms (7 slots each, zero padded).
+int mot_debug_any_plan(int hr, int wc, int *out, int *radices)
+{
+    if (hr < 1 || wc < 1 || !out) return fail(MOT_ERR_ARG, "mot_debug_any_plan: bad argument");
+    const FhogTables &t = fhog_tables();
+    if (!t.ok) return fail(MOT_ERR_TABLES, "%s", t.error.c_str());
+    int lut = 2 * (2 << t.rsqrt_bits) + ((2 * t.bin_nseg + 3) & ~3);
+    if (lut > 8192) lut = 0;
+    const AnyGeo g = any_geo(hr, wc, lut);
+    int threads = 0, ctas = 0;
+    if (g.ok) any_launch_shape((size_t)g.total * 4, &threads, &ctas);
+    AnyPlan pr{}, pc{};
+    any_plan(hr, pr); any_plan(wc, pc);
+    const int v[16] = { g.ok, g.strips, g.total * 4, g.tc, g.xw, g.cs, g.xbuf, g.aF, g.bF, (int)kcf_any_scratch_bytes(hr, wc, lut), ctas, threads, pr.nf, pc.nf, 0, 0 };
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+    if (radices) for (int i = 0; i < 7; ++i) { radices[i] = pr.r[i]; radices[7 + i] = pc.r[i]; }
+    return 0;
 }
 
 long mot_debug_tables(int which, float *out, long max_floats, int *info)

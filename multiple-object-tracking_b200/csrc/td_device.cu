@@ -63,7 +63,7 @@ __device__ __forceinline__ int kcf_list_of(const TddState &st, int rows, int col
     if (k >= 0) return k;
     if (fused_side(rows / KCF_CELL) >= 0 && fused_side(cols / KCF_CELL) >= 0) return -1;      // a fixed-size class that was switched off
     const AnyGeo g = any_geo(rows / KCF_CELL, cols / KCF_CELL, st.lut_floats);
-    if (!g.ok) return -1;
+    if (!g.ok || g.strips || g.S > NB_MAX) return -1;      // strip-mode windows need per-CTA scratch and, beyond NB_MAX bins, their own model storage: host loop only
     const size_t bytes = (size_t)g.total * 4;
     const int b = bytes <= tdd_any_list_bytes(0) ? 0 : bytes <= tdd_any_list_bytes(1) ? 1 : 2;
     return st.any_on[b] ? 9 + b : -1;
@@ -428,6 +428,21 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
     return 0;
 }
 
+/* the same with one bbox_chain_t per stream, the detector's wire format (top/cnntype.h:43-47; filled by tensorRunB, top/td.cpp:204) */
+int mot_tdd_step_chains(mot_tdd_t *t, const mot_bbox_chain_t *const *chains)
+{
+    if (!t || !chains) return mot_fail(MOT_ERR_ARG, "mot_tdd_step_chains: null argument");
+    const int S = t->st.S;
+    std::vector<const mot_bbox_t *> dets(S);
+    std::vector<int> nd(S);
+    for (int s = 0; s < S; ++s) {
+        if (!chains[s]) { dets[s] = nullptr; nd[s] = 0; continue; }
+        if (chains[s]->nbox < 0 || chains[s]->nbox > 128) return mot_fail(MOT_ERR_ARG, "stream %d: chain with %d boxes (0..128)", s, chains[s]->nbox);
+        dets[s] = chains[s]->bbox; nd[s] = chains[s]->nbox;
+    }
+    return mot_tdd_step(t, dets.data(), nd.data());
+}
+
 /* KCF kind: from the next step on, stream s reads frame slot base + s.  The steps are asynchronous, so a slot must not be
  * uploaded again while a step that reads it is still in flight: alternate two bases (2 * n_streams slots), or mot_sync first. */
 int mot_tdd_frame_base(mot_tdd_t *t, int base)
@@ -453,7 +468,7 @@ int mot_tdd_kcf_windows(mot_tdd_t *t, int n, const int *rows, const int *cols)
         for (int q = 0; q < 3; ++q) { if (hr == side[q]) hi = q; if (wc == side[q]) wi = q; }
         if (hi >= 0 && wi >= 0) { keep[3 * hi + wi] = 1; continue; }
         const AnyGeo g = (hr >= 2 && wc >= 2) ? any_geo(hr, wc, t->st.lut_floats) : AnyGeo{};
-        if (hr < 2 || wc < 2 || !g.ok) return mot_fail(MOT_ERR_SHAPE, "window %dx%d px: no fused kernel holds it (2x2 cells up to about 1400 cells)", rows[i], cols[i]);
+        if (hr < 2 || wc < 2 || !g.ok || g.strips || g.S > NB_MAX) return mot_fail(MOT_ERR_SHAPE, "window %dx%d px: no fused kernel holds it (2x2 cells up to about 1400 cells)", rows[i], cols[i]);
         const size_t bytes = (size_t)g.total * 4;
         any_keep[bytes <= tdd_any_list_bytes(0) ? 0 : bytes <= tdd_any_list_bytes(1) ? 1 : 2] = 1;
     }

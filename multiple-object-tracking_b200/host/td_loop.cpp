@@ -180,6 +180,25 @@ int mot_td_step(mot_td_t *td, const uint8_t *host_bgr, int stride_bytes, const m
     return mot_td_step_multi(&td, 1, f, stride_bytes, d, &ndet);
 }
 
+// ---- the detector's wire format ----------------------------------------------------------------------------------
+// The tracking thread receives one bbox_chain_t per frame (top/td.cpp:326-335 reads pdetected->nbox and pdetected->bbox[]); the detector
+// thread fills up to MAX_GPU_BATCH = 4 of them per tensorRunB call (top/td.cpp:178-204) and queues them in order.
+int mot_td_step_chain(mot_td_t *td, const uint8_t *host_bgr, int stride_bytes, const mot_bbox_chain_t *chain)
+{
+    if (!td || !chain || chain->nbox < 0 || chain->nbox > 128) return MOT_ERR_ARG;
+    return mot_td_step(td, host_bgr, stride_bytes, chain->bbox, chain->nbox);
+}
+
+int mot_td_step_chain_batch(mot_td_t *td, int nbatch, const uint8_t *const *host_bgr, int stride_bytes, const mot_bbox_chain_t *const *chains)
+{
+    if (!td || nbatch < 0 || nbatch > 4 || (nbatch && !chains)) return MOT_ERR_ARG;
+    for (int i = 0; i < nbatch; ++i) {                       // consumed in queue order, one frame at a time, like prc_rptr walks the ring
+        const int rc = mot_td_step_chain(td, host_bgr ? host_bgr[i] : nullptr, stride_bytes, chains[i]);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int mot_td_ntracks(mot_td_t *td) { return td ? (int)td->tracks.size() : 0; }
 long mot_td_dropped(mot_td_t *td) { return td ? td->dropped : 0; }
 

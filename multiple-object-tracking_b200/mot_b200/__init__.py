@@ -17,15 +17,24 @@ TRACKER_KALMAN, TRACKER_KCF = 0, 1
 COST_REF_CENTROID, COST_IOU_CLAMPED = 0, 1
 
 BBOX_DTYPE = np.dtype([("l", "<i4"), ("t", "<i4"), ("b", "<i4"), ("r", "<i4"), ("type", "<i4"), ("score", "<f4")])
+CHAIN_DTYPE = np.dtype([("nbox", "<i4"), ("bbox", BBOX_DTYPE, (128,))])        # bbox_chain_t, top/cnntype.h:43-47 (3076 bytes)
+
+
+def make_chain(dets):
+    """A detector-style bbox_chain_t holding `dets` (at most 128 boxes)."""
+    c = np.zeros(1, CHAIN_DTYPE)
+    c["nbox"] = len(dets)
+    c["bbox"][0, :len(dets)] = dets
+    return c
 
 EXPORTS = [
     "mot_ctx_create", "mot_ctx_destroy", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
     "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_yolo_post", "mot_tracker_new_batch", "mot_tracker_delete_batch", "mot_tracker_spawnable",
     "mot_predict_batch", "mot_update_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_rgb2gray_host", "mot_resize_gray_host", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
-    "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_multi", "mot_td_ntracks", "mot_td_dropped", "mot_td_get", "mot_td_last", "mot_td_overlay",
-    "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_read", "mot_tdd_kcf_windows", "mot_tdd_dropped", "mot_tdd_frame_base",
-    "mot_debug_enable_dumps", "mot_debug_fetch", "mot_debug_state", "mot_debug_tables",
+    "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_chain", "mot_td_step_chain_batch", "mot_td_step_multi", "mot_td_ntracks", "mot_td_dropped", "mot_td_get", "mot_td_last", "mot_td_overlay",
+    "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_step_chains", "mot_tdd_read", "mot_tdd_kcf_windows", "mot_tdd_dropped", "mot_tdd_frame_base",
+    "mot_debug_enable_dumps", "mot_debug_fetch", "mot_debug_state", "mot_debug_tables", "mot_debug_any_plan",
 ]
 
 
@@ -87,6 +96,9 @@ def lib():
             "mot_td_create": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int],
             "mot_td_destroy": [C.c_void_p],
             "mot_td_step": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int],
+            "mot_td_step_chain": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p],
+            "mot_td_step_chain_batch": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p],
+            "mot_tdd_step_chains": [C.c_void_p, C.c_void_p],
             "mot_td_step_multi": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
             "mot_td_ntracks": [C.c_void_p],
             "mot_td_get": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -293,6 +305,10 @@ class DeviceLoop:
         nd = np.array([len(d) for d in dl], np.int32)
         _chk(lib().mot_tdd_step(self.h, arr, _p(nd)))
 
+    def step_chains(self, chains):
+        arr = (C.c_void_p * self.n)(*[c.ctypes.data if c is not None else None for c in chains])
+        _chk(lib().mot_tdd_step_chains(self.h, arr))
+
     def step_dev(self, d_dets, d_ndet):
         _chk(lib().mot_tdd_step_dev(self.h, C.c_void_p(d_dets), C.c_void_p(d_ndet)))
 
@@ -338,6 +354,15 @@ class TdLoop:
         else:
             assert frame.dtype == np.uint8 and frame.flags.c_contiguous
             _chk(lib().mot_td_step(self.h, _p(frame), frame.strides[0], _p(d), len(d)))
+
+    def step_chain(self, frame, chain):
+        _chk(lib().mot_td_step_chain(self.h, _p(frame) if frame is not None else None, frame.strides[0] if frame is not None else 0, _p(chain)))
+
+    def step_chain_batch(self, frames, chains):
+        n = len(chains)
+        arr_f = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        arr_c = (C.c_void_p * n)(*[c.ctypes.data for c in chains])
+        _chk(lib().mot_td_step_chain_batch(self.h, n, arr_f, frames[0].strides[0], arr_c))
 
     def tracks(self):
         n = lib().mot_td_ntracks(self.h)

@@ -19,7 +19,7 @@ def one_box(l, t, rows, cols, typ=1):
 
 
 @pytest.mark.parametrize("rows,cols", [(128, 128), (64, 64), (64, 128), (130, 67), (35, 34), (35, 66), (66, 33), (129, 34), (34, 131),
-                                       (120, 160), (100, 60), (37, 53), (150, 91), (8, 8)])   # first row: every fused class (cell sides 8/16/32 in all nine combinations, 64x128 px = 16x32 cells included); second row: any-size path
+                                       (120, 160), (100, 60), (37, 53), (150, 91), (8, 8), (300, 148), (200, 203), (90, 330)])   # first row: every fixed-size fused class (cell sides 8/16/32 in all nine combinations); second row: the any-size kernel -- mixed radices, primes (37 cells), the smallest window, and windows that run in strips (75x37, 50x50, 22x82 cells)
 def test_stagewise_vs_oracle(oracle, rows, cols):
     require_gpu()
     M = mot()
@@ -203,7 +203,7 @@ def test_config1_mixed_radix_window_sequence(oracle):
 
 
 @pytest.mark.parametrize("rows,cols", [(128, 128), (64, 64), (64, 128), (130, 67), (35, 34), (35, 66), (66, 33), (129, 34), (34, 131),
-                                       (120, 160), (100, 60), (37, 53)])
+                                       (120, 160), (100, 60), (37, 53), (300, 148), (200, 203)])
 def test_model_state_with_dumps_off(oracle, rows, cols):
     """The PRODUCTION instantiation (stage dumps compiled out / never enabled): xf_md and alpha read back with mot_debug_state
     after six predict + update rounds against the compiled reference's model -- all nine fused classes and any-size windows."""

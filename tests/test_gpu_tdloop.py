@@ -228,3 +228,37 @@ def test_device_resident_kcf_loop_with_detections_of_any_size(oracle):
     for r in refs:
         r.close()
     ctx.close()
+
+
+def test_detector_wire_format_gives_the_same_trace(oracle):
+    """detections arrive as bbox_chain_t (top/cnntype.h:43-47), in batches of up to four frames as tensorRunB delivers
+    them (top/td.cpp:178-204).  Feeding chains -- one by one, batched, and to the device-resident loop -- gives exactly the track tables
+    that flat arrays give, which are the oracle's."""
+    require_gpu()
+    M = mot()
+    assert M.CHAIN_DTYPE.itemsize == 4 + 128 * 24
+    W, H = 1280, 720
+    sc = Scene(41, W, H, 7, tsize=40, win=64)
+    frames, dets = [], []
+    for f in range(9):
+        sc.step(); frames.append(sc.render()); dets.append(sc.windows(jitter=1))
+    ctx = M.Context(W, H, max_tracks=4 * 32, n_frame_slots=4, kind=M.TRACKER_KCF)
+    td_flat, td_chain, td_batch = ctx.td(0, cap=32), ctx.td(1, cap=32), ctx.td(2, cap=32)
+    loop_ctx = M.Context(W, H, max_tracks=32, n_frame_slots=1, kind=M.TRACKER_KCF)
+    loop = M.DeviceLoop(loop_ctx, 1, cap=32, max_det=128, cost_mode=0)
+    ref = oracle.td_new("kcf", W, H, 32, 0)
+    chains = [M.make_chain(d) for d in dets]
+    for f in range(9):
+        td_flat.step(frames[f], dets[f]); td_chain.step_chain(frames[f], chains[f]); ref.step(frames[f], dets[f])
+        loop_ctx.upload(0, frames[f]); loop.step_chains([chains[f]]); loop_ctx.sync()
+    for f0 in (0, 4, 8):                                      # batches of 4, 4 and 1 frames
+        td_batch.step_chain_batch(frames[f0:f0 + 4], chains[f0:f0 + 4])
+    want = ref.tracks()
+    for got in (td_flat.tracks(), td_chain.tracks(), td_batch.tracks(), loop.tracks(0)):
+        for k in got:
+            assert np.array_equal(got[k], want[k]), k
+    assert len(want["tid"]) >= 5
+    loop.close(); loop_ctx.close()
+    for t in (td_flat, td_chain, td_batch):
+        t.close()
+    ref.close(); ctx.close()
