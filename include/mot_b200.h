@@ -117,6 +117,11 @@ int mot_predict_batch(mot_ctx_t *ctx, int n, const int *handles, const int *fram
  * crop rectangle and the measurement / new position.  HOST arrays; asynchronous on the context stream. */
 int mot_update_batch(mot_ctx_t *ctx, int n, const int *handles, const int *frame_slots, const mot_bbox_t *boxes);
 
+/* tracker_predict (+ clamp) followed at once by tracker_update with the predicted box -- the reference's treatment of a track
+ * without a detection (top/td.cpp:344-384 then :550-582), and the whole per-frame work of single-target tracking (BASELINE config 1) --
+ * as ONE call with one synchronisation.  boxes[i] in = crop rectangle, out = predicted (clamped) box.  HOST arrays. */
+int mot_track_batch(mot_ctx_t *ctx, int n, const int *handles, const int *frame_slots, mot_bbox_t *boxes, int clamp);
+
 /* Same two calls with every array already resident on the DEVICE (no copies, no sync): the steady-state path. */
 int mot_predict_batch_dev(mot_ctx_t *ctx, int n, const int *d_handles, const int *d_frame_slots, mot_bbox_t *d_boxes, int clamp);
 int mot_update_batch_dev(mot_ctx_t *ctx, int n, const int *d_handles, const int *d_frame_slots, const mot_bbox_t *d_boxes);

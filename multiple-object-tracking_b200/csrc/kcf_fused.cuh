@@ -49,7 +49,7 @@ template <int HR, int WC> struct Geo {
     static constexpr int RAW_FLOATS = RMAX * RAW_PITCH / 4;
     static constexpr int F_MIN = 31 * NB;
     static constexpr int F_A = (CMAX + 2) * GS > PADM ? (CMAX + 2) * GS : PADM;
-    static constexpr int F_FLOATS = ((F_MIN > F_A ? F_MIN : F_A) + 3) & ~3;
+    static constexpr int F_FLOATS = ((F_MIN > F_A ? F_MIN : F_A) + 31) & ~31;       // the regions behind it stay 128-byte aligned (2-D TMA destination)
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
     static constexpr int MQ_FLOATS = 4 * KCF_THREADS;      // P5: two model values (float2) per thread in flight through cp.async
@@ -64,7 +64,7 @@ template <int HR, int WC> struct Geo {
 // R1 region: cell histograms later, but first the SSE tables (lut_floats) and the staged frame rows (raw_floats)
 __host__ __device__ inline int r1_region_floats(int r1_min, int lut_floats, int raw_floats)
 {
-    const int early = ((lut_floats + 3) & ~3) + raw_floats;
+    const int early = ((lut_floats + 31) & ~31) + raw_floats;
     const int v = r1_min > early ? r1_min : early;
     return (v + 3) & ~3;
 }
@@ -80,7 +80,7 @@ template <int HR, int WC> size_t smem_bytes(int lut_floats)
 struct JobDesc {
     mot_bbox_t box, pos;              // p.boxes[job]; meta->pos
     const uint8_t *frame;             // p.frame_ptr[p.frames[job]] (null with pre-cropped gray input)
-    int slot, rows, cols, size_class, first_update;
+    int slot, rows, cols, size_class, first_update, fslot;
     float scale_horiz, scale_vert;
     int box_idx;                      // where the job's box lives in p.boxes (job index, or p.box_index[job])
 };
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     using G = Geo<HR, WC>;
     constexpr int NT = KCF_THREADS, NB = G::NB, HK = G::HK, SK = G::SK, S = G::S, GS = G::GS, RS = G::RS;
     constexpr int H0 = G::H0, W0 = G::W0;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float *const F = smem;
     float *const R1 = F + G::F_FLOATS;
     float2 *const MQ = reinterpret_cast<float2 *>(R1 + r1_region_floats(G::R1_MIN, lut_floats, G::RAW_FLOATS));
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     __syncthreads();
     const bool lut_smem = lut_floats > 0;
     const int n_rs = 2 * (2 << p.tab.rsqrt_bits), n_bn = (2 * p.tab.bin_nseg + 3) & ~3;      // floats of the fused {rsqrt, rcp} table; bin entries
-    unsigned char *const raw = reinterpret_cast<unsigned char *>(R1 + ((lut_floats + 3) & ~3));
+    unsigned char *const raw = reinterpret_cast<unsigned char *>(R1 + ((lut_floats + 31) & ~31));
     const int Wm = p.frame_w - 1, Hm = p.frame_h - 1;
 
     // Fetch the frame rows of job `jb`'s crop into the staging area with the bulk-copy engine (cp.async.bulk on mbar2).
@@ -124,11 +124,17 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         const KcfMeta *m = p.meta + sl;
         const int bi = p.box_index ? p.box_index[jb] : jb;
         d->box = p.boxes[bi]; d->box_idx = bi;
-        d->frame = (p.gray == nullptr) ? p.frame_ptr[p.frames[jb]] : nullptr;
+        d->fslot = (p.gray == nullptr) ? p.frames[jb] : 0;
+        d->frame = (p.gray == nullptr) ? p.frame_ptr[d->fslot] : nullptr;
         d->slot = sl; d->rows = m->rows; d->cols = m->cols; d->size_class = m->size_class; d->first_update = m->first_update;
         d->pos = m->pos; d->scale_horiz = m->scale_horiz; d->scale_vert = m->scale_vert;
     };
-    auto issue_roi = [&](const mot_bbox_t bx, const uint8_t *frame_of_job) {
+    // A crop that lies inside the frame vertically is fetched by ONE 2-D TMA load through the frame's tensor map (box = RAW_PITCH
+    // bytes x RMAX rows, rows past the crop are simply not used, columns past the frame row are zero-filled and never read); crops
+    // that reach over the top / bottom edge need the edge row replicated and take the row-by-row path.
+    const bool tma_ok = p.frame_tmaps != nullptr && (smem_u32(raw) & 127u) == 0;
+    constexpr int TMAP_ROWCLASS = HR == 8 ? 0 : HR == 16 ? 1 : 2;
+    auto issue_roi = [&](const mot_bbox_t bx, const uint8_t *frame_of_job, int fslot) {
         const int lane = tid & 31;
         int l = bx.l, t = bx.t, r = bx.r, b = bx.b;
         if (t > b) { const int q = t; t = b; b = q; }
@@ -138,9 +144,13 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         const bool fetch = (p.gray == nullptr) && rows_s <= G::RMAX && cols_s <= G::CMAX && (((uintptr_t)frame | (uintptr_t)p.frame_stride) & 15) == 0;
         const int x_lo = clampi(l, 0, Wm), x_hi = clampi(l + cols_s - 1, 0, Wm);
         const int a0 = (x_lo * 3) & ~15, a1 = ((x_hi + 1) * 3 + 15) & ~15;
-        if (lane == 0) mbar_expect_tx(&mbar2, fetch ? (uint32_t)rows_s * (uint32_t)(a1 - a0) : 0u);
+        const bool tma = fetch && tma_ok && t >= 0 && t + rows_s - 1 <= Hm;
+        if (lane == 0) {
+            mbar_expect_tx(&mbar2, tma ? (uint32_t)(G::RMAX * G::RAW_PITCH) : fetch ? (uint32_t)rows_s * (uint32_t)(a1 - a0) : 0u);
+            if (tma) tma_load_2d(raw, reinterpret_cast<const char *>(p.frame_tmaps) + ((long)fslot * 3 + TMAP_ROWCLASS) * 128, a0 >> 2, t, &mbar2);
+        }
         __syncwarp();
-        if (fetch)
+        if (fetch && !tma)
             for (int y = lane; y < rows_s; y += 32)
                 bulk_g2s(raw + y * G::RAW_PITCH, frame + (long)clampi(t + y, 0, Hm) * p.frame_stride + a0, a1 - a0, &mbar2);
     };
@@ -236,7 +246,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             if ((int)(blockIdx.x + gridDim.x) < n_jobs) fetch_desc(blockIdx.x + gridDim.x, &s_desc[1]);
         }
         __syncwarp();
-        issue_roi(s_desc[0].box, s_desc[0].frame);
+        issue_roi(s_desc[0].box, s_desc[0].frame, s_desc[0].fslot);
     }
     int it = 0;
     for (int job = blockIdx.x; job < n_jobs; job += gridDim.x, phase ^= 1u, ++it) {
@@ -612,7 +622,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // The histograms are consumed: the staging area is free again -> start streaming the next job's crop underneath P5..P7
     if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < n_jobs) {
         const JobDesc &nd = s_desc[(it + 1) & 3];
-        issue_roi(nd.box, nd.frame);
+        issue_roi(nd.box, nd.frame, nd.fslot);
         if ((tid & 31) == 0 && job + 2 * (int)gridDim.x < n_jobs) fetch_desc(job + 2 * gridDim.x, &s_desc[(it + 2) & 3]);
     }
 

@@ -6,6 +6,8 @@
 #include "overlay.h"
 #include "yolo_post.h"
 
+#include <cuda.h>            // CUtensorMap and its enums (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -209,9 +211,47 @@ static int wait_frames(mot_ctx_t *c, int n, const int *frame_slots)
     return 0;
 }
 
+// Tensor maps of the frame slots: every frame as a 2-D array of 32-bit words (rows of frame_stride bytes), box = 108 words (432 bytes,
+// the staged row pitch of kcf_fused.cuh) x 35 / 67 / 131 rows (the tallest crop of an 8 / 16 / 32-cell window).  One
+// cp.async.bulk.tensor.2d then fetches a whole crop.  Any failure just leaves the kernels on their row-by-row bulk copies.
+static void build_frame_tmaps(mot_ctx_t *c)
+{
+    c->tmaps_ok = false;
+    if (c->kind != MOT_TRACKER_KCF || (c->frame_stride & 15) || c->frame_stride < 432) return;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *fp = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) encode = (encode_fn)fp;
+    }
+    if (!encode) return;
+    static const cuuint32_t box_rows[3] = { 35, 67, 131 };
+    std::vector<CUtensorMap> maps((size_t)c->n_frames * 3);
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    for (int s = 0; s < c->n_frames; ++s)
+        for (int k = 0; k < 3; ++k) {
+            CUtensorMap &m = maps[(size_t)s * 3 + k];
+            memset(&m, 0, sizeof(m));
+            if (!c->frame_ptr_h[s] || ((uintptr_t)c->frame_ptr_h[s] & 15)) { if (c->frame_ptr_h[s]) return; else continue; }
+            const cuuint64_t dims[2] = { (cuuint64_t)c->frame_stride / 4, (cuuint64_t)c->H };
+            const cuuint64_t strides[1] = { (cuuint64_t)c->frame_stride };
+            const cuuint32_t box[2] = { 108, box_rows[k] }, estr[2] = { 1, 1 };
+            if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(c->frame_ptr_h[s]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
+        }
+    if (!c->d_frame_tmaps && cudaMalloc(&c->d_frame_tmaps, sizeof(CUtensorMap) * maps.size()) != cudaSuccess) { c->d_frame_tmaps = nullptr; return; }
+    if (cudaMemcpyAsync(c->d_frame_tmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return;
+    c->tmaps_ok = getenv("MOT_NO_TMA2D") == nullptr;
+}
+
 static int sync_frame_ptrs(mot_ctx_t *c)
 {
     if (!c->frame_ptr_dirty) return 0;
+    build_frame_tmaps(c);
     CU(cudaMemcpyAsync(c->d_frame_ptr, c->frame_ptr_h.data(), sizeof(void *) * c->n_frames, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));      // the host vector may change right after
     c->frame_ptr_dirty = false;
@@ -375,7 +415,7 @@ void mot_ctx_destroy(mot_ctx_t *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto p : c->frame_owned) if (p) cudaFree(p);
-    cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
+    cudaFree(c->d_frame_tmaps); cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
     cudaFree(c->d_tab_rsqrt); cudaFree(c->d_tab_rcp); cudaFree(c->d_tab_rsrc); cudaFree(c->d_tab_bin); cudaFree(c->d_tab_bin2); cudaFree(c->kal.x); cudaFree(c->kal.P);
     if (c->h_any_err) cudaFreeHost(c->h_any_err);
     cudaFree((void *)c->any.hann); cudaFree((void *)c->any.tw); cudaFree((void *)c->any.lab); cudaFree((void *)c->any.plan);
@@ -605,6 +645,7 @@ static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, c
 {
     L = KcfLaunch{};
     L.n_jobs = n; L.slots = d_slots; L.frames = d_frames; L.boxes = d_boxes;
+    L.frame_tmaps = c->tmaps_ok ? c->d_frame_tmaps : nullptr;
     L.frame_ptr = c->d_frame_ptr; L.frame_w = c->W; L.frame_h = c->H; L.frame_stride = c->frame_stride;
     L.gray = nullptr; L.gray_stride = 0;
     L.meta = c->d_meta; L.model = c->d_model; L.model_stride = c->model_stride; L.alpha = c->d_alpha; L.alpha_stride = c->alpha_stride;
@@ -690,6 +731,47 @@ static int kcf_batch_host(mot_ctx_t *c, int mode, int n, const int *handles, con
     return 0;
 }
 
+// predict (+ clamp) followed at once by update with the predicted box -- what the reference does for a track without a detection
+// (top/td.cpp:344-384 then :550-582) -- as ONE call: one staging kernel, predict and update launches back to back per window size,
+// one synchronisation.  Host arrays; boxes in = crop rectangles, out = predicted (clamped) boxes.
+static int kcf_track_host(mot_ctx_t *c, int n, const int *handles, const int *frame_slots, mot_bbox_t *boxes, int clamp)
+{
+    if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
+    if (n == 0) return 0;
+    if (!handles || !frame_slots || !boxes) return fail(MOT_ERR_ARG, "null array");
+    if (c->dumps) return fail(MOT_ERR_ARG, "stage dumps are per call of mot_predict_batch / mot_update_batch");
+    CU(cudaSetDevice(c->device));
+    { const int rc = sync_frame_ptrs(c); if (rc) return rc; }
+    { const int rc = wait_frames(c, n, frame_slots); if (rc) return rc; }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) {
+        const int s = handles[i];
+        if (s < 0 || s >= c->max_tracks || !c->used[s]) return fail(MOT_ERR_ARG, "invalid handle %d", s);
+        if (frame_slots[i] < 0 || frame_slots[i] >= c->n_frames || !c->frame_ptr_h[frame_slots[i]]) return fail(MOT_ERR_ARG, "frame slot %d is empty", frame_slots[i]);
+        order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->meta_h[handles[a]].size_class < c->meta_h[handles[b]].size_class; });
+    CU(c->h_slots.ensure(n)); CU(c->h_frames.ensure(n)); CU(c->h_boxes.ensure(n));
+    CU(c->d_slots.ensure(n)); CU(c->d_frames.ensure(n)); CU(c->d_boxes.ensure(n));
+    for (int i = 0; i < n; ++i) { c->h_slots.p[i] = handles[order[i]]; c->h_frames.p[i] = frame_slots[order[i]]; c->h_boxes.p[i] = boxes[order[i]]; }
+    stage_in_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_slots.p, c->h_slots.p, c->d_frames.p, c->h_frames.p, c->d_boxes.p, c->h_boxes.p, n);
+    CU(cudaGetLastError());
+    c->launches += 1;
+    for (int mode = KCF_MODE_PREDICT; mode <= KCF_MODE_UPDATE; ++mode)
+        for (int a = 0; a < n;) {
+            const int cls = c->meta_h[c->h_slots.p[a]].size_class;
+            int b = a; while (b < n && c->meta_h[c->h_slots.p[b]].size_class == cls) ++b;
+            KcfLaunch L; fill_launch(c, L, b - a, c->d_slots.p + a, c->d_frames.p + a, c->d_boxes.p + a, mode == KCF_MODE_PREDICT ? clamp : 0);
+            const int rc = kcf_run(c, mode, c->classes[cls].hr, c->classes[cls].wc, L); if (rc) return rc;
+            a = b;
+        }
+    CU(cudaMemcpyAsync(c->h_boxes.p, c->d_boxes.p, sizeof(mot_bbox_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) boxes[order[i]] = c->h_boxes.p[i];
+    if (c->h_any_err && *c->h_any_err) { *c->h_any_err = 0; return fail(MOT_ERR_SHAPE, "a KCF job did not fit the shared memory of its launch and was skipped (internal sizing error)"); }
+    return 0;
+}
+
 static int kcf_batch_dev(mot_ctx_t *c, int mode, int n, const int *d_handles, const int *d_frame_slots, mot_bbox_t *d_boxes, int clamp)
 {
     if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
@@ -731,6 +813,16 @@ int mot_predict_batch(mot_ctx_t *c, int n, const int *handles, const int *frame_
     if (!c || n < 0) return fail(MOT_ERR_ARG, "mot_predict_batch: bad argument");
     if (c->kind == MOT_TRACKER_KCF) return kcf_batch_host(c, KCF_MODE_PREDICT, n, handles, frame_slots, boxes, clamp, true);
     return kalman_batch_host(c, KCF_MODE_PREDICT, n, handles, boxes, clamp);
+}
+
+int mot_track_batch(mot_ctx_t *c, int n, const int *handles, const int *frame_slots, mot_bbox_t *boxes, int clamp)
+{
+    if (!c || n < 0) return fail(MOT_ERR_ARG, "mot_track_batch: bad argument");
+    if (c->kind == MOT_TRACKER_KCF) return kcf_track_host(c, n, handles, frame_slots, boxes, clamp);
+    // Kalman: the update of an unassigned track takes its own predicted box as the measurement (top/td.cpp:581)
+    int rc = kalman_batch_host(c, KCF_MODE_PREDICT, n, handles, boxes, clamp);
+    if (!rc) rc = kalman_batch_host(c, KCF_MODE_UPDATE, n, handles, boxes, 0);
+    return rc;
 }
 
 int mot_update_batch(mot_ctx_t *c, int n, const int *handles, const int *frame_slots, const mot_bbox_t *boxes)

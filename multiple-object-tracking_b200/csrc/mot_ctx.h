@@ -65,6 +65,8 @@ struct mot_ctx_s {
     std::vector<uint8_t *> frame_owned;
     std::vector<const uint8_t *> frame_ptr_h;
     const uint8_t **d_frame_ptr = nullptr;
+    void *d_frame_tmaps = nullptr;        // [n_frames][3] tensor maps of the frame slots (2-D TMA crop loads of the fixed-size fused kernels)
+    bool tmaps_ok = false;
     bool frame_ptr_dirty = true;
     int frame_stride = 0;
     // track slots

@@ -67,6 +67,8 @@ struct KcfLaunch {
     const int *frames;                // [n] frame slot of each job (ignored when gray != null)
     mot_bbox_t *boxes;                // [n] predict: in = crop box, out = predicted box; update: in = new position / crop box
     const uint8_t *const *frame_ptr;  // [n_frame_slots] device base pointers of BGR u8 frames
+    const void *frame_tmaps;          // optional: [n_frame_slots][3] tensor maps (128 bytes each) of the frames as 2-D arrays of 32-bit words,
+                                      // box = 108 words x {35, 67, 131} rows: the staged crop of a fixed-size fused kernel in ONE TMA load
     int frame_w, frame_h, frame_stride;
     const float *gray;                // optional: [n] pre-cropped gray patches (rows*cols col-major, stride gray_stride floats)
     long gray_stride;

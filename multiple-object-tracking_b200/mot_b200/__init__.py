@@ -30,7 +30,7 @@ def make_chain(dets):
 EXPORTS = [
     "mot_ctx_create", "mot_ctx_destroy", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
     "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_yolo_post", "mot_tracker_new_batch", "mot_tracker_delete_batch", "mot_tracker_spawnable",
-    "mot_predict_batch", "mot_update_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
+    "mot_predict_batch", "mot_update_batch", "mot_track_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_rgb2gray_host", "mot_resize_gray_host", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
     "mot_td_create", "mot_td_destroy", "mot_td_step", "mot_td_step_chain", "mot_td_step_chain_batch", "mot_td_step_multi", "mot_td_ntracks", "mot_td_dropped", "mot_td_get", "mot_td_last", "mot_td_overlay",
     "mot_tdd_create", "mot_tdd_destroy", "mot_tdd_step_dev", "mot_tdd_step", "mot_tdd_step_chains", "mot_tdd_read", "mot_tdd_kcf_windows", "mot_tdd_dropped", "mot_tdd_frame_base",
@@ -78,6 +78,7 @@ def lib():
             "mot_assign_batch": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p],
             "mot_predict_batch": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
             "mot_update_batch": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+            "mot_track_batch": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
             "mot_predict_batch_dev": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
             "mot_update_batch_dev": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
             "mot_frame_upload": [C.c_void_p, C.c_int, C.c_void_p, C.c_int],
@@ -211,6 +212,12 @@ class Context:
     def predict(self, handles, frame_slots, boxes, clamp=0):
         hs = _i32(handles); fs = None if frame_slots is None else _i32(frame_slots); b = _boxes(boxes).copy()
         _chk(lib().mot_predict_batch(self.h, len(hs), _p(hs), _p(fs), _p(b), clamp))
+        return b
+
+    def track(self, handles, frame_slots, boxes, clamp=1):
+        """predict (+ clamp) and update with the predicted box in one call (mot_track_batch)."""
+        hs = _i32(handles); fs = None if frame_slots is None else _i32(frame_slots); b = _boxes(boxes).copy()
+        _chk(lib().mot_track_batch(self.h, len(hs), _p(hs), _p(fs), _p(b), clamp))
         return b
 
     def update(self, handles, frame_slots, boxes):

@@ -231,3 +231,35 @@ def test_model_state_with_dumps_off(oracle, rows, cols):
         assert rel_err(ctx.state(h[0], "alpha"), oracle.kcf_get(oh, "alpha")) < 5e-5, step
         assert rel_err(ctx.state(h[0], "xf_md").reshape(31, S, 2), oracle.kcf_get(oh, "xf_md").reshape(31, S, 2)) < 5e-6, step
     oracle.kcf_delete(oh); ctx.close()
+
+
+def test_track_call_equals_predict_then_update(oracle):
+    """mot_track_batch = predict (+ clamp) then update with the predicted box, in one call: same boxes and same model as the two calls,
+    over tracks of different window sizes (fixed-size and any-size kernels in one batch)."""
+    require_gpu()
+    M = mot()
+    W, H = 1280, 720
+    sc = Scene(55, W, H, 8, tsize=40, win=64)
+    sizes = [(128, 128), (64, 64), (100, 60), (51, 77), (120, 160), (64, 128)]
+    b = boxes_array(len(sizes))
+    for i, (r, c) in enumerate(sizes):
+        b[i] = one_box(60 + 190 * i, 120 + 40 * (i % 3), r, c, typ=i % 3)[0]
+    ca = M.Context(W, H, max_tracks=16, n_frame_slots=1, kind=M.TRACKER_KCF)
+    cb = M.Context(W, H, max_tracks=16, n_frame_slots=1, kind=M.TRACKER_KCF)
+    frame = sc.render()
+    fs = np.zeros(len(sizes), np.int32)
+    ha, hb = None, None
+    for ctx in (ca, cb):
+        ctx.upload(0, frame)
+    ha = ca.new(b); hb = cb.new(b)
+    ca.update(ha, fs, b); cb.update(hb, fs, b)
+    ba, bb = b.copy(), b.copy()
+    for step in range(5):
+        sc.step(); frame = sc.render()
+        ca.upload(0, frame); cb.upload(0, frame)
+        ba = ca.predict(ha, fs, ba, clamp=1); ca.update(ha, fs, ba)
+        bb = cb.track(hb, fs, bb, clamp=1)
+        assert ba.tobytes() == bb.tobytes(), step
+    for i in range(len(sizes)):
+        assert np.array_equal(ca.state(ha[i], "xf_md"), cb.state(hb[i], "xf_md")) and np.array_equal(ca.state(ha[i], "alpha"), cb.state(hb[i], "alpha")), i
+    ca.close(); cb.close()
