@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-phase and per-line breakdown of an `ncu --set full --import-source on` capture of the any-size kernel (csrc/kcf_any.cu).
 
-usage: python profiles/any_profile.py REPORT.ncu-rep MODE(0=predict,1=update) [TOP_LINES]      (same build as the report)
+usage: python profiles/any_profile.py REPORT.ncu-rep MODE(0=predict,1=update) [TOP_LINES [NTMAX(512|1024) [STRIPS(0|1)]]]      (same build as the report)
 """
 import collections, csv, os, re, subprocess, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -35,7 +35,8 @@ def main():
         if cur is not None and shdr and len(r) == len(shdr):
             cur.append(dict(zip(shdr, r)))
     ntmax = int(sys.argv[4]) if len(sys.argv) > 4 else 512
-    insts = parse_disasm(dis, "kcf_any_kernelILi%dELb0ELi%dE" % (mode, ntmax))
+    strips = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    insts = parse_disasm(dis, "kcf_any_kernelILi%dELb0ELi%dELb%dE" % (mode, ntmax, strips))
     sect = next(s for k, s in sects if len(s) == len(insts))
 
     def phase_of(line):
