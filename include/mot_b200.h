@@ -66,6 +66,22 @@ int mot_ctx_kind(mot_ctx_t *ctx);
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 long mot_launch_count(mot_ctx_t *ctx);
 
+/* ---- north-star extensions of the correlation filter -------------------------------------------------------------
+ * The reference's filter is the LINEAR-kernel DCF with an integer peak, no padding and a fixed label sigma (trackers/kcf.cpp:269-304,
+ * 397-428, 205); that is the default here and the only mode with a reference oracle.  These options add what the reference lacks:
+ * the Gaussian kernel correlation of KCF (Henriques et al.), a parabolic sub-pixel refinement of the response peak, a tracking window
+ * larger than the target box (padding), and a label width that follows the target size.  Parity UNPINNED by the reference: validated
+ * against the NumPy restatement tests/kcf_ext_numpy.py.  Set before the first tracker exists; every window then runs in the fused
+ * any-size kernel (up to 1152 spectrum bins).  All zero = reference behaviour. */
+typedef struct mot_kcf_options_s {
+    int gaussian_kernel;          /* 1: k = exp(-max(0, |x|^2 + |z|^2 - 2 x.z) / (sigma^2 numel)), alpha complex */
+    float kernel_sigma;           /* its bandwidth (KCF on HOG: 0.5) */
+    int subpixel_peak;            /* 1: refine the peak by a parabola through its circular neighbours; the box moves by 4 (peak + delta) scale */
+    float padding;                /* window = target box x padding about its centre (0 or 1: none; north-star: 2.5); boxes in/out stay TARGET boxes */
+    float output_sigma_factor;    /* label sigma = sqrt(target w x h) x factor / cell (0: the reference's fixed 0.7289 cells; KCF: 0.1) */
+} mot_kcf_options_t;
+int mot_ctx_set_kcf_options(mot_ctx_t *ctx, const mot_kcf_options_t *opt);
+
 /* ---- frames (replaces the cv::Mat the tracking thread pops, top/td.cpp:330-331) --------------------------- */
 
 /* Copy a host BGR u8 frame (rows of stride_bytes) into frame slot `slot` (async on the context stream). */
@@ -217,7 +233,8 @@ int mot_tdd_read(mot_tdd_t *tdd, int stream, uint32_t *tid, mot_bbox_t *boxes, i
  *         9 kf | 10 peak(int x2) | 11 margin(float x2).  Enable before a predict/update of ONE track, then fetch. */
 int mot_debug_enable_dumps(mot_ctx_t *ctx, int enable);
 long mot_debug_fetch(mot_ctx_t *ctx, int stage, void *host_out, long max_bytes);
-/* Raw per-slot state: which = 0 xf_md (31*S float pairs) | 1 alpha (S floats) | 2 Kalman x[6] | 3 Kalman P[36] col-major. */
+/* Raw per-slot state: which = 0 xf_md (31*S float pairs) | 1 alpha (S floats) | 2 Kalman x[6] | 3 Kalman P[36] col-major |
+ * 4 extension: sub-cell refinement {vertical, horizontal} of the last predicted peak | 5 extension: Im(alpha) (S floats). */
 long mot_debug_state(mot_ctx_t *ctx, int handle, int which, void *host_out, long max_bytes);
 /* Host-harvested SSE tables (no GPU needed): which = 0 rsqrt | 1 rcp | 2 acos(20020) | 3 fused {rsqrt, rcp(rsqrt)/16} pairs |
  * 4 orientation-bin step table (u32 bits) | 5 the same with the wrap folded in (u32 bits) | 6 {saturation threshold bits, rcp(1e10f)};

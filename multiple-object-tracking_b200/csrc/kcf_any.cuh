@@ -1,4 +1,5 @@
-// kcf_any.cuh -- geometry of the fused any-size KCF kernel (kcf_any.cu), shared with the host layer that sizes its launches.
+// kcf_any.cuh -- geometry of the fused any-size KCF kernel (kcf_any_kernel.cuh; instantiated in kcf_any_inst.cu, launched by kcf_any.cu),
+// shared with the host layer that sizes its launches.
 #pragma once
 #include "mot_internal.h"
 
@@ -21,7 +22,7 @@ struct AnyGeo {
     int raw_pitch;          // bytes per staged frame row
     int lutp;               // floats reserved for the SSE tables
     int aF, bF;             // region sizes
-    int oB, oN, oE, oACC, oTWR, oTWC, oWY, oWX, oRED, total;   // offsets / total (floats)
+    int oB, oN, oE, oACC, oTWR, oTWC, oWY, oWX, oRED, oLAB, total;   // offsets / total (floats)
     int ok;                 // fits the budget
     // Windows whose (M | bin) map and cell histograms do not fit one CTA's shared memory together run in STRIPS of `cs` cell columns:
     // frame rows, gray, (M | bin) and the histograms of one strip at a time in shared memory, the finished histograms parked in a
@@ -61,6 +62,7 @@ __host__ __device__ inline AnyGeo any_geo(int hr, int wc, int lut_floats)
     const int cWY = o;  o += (hr + 3) & ~3;
     const int cWX = o;  o += (wc + 3) & ~3;
     const int cRED = o; o += 64;
+    const int cLAB = o; o += 4 * (g.sk + wc);               // 1-D label spectra of a per-track label sigma (double2), extensions only
     const int cF = o;
     g.ok = 0; g.xw = 0; g.bF = 0; g.aF = 0; g.ps = 0; g.pc = 0; g.padm = 0;
     // Two choices, most comfortable first: the sub-column pitch of the (M | bin) layout = 8 (mod 16), which makes the gradient phase's
@@ -105,7 +107,7 @@ __host__ __device__ inline AnyGeo any_geo(int hr, int wc, int lut_floats)
     g.xbuf = any_xbuf(hr, wc, g.jp, g.sk, g.tc);
     g.oB = g.aF;
     const int c0 = g.aF + g.bF;
-    g.oN = c0 + cN; g.oE = c0 + cE; g.oACC = c0 + cACC; g.oTWR = c0 + cTWR; g.oTWC = c0 + cTWC; g.oWY = c0 + cWY; g.oWX = c0 + cWX; g.oRED = c0 + cRED;
+    g.oN = c0 + cN; g.oE = c0 + cE; g.oACC = c0 + cACC; g.oTWR = c0 + cTWR; g.oTWC = c0 + cTWC; g.oWY = c0 + cWY; g.oWX = c0 + cWX; g.oRED = c0 + cRED; g.oLAB = c0 + cLAB;
     g.total = c0 + cF;
     if (hr < 2 || wc < 2) g.ok = 0;
     return g;

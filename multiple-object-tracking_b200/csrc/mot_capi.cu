@@ -176,8 +176,8 @@ static int get_class(mot_ctx_t *c, int hr, int wc, int *out)
     CU(cudaMemcpy(sc.d_wy, wy.data(), sizeof(float) * hr, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.d_wx, wx.data(), sizeof(float) * wc, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(sc.d_yf, yf.data(), sizeof(float) * yf.size(), cudaMemcpyHostToDevice));
-    sc.fast = kcf_fast_smem_bytes(hr, wc) != 0;
-    sc.any_smem = (!sc.fast && hr <= c->any.nmax && wc <= c->any.nmax) ? kcf_any_smem_bytes(hr, wc, c->lut_floats) : 0;
+    sc.fast = !c->ext_on && kcf_fast_smem_bytes(hr, wc) != 0;          // the extensions live in the any-size kernel only
+    sc.any_smem = (!sc.fast && hr >= 2 && wc >= 2 && hr <= c->any.nmax && wc <= c->any.nmax) ? kcf_any_smem_bytes(hr, wc, c->lut_floats) : 0;
     {
         // exp(-2 pi i t / n) tables for the any-size DFT path, evaluated in double with exact argument reduction
         const double two_pi = 6.283185307179586476925286766559;
@@ -415,7 +415,7 @@ void mot_ctx_destroy(mot_ctx_t *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto p : c->frame_owned) if (p) cudaFree(p);
-    cudaFree(c->d_frame_tmaps); cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
+    cudaFree(c->d_alpha_im); cudaFree(c->d_frame_tmaps); cudaFree(c->d_frame_ptr); cudaFree(c->d_meta); cudaFree(c->d_model); cudaFree(c->d_alpha); cudaFree(c->d_classes);
     cudaFree(c->d_tab_rsqrt); cudaFree(c->d_tab_rcp); cudaFree(c->d_tab_rsrc); cudaFree(c->d_tab_bin); cudaFree(c->d_tab_bin2); cudaFree(c->kal.x); cudaFree(c->kal.P);
     if (c->h_any_err) cudaFreeHost(c->h_any_err);
     cudaFree((void *)c->any.hann); cudaFree((void *)c->any.tw); cudaFree((void *)c->any.lab); cudaFree((void *)c->any.plan);
@@ -431,6 +431,24 @@ void mot_ctx_destroy(mot_ctx_t *c)
     cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); for (auto e : c->slot_uploaded) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->own_stream);
     delete c;
+}
+
+int mot_ctx_set_kcf_options(mot_ctx_t *c, const mot_kcf_options_t *o)
+{
+    if (!c || !o) return fail(MOT_ERR_ARG, "mot_ctx_set_kcf_options: null argument");
+    if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
+    for (char u : c->used) if (u) return fail(MOT_ERR_ARG, "the KCF options must be set before the first tracker is created");
+    if (o->gaussian_kernel && !(o->kernel_sigma > 0.f)) return fail(MOT_ERR_ARG, "the Gaussian kernel needs kernel_sigma > 0");
+    if (o->padding != 0.f && (o->padding < 1.f || o->padding > 4.f)) return fail(MOT_ERR_ARG, "padding must be in [1, 4]");
+    if (o->output_sigma_factor < 0.f) return fail(MOT_ERR_ARG, "output_sigma_factor must be >= 0");
+    CU(cudaSetDevice(c->device));
+    c->ext = KcfExt{ o->gaussian_kernel ? 1 : 0, o->kernel_sigma, o->subpixel_peak ? 1 : 0, o->padding > 1.f ? o->padding : 0.f, o->output_sigma_factor };
+    c->ext_on = c->ext.gaussian || c->ext.subpixel || c->ext.padding > 1.f || c->ext.osf > 0.f;
+    if (c->ext.gaussian && !c->d_alpha_im) CU(cudaMalloc(&c->d_alpha_im, sizeof(float) * c->alpha_stride * c->max_tracks));
+    // the per-size classes remember which kernel serves them: start afresh
+    for (auto &sc : c->classes) { sc.fast = !c->ext_on && kcf_fast_smem_bytes(sc.hr, sc.wc) != 0;
+                                  sc.any_smem = (!sc.fast && sc.hr >= 2 && sc.wc >= 2 && sc.hr <= c->any.nmax && sc.wc <= c->any.nmax) ? kcf_any_smem_bytes(sc.hr, sc.wc, c->lut_floats) : 0; }
+    return 0;
 }
 
 int mot_ctx_set_stream(mot_ctx_t *c, void *s) { if (!c) return fail(MOT_ERR_ARG, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
@@ -566,18 +584,24 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
     if (c->kind == MOT_TRACKER_KCF) {
         CU(c->h_meta_stage.ensure(n)); CU(c->d_meta_stage.ensure(n));
         // validate everything first so that a failure leaves no half-created trackers
+        const bool padded = c->ext.padding > 1.0f;
         for (int i = 0; i < n; ++i) {
-            const int rows = boxes[i].b - boxes[i].t + 1, cols = boxes[i].r - boxes[i].l + 1;          // kcf.cpp:148-149
+            const mot_bbox_t wb = padded ? kcf_pad_box(boxes[i], c->ext.padding) : boxes[i];           // extension: the window is the padded target
+            const int rows = wb.b - wb.t + 1, cols = wb.r - wb.l + 1;                                  // kcf.cpp:148-149
             const int hr = rows / KCF_CELL, wc = cols / KCF_CELL;
             if (hr < 2 || wc < 2) return fail(MOT_ERR_SHAPE, "window %dx%d px is smaller than 2x2 cells (8x8 px)", rows, cols);
-            if (rows > c->H || cols > c->W) return fail(MOT_ERR_SHAPE, "window %dx%d px is larger than the %dx%d frame", rows, cols, c->H, c->W);
+            if (!padded && (rows > c->H || cols > c->W)) return fail(MOT_ERR_SHAPE, "window %dx%d px is larger than the %dx%d frame", rows, cols, c->H, c->W);
+            if (c->ext_on && (!kcf_any_smem_bytes(hr, wc, c->lut_floats) || hr > c->any.nmax || wc > c->any.nmax || (long)wc * (hr / 2 + 1) > NB_MAX))
+                return fail(MOT_ERR_SHAPE, "window %dx%d px: the KCF extensions are served by the any-size kernel up to %d spectrum bins", rows, cols, NB_MAX);
         }
         long max_model = 0, max_alpha = 0;
         for (int i = 0; i < n; ++i) {
             KcfMeta m{};
-            m.rows = boxes[i].b - boxes[i].t + 1; m.cols = boxes[i].r - boxes[i].l + 1;
+            const mot_bbox_t wb = padded ? kcf_pad_box(boxes[i], c->ext.padding) : boxes[i];
+            m.rows = wb.b - wb.t + 1; m.cols = wb.r - wb.l + 1;
             m.hr = m.rows / KCF_CELL; m.wc = m.cols / KCF_CELL;
-            m.pos = boxes[i]; m.scale_horiz = 1.0f; m.scale_vert = 1.0f; m.first_update = 1;          // kcf.cpp:200-209
+            m.pos = wb; m.scale_horiz = 1.0f; m.scale_vert = 1.0f; m.first_update = 1;                // kcf.cpp:200-209
+            m.tw = std::abs(boxes[i].r - boxes[i].l) + 1; m.th = std::abs(boxes[i].b - boxes[i].t) + 1;
             int cls = 0; const int rc = get_class(c, m.hr, m.wc, &cls); if (rc) return rc;
             m.size_class = cls;
             const long S_ = (long)m.wc * (m.hr / 2 + 1);
@@ -619,8 +643,12 @@ int mot_tracker_spawnable(mot_ctx_t *c, const mot_bbox_t *box)
 {
     if (!c || !box) return 0;
     if (c->kind != MOT_TRACKER_KCF) return 1;
-    const int rows = box->b - box->t + 1, cols = box->r - box->l + 1;
-    return rows / KCF_CELL >= 2 && cols / KCF_CELL >= 2 && rows <= c->H && cols <= c->W;
+    const bool padded = c->ext.padding > 1.0f;
+    const mot_bbox_t wb = padded ? kcf_pad_box(*box, c->ext.padding) : *box;
+    const int rows = wb.b - wb.t + 1, cols = wb.r - wb.l + 1, hr = rows / KCF_CELL, wc = cols / KCF_CELL;
+    if (hr < 2 || wc < 2) return 0;
+    if (c->ext_on) return kcf_any_smem_bytes(hr, wc, c->lut_floats) != 0 && hr <= c->any.nmax && wc <= c->any.nmax && (long)wc * (hr / 2 + 1) <= NB_MAX;
+    return rows <= c->H && cols <= c->W;
 }
 
 int mot_tracker_delete_batch(mot_ctx_t *c, int n, const int *handles)
@@ -651,12 +679,13 @@ static void fill_launch(mot_ctx_t *c, KcfLaunch &L, int n, const int *d_slots, c
     L.meta = c->d_meta; L.model = c->d_model; L.model_stride = c->model_stride; L.alpha = c->d_alpha; L.alpha_stride = c->alpha_stride;
     L.classes = c->d_classes; L.tab = c->tab; L.clamp_to_frame = clamp;
     L.factor = 0.05f; L.lamda = 0.0001f;                                 // kcf.cpp:211-212
+    L.ext = c->ext; L.alpha_im = c->d_alpha_im;
     if (c->dumps) L.dump = c->dump;
 }
 
 static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
 {
-    if (kcf_fast_smem_bytes(hr, wc) != 0) {
+    if (!c->ext_on && kcf_fast_smem_bytes(hr, wc) != 0) {
         const int rc = kcf_launch_fast(mode, hr, wc, L, c->stream);
         if (rc) return fail(MOT_ERR_CUDA, "KCF launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
@@ -678,6 +707,7 @@ static int kcf_run(mot_ctx_t *c, int mode, int hr, int wc, KcfLaunch &L)
             return 0;
         }
     }
+    if (c->ext_on) return fail(MOT_ERR_SHAPE, "the KCF extensions need a window the any-size kernel holds (%dx%d cells does not fit)", hr, wc);
     // whatever is left (windows too large for one CTA): unfused pipeline with per-job scratch, processed in chunks of at most ~1 GB of scratch
     const size_t per_job = kcf_generic_scratch_bytes(hr, wc);
     size_t jobs = std::min<size_t>((size_t)L.n_jobs, std::max<size_t>(1, ((size_t)1 << 30) / per_job));
@@ -1053,6 +1083,19 @@ long mot_debug_state(mot_ctx_t *c, int handle, int which, void *host_out, long m
         if (which == 1) {
             const long bytes = 4 * S; if (bytes > max_bytes) return fail(MOT_ERR_ARG, "buffer too small");
             e = cudaMemcpy(host_out, m.alpha_ptr ? m.alpha_ptr : c->d_alpha + (long)handle * c->alpha_stride, bytes, cudaMemcpyDeviceToHost);
+            return e == cudaSuccess ? bytes : fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
+        }
+        if (which == 4) {                               // extension: sub-cell refinement (vertical, horizontal) of the last predicted peak
+            if (max_bytes < 8) return fail(MOT_ERR_ARG, "buffer too small");
+            KcfMeta mt;
+            e = cudaMemcpy(&mt, c->d_meta + handle, sizeof(KcfMeta), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) return fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
+            float v[2] = { mt.sub_dv, mt.sub_dh }; memcpy(host_out, v, 8);
+            return 8;
+        }
+        if (which == 5) {                               // extension: imaginary part of alpha (Gaussian kernel)
+            const long bytes = 4 * S; if (bytes > max_bytes || !c->d_alpha_im) return fail(MOT_ERR_ARG, "no complex alpha / buffer too small");
+            e = cudaMemcpy(host_out, c->d_alpha_im + (long)handle * c->alpha_stride, bytes, cudaMemcpyDeviceToHost);
             return e == cudaSuccess ? bytes : fail(MOT_ERR_CUDA, "%s", cudaGetErrorString(e));
         }
         return fail(MOT_ERR_ARG, "unknown state %d for a KCF context", which);

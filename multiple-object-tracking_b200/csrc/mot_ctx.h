@@ -82,6 +82,9 @@ struct mot_ctx_s {
     AnyTablesDev any{};                   // per-N tables of the any-size kernel (Hann, twiddles, label spectra, radix plans)
     int lut_floats = 0;                   // floats of the SSE tables a fused kernel stages in shared memory
     int sm_count = 0;
+    KcfExt ext{};                         // north-star extensions (mot_ctx_set_kcf_options); all zero = the reference's filter
+    bool ext_on = false;
+    float *d_alpha_im = nullptr;          // imaginary part of alpha (Gaussian kernel), same slot stride as d_alpha
     int *h_any_err = nullptr, *d_any_err = nullptr;   // mapped pinned word the any-size kernel sets when a job does not fit its launch
     float *d_tab_rsqrt = nullptr, *d_tab_rcp = nullptr, *d_tab_rsrc = nullptr; uint32_t *d_tab_bin = nullptr, *d_tab_bin2 = nullptr;
     KalmanState kal{};

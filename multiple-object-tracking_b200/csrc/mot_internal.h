@@ -21,7 +21,38 @@ struct KcfMeta {
     int size_class;                   // index into the per-size constant tables
     float2 *model_ptr;                // any-size tracks own their model / alpha (null: slot arena, see KcfLaunch)
     float *alpha_ptr;
+    int tw, th;                       // extensions: size of the TARGET box at the last update (the window is tw x th times the padding)
+    float sub_dv, sub_dh;             // extensions: sub-cell refinement of the last predicted peak (0 without sub-pixel mode)
 };
+
+// North-star extensions of the filter.  All off = the reference's filter (linear kernel, integer peak, window =
+// box, label sigma 0.7289 cells), which is the only mode with a reference oracle; anything else is validated against the NumPy
+// restatement tests/kcf_ext_numpy.py (parity unpinned by the reference) and served by the any-size kernel.
+struct KcfExt {
+    int gaussian;                     // Gaussian kernel correlation (Henriques et al., KCF) instead of the linear one
+    float sigma;                      // its bandwidth
+    int subpixel;                     // parabolic refinement of the response peak
+    float padding;                    // window = target box x padding about its centre (<= 1: none)
+    float osf;                        // label sigma = sqrt(target w x h) x osf / cell (0: the reference's fixed 0.7289 cells)
+};
+
+// window of a target box and back; integer arithmetic shared by host and device (unpad(pad(b)) == b)
+__host__ __device__ inline mot_bbox_t kcf_pad_box(mot_bbox_t b, float p)
+{
+    if (b.t > b.b) { const int q = b.t; b.t = b.b; b.b = q; }
+    if (b.l > b.r) { const int q = b.l; b.l = b.r; b.r = q; }
+    const int w = b.r - b.l + 1, h = b.b - b.t + 1;
+    const int pw = (int)((float)w * p), ph = (int)((float)h * p);
+    const int nl = (b.l + b.r - pw + 1) >> 1, nt = (b.t + b.b - ph + 1) >> 1;
+    b.l = nl; b.r = nl + pw - 1; b.t = nt; b.b = nt + ph - 1;
+    return b;
+}
+__host__ __device__ inline mot_bbox_t kcf_unpad_box(mot_bbox_t wdw, int tw, int th)
+{
+    const int l = (wdw.l + wdw.r - tw + 2) >> 1, t = (wdw.t + wdw.b - th + 2) >> 1;
+    wdw.l = l; wdw.r = l + tw - 1; wdw.t = t; wdw.b = t + th - 1;
+    return wdw;
+}
 
 // Per-size constants shared by every track of the same window (kcf.cpp:203-207 are size-only).
 struct KcfClassDev {
@@ -79,6 +110,8 @@ struct KcfLaunch {
     FhogTablesDev tab;
     int clamp_to_frame;               // fold top/td.cpp:378-381 into predict
     float factor, lamda;              // kcf.cpp:211-212
+    KcfExt ext;                       // extensions (any-size kernel only); all zero = the reference's filter
+    float *alpha_im;                  // Gaussian kernel: imaginary part of the (then complex) alpha, same slot stride as alpha
     KcfDump dump;
 };
 

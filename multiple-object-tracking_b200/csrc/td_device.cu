@@ -305,6 +305,7 @@ int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int ma
 {
     if (!out || !c || n_streams <= 0 || cap <= 0 || cap > 1024 || max_det <= 0 || max_det > 1024) return mot_fail(MOT_ERR_ARG, "mot_tdd_create: bad argument (cap and max_det must be in 1..1024)");
     const bool kcf = c->kind == MOT_TRACKER_KCF;
+    if (kcf && c->ext_on) return mot_fail(MOT_ERR_ARG, "the device-resident loop runs the reference's filter only; use mot_td_step with the KCF extensions");
     if (kcf && c->n_frames < n_streams) return mot_fail(MOT_ERR_ARG, "the KCF frame loop reads stream s from frame slot s: the context has %d frame slots, %d are needed", c->n_frames, n_streams);
     if ((long)n_streams * cap > c->max_tracks) return mot_fail(MOT_ERR_CAPACITY, "context has %d track slots, %d streams x %d are needed", c->max_tracks, n_streams, cap);
     for (char u : c->used) if (u) return mot_fail(MOT_ERR_ARG, "the context already holds host-managed trackers");

@@ -28,7 +28,7 @@ def make_chain(dets):
     return c
 
 EXPORTS = [
-    "mot_ctx_create", "mot_ctx_destroy", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
+    "mot_ctx_create", "mot_ctx_destroy", "mot_ctx_set_kcf_options", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
     "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_yolo_post", "mot_tracker_new_batch", "mot_tracker_delete_batch", "mot_tracker_spawnable",
     "mot_predict_batch", "mot_update_batch", "mot_track_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_rgb2gray_host", "mot_resize_gray_host", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
@@ -40,7 +40,7 @@ EXPORTS = [
 
 def build(verbose=False):
     """Compile libmot_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    out = subprocess.run(["make", "-C", PKG_DIR, "-j4"], capture_output=True, text=True)
+    out = subprocess.run(["make", "-C", PKG_DIR, "-j%d" % max(4, os.cpu_count() or 4)], capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("building libmot_b200.so failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
     if verbose:
@@ -160,6 +160,13 @@ class Context:
             pass
 
     # context
+    def set_kcf_options(self, gaussian=False, sigma=0.5, subpixel=False, padding=0.0, osf=0.0):
+        """North-star extensions (mot_ctx_set_kcf_options); call before the first tracker is created."""
+        class Opt(C.Structure):
+            _fields_ = [("gaussian_kernel", C.c_int), ("kernel_sigma", C.c_float), ("subpixel_peak", C.c_int), ("padding", C.c_float), ("output_sigma_factor", C.c_float)]
+        o = Opt(1 if gaussian else 0, sigma, 1 if subpixel else 0, padding, osf)
+        _chk(lib().mot_ctx_set_kcf_options(self.h, C.byref(o)))
+
     def set_stream(self, cuda_stream_ptr):
         _chk(lib().mot_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
@@ -285,8 +292,8 @@ class Context:
         return out[: n // out.itemsize].copy()
 
     def state(self, handle, which):
-        code = dict(xf_md=0, alpha=1, x=2, P=3)[which]
-        out = np.zeros(1 << 18, np.float64 if code >= 2 else np.float32)
+        code = dict(xf_md=0, alpha=1, x=2, P=3, subpixel=4, alpha_im=5)[which]
+        out = np.zeros(1 << 18, np.float64 if code in (2, 3) else np.float32)
         n = lib().mot_debug_state(self.h, int(handle), code, _p(out), out.nbytes)
         if n < 0:
             _chk(int(n))

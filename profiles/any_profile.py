@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-phase and per-line breakdown of an `ncu --set full --import-source on` capture of the any-size kernel (csrc/kcf_any.cu).
+"""Per-phase and per-line breakdown of an `ncu --set full --import-source on` capture of the any-size kernel (csrc/kcf_any_kernel.cuh).
 
 usage: python profiles/any_profile.py REPORT.ncu-rep MODE(0=predict,1=update) [TOP_LINES [NTMAX(512|1024) [STRIPS(0|1)]]]      (same build as the report)
 """
@@ -9,7 +9,7 @@ from sass_lines import parse_disasm  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "multiple-object-tracking_b200")
-SRC = os.path.join(PKG, "csrc", "kcf_any.cu")
+SRC = os.path.join(PKG, "csrc", "kcf_any_kernel.cuh")
 STALLS = ["stall_barrier", "stall_long_sb", "stall_short_sb", "stall_mio", "stall_math", "stall_wait", "stall_not_selected", "stall_selected",
           "stall_lg", "stall_dispatch", "stall_no_inst", "stall_branch_resolving", "stall_membar", "stall_tex", "stall_sleeping"]
 
@@ -19,7 +19,7 @@ def main():
     topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     tmp = tempfile.mkdtemp()
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(PKG, "build", "kcf_any.o")], cwd=tmp, capture_output=True)
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(PKG, "build", "kcf_any_inst_%d_0.o" % mode)], cwd=tmp, capture_output=True)
     cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
     dis = os.path.join(tmp, "dis.txt")
     open(dis, "w").write(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout)
@@ -36,13 +36,13 @@ def main():
             cur.append(dict(zip(shdr, r)))
     ntmax = int(sys.argv[4]) if len(sys.argv) > 4 else 512
     strips = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-    insts = parse_disasm(dis, "kcf_any_kernelILi%dELb0ELi%dELb%dE" % (mode, ntmax, strips))
+    insts = parse_disasm(dis, "kcf_any_kernelILi%dELb0ELi%dELb%dELb0E" % (mode, ntmax, strips))
     sect = next(s for k, s in sects if len(s) == len(insts))
 
     def phase_of(line):
         if not line:
             return "?"
-        if line[0] != "kcf_any.cu":
+        if line[0] != "kcf_any_kernel.cuh":
             return line[0]
         key = "pre"
         for ln, nm in marks:
@@ -77,7 +77,7 @@ def main():
         print("%-22s %5.1f%% smp %5.1f%% inst %9d  smem wf %9d (excess %8d) | %s" % (ph[:22], 100.0 * a["n"] / tot, 100.0 * a["inst"] / toti, a["inst"], a["wf"], a["wfx"], top))
     print("-" * 40, "hottest source lines")
     for line, a in sorted(lines.items(), key=lambda kv: -kv[1]["n"])[:topn]:
-        text = src[line[1] - 1].strip()[:90] if line and line[0] == "kcf_any.cu" else ""
+        text = src[line[1] - 1].strip()[:90] if line and line[0] == "kcf_any_kernel.cuh" else ""
         st = ", ".join("%s %.0f%%" % (s.replace("stall_", ""), 100.0 * a[s] / max(a["n"], 1)) for s in sorted(STALLS, key=lambda s: -a[s])[:2])
         print("  %-22s %4.1f%% smp %4.1f%% inst wf %8d/%7d  %-30s| %s" % ("%s:%d" % line if line else "?", 100.0 * a["n"] / tot, 100.0 * a["inst"] / toti, a["wf"], a["wfx"], st, text))
 

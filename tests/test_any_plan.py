@@ -47,3 +47,19 @@ def test_shared_memory_plans():
     assert plan(13, 9)["ctas"] == 4 and plan(25, 15)["ctas"] == 2 and plan(30, 40)["ctas"] == 1
     # a window no CTA can hold even in strips is refused (the unfused path serves it): the whole 1080p frame, or 100 x 100 cells
     assert not plan(270, 480)["ok"] and not plan(100, 100)["ok"]
+
+
+def test_padding_round_trip_of_the_restatement():
+    """kcf_pad_box / kcf_unpad_box (csrc/mot_internal.h) as restated in tests/kcf_ext_numpy.py: window -> target is the identity,
+    the window is centred on the target (to within half a pixel) and has int(size * p) pixels per side."""
+    from kcf_ext_numpy import pad_box, unpad_box
+    rng = np.random.default_rng(1)
+    for _ in range(2000):
+        l, t = int(rng.integers(-50, 2000)), int(rng.integers(-50, 1100))
+        w, h = int(rng.integers(8, 400)), int(rng.integers(8, 400))
+        p = float(rng.choice([1.5, 2.0, 2.5, 3.0]))
+        tgt = (l, t, t + h - 1, l + w - 1)
+        wl, wt, wb, wr = pad_box(*tgt, p)
+        assert wr - wl + 1 == int(np.float32(w) * np.float32(p)) and wb - wt + 1 == int(np.float32(h) * np.float32(p))
+        assert abs((wl + wr) - (l + l + w - 1)) <= 1 and abs((wt + wb) - (t + t + h - 1)) <= 1
+        assert unpad_box(wl, wt, wb, wr, w, h) == tgt
