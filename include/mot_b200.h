@@ -82,6 +82,13 @@ typedef struct mot_kcf_options_s {
 } mot_kcf_options_t;
 int mot_ctx_set_kcf_options(mot_ctx_t *ctx, const mot_kcf_options_t *opt);
 
+/* KCF contexts: size the slots of the model arena for windows up to max_rows x max_cols pixels (either orientation).  The reference
+ * allocates every tracker's spectra for whatever size its detection box has (trackers/kcf.cpp:146-195); here a slot holds 1152
+ * half-spectrum bins by default (the named 128x128 shape: 544), host-managed trackers beyond that own individually allocated storage,
+ * and the device-resident loop can only spawn windows a slot holds.  Call before the first tracker exists; memory = 252 bytes per bin
+ * and track slot. */
+int mot_ctx_reserve_window(mot_ctx_t *ctx, int max_rows, int max_cols);
+
 /* ---- frames (replaces the cv::Mat the tracking thread pops, top/td.cpp:330-331) --------------------------- */
 
 /* Copy a host BGR u8 frame (rows of stride_bytes) into frame slot `slot` (async on the context stream). */
@@ -207,9 +214,11 @@ typedef struct mot_tdd_s mot_tdd_t;
 /* n_streams independent streams, at most cap tracks (reference: 256, top/td.cpp:12) and max_det detections
  * (reference: 128, top/cnntype.h:46) each, both <= 1024.  The context needs >= n_streams*cap free slots and no host-managed
  * trackers.  KCF contexts: stream s reads frame slot base + s (mot_tdd_frame_base; mot_frame_upload / mot_frame_bind_device
- * before each step), and only
- * detections whose window has a fused kernel (cell grid sides 8, 16 or 32, i.e. 32..35, 64..67 or 128..131 pixels per side)
- * can spawn a track; the others are counted (mot_tdd_dropped) -- the host-side loop mot_td_step serves every size. */
+ * before each step).  A detection of any window size a fused kernel serves spawns a track on the device: the fixed-size kernels
+ * (cell grid sides 8, 16, 32), the any-size kernel in shared memory (up to about 1400 cells) and in strip mode (up to about 8000
+ * cells = e.g. 360 x 360 px), provided its half spectrum fits a slot of the model arena (1152 bins by default: call
+ * mot_ctx_reserve_window before mot_tdd_create for larger windows).  Detections beyond that, smaller than 8x8 px or larger than the
+ * frame are counted (mot_tdd_dropped) -- the host-side loop mot_td_step serves every size. */
 int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *ctx, int n_streams, int cap, int max_det, int cost_mode);
 void mot_tdd_destroy(mot_tdd_t *tdd);
 /* detections already on the device: d_dets[n_streams][max_det], d_ndet[n_streams]; asynchronous on the context stream */

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(NTMAX, 1) kcf_any_kernel(const KcfLaunch p, co
             __syncthreads();
         }
         const AnyGeo &g = jc.g;
-        if (g.total > smem_floats || !g.ok || (g.strips != 0) != STRIPS) {     // cannot happen when the host sized the launch; never run out of bounds
+        if (g.total > smem_floats || !g.ok || (g.strips != 0) != STRIPS || (STRIPS && 18L * g.os > r1g_stride)) {     // cannot happen when the host sized the launch; never run out of bounds
             if (tid == 0 && err_flag) *reinterpret_cast<volatile int *>(err_flag) = 1;
             continue;
         }

@@ -321,12 +321,12 @@ static void any_launch_shape(size_t smem, int *threads, int *ctas)
 
 
 int mot_ctx_kcf_launch_any(mot_ctx_t *c, int mode, size_t smem_bytes, int n_max, const int *n_dev, const int *slots, const int *frames,
-                           mot_bbox_t *boxes, const int *box_index, int clamp)
+                           mot_bbox_t *boxes, const int *box_index, int clamp, float *scratch, long scratch_stride_floats, int scratch_ctas)
 {
     KcfLaunch L; fill_launch(c, L, n_max, slots, frames, boxes, clamp);
     L.n_jobs_dev = n_dev; L.box_index = box_index; L.dump = KcfDump{};
     int threads, ctas; any_launch_shape(smem_bytes, &threads, &ctas);
-    const int rc = kcf_launch_any(mode, L, c->any, smem_bytes, threads, ctas, c->d_any_err, nullptr, 0, 0, c->stream);
+    const int rc = kcf_launch_any(mode, L, c->any, smem_bytes, threads, ctas, c->d_any_err, scratch, scratch_stride_floats, scratch ? scratch_ctas : 0, c->stream);
     if (rc) return fail(MOT_ERR_CUDA, "KCF (any-size kernel) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     c->launches += 1;
     return 0;
@@ -448,6 +448,30 @@ int mot_ctx_set_kcf_options(mot_ctx_t *c, const mot_kcf_options_t *o)
     // the per-size classes remember which kernel serves them: start afresh
     for (auto &sc : c->classes) { sc.fast = !c->ext_on && kcf_fast_smem_bytes(sc.hr, sc.wc) != 0;
                                   sc.any_smem = (!sc.fast && sc.hr >= 2 && sc.wc >= 2 && sc.hr <= c->any.nmax && sc.wc <= c->any.nmax) ? kcf_any_smem_bytes(sc.hr, sc.wc, c->lut_floats) : 0; }
+    return 0;
+}
+
+// The slot arena holds model and alpha of every window up to `alpha_stride` half-spectrum bins (default NB_MAX: the named 32x32-cell
+// shape with room to spare).  Larger windows otherwise own individually allocated storage (host-managed trackers) or cannot be born on
+// the device at all (device-resident loop): this call re-sizes the arena for windows up to max_rows x max_cols pixels, either orientation.
+int mot_ctx_reserve_window(mot_ctx_t *c, int max_rows, int max_cols)
+{
+    if (!c || max_rows < 2 * KCF_CELL || max_cols < 2 * KCF_CELL) return fail(MOT_ERR_ARG, "mot_ctx_reserve_window: bad argument");
+    if (c->kind != MOT_TRACKER_KCF) return fail(MOT_ERR_KIND, "context is not a KCF context");
+    for (char u : c->used) if (u) return fail(MOT_ERR_ARG, "the window reservation must be made before the first tracker is created");
+    CU(cudaSetDevice(c->device));
+    const long hr = max_rows / KCF_CELL, wc = max_cols / KCF_CELL;
+    const long bins = std::max<long>(NB_MAX, std::max(wc * (hr / 2 + 1), hr * (wc / 2 + 1)));
+    if (bins == c->alpha_stride) return 0;
+    float2 *nm = nullptr; float *na = nullptr, *ni = nullptr;
+    cudaError_t e = cudaMalloc(&nm, sizeof(float2) * KCF_CHAN * bins * c->max_tracks);
+    if (e == cudaSuccess) e = cudaMalloc(&na, sizeof(float) * bins * c->max_tracks);
+    if (e == cudaSuccess && c->d_alpha_im) e = cudaMalloc(&ni, sizeof(float) * bins * c->max_tracks);
+    if (e != cudaSuccess) { cudaFree(nm); cudaFree(na); cudaFree(ni); cudaGetLastError(); return fail(MOT_ERR_CAPACITY, "no memory for %d slots of %ld bins: %s", c->max_tracks, bins, cudaGetErrorString(e)); }
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_model); cudaFree(c->d_alpha); if (c->d_alpha_im) cudaFree(c->d_alpha_im);
+    c->d_model = nm; c->d_alpha = na; c->d_alpha_im = ni;
+    c->model_stride = (long)KCF_CHAN * bins; c->alpha_stride = bins;
     return 0;
 }
 
@@ -591,8 +615,8 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
             const int hr = rows / KCF_CELL, wc = cols / KCF_CELL;
             if (hr < 2 || wc < 2) return fail(MOT_ERR_SHAPE, "window %dx%d px is smaller than 2x2 cells (8x8 px)", rows, cols);
             if (!padded && (rows > c->H || cols > c->W)) return fail(MOT_ERR_SHAPE, "window %dx%d px is larger than the %dx%d frame", rows, cols, c->H, c->W);
-            if (c->ext_on && (!kcf_any_smem_bytes(hr, wc, c->lut_floats) || hr > c->any.nmax || wc > c->any.nmax || (long)wc * (hr / 2 + 1) > NB_MAX))
-                return fail(MOT_ERR_SHAPE, "window %dx%d px: the KCF extensions are served by the any-size kernel up to %d spectrum bins", rows, cols, NB_MAX);
+            if (c->ext_on && (!kcf_any_smem_bytes(hr, wc, c->lut_floats) || hr > c->any.nmax || wc > c->any.nmax || (long)wc * (hr / 2 + 1) > c->alpha_stride))
+                return fail(MOT_ERR_SHAPE, "window %dx%d px: the KCF extensions are served by the any-size kernel up to %ld spectrum bins (mot_ctx_reserve_window raises it)", rows, cols, c->alpha_stride);
         }
         long max_model = 0, max_alpha = 0;
         for (int i = 0; i < n; ++i) {
@@ -605,7 +629,7 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
             int cls = 0; const int rc = get_class(c, m.hr, m.wc, &cls); if (rc) return rc;
             m.size_class = cls;
             const long S_ = (long)m.wc * (m.hr / 2 + 1);
-            if (!c->classes[cls].fast && (!c->classes[cls].any_smem || S_ > NB_MAX)) {
+            if (!c->classes[cls].fast && (!c->classes[cls].any_smem || S_ > c->alpha_stride)) {
                 // sizes that no fused kernel holds own their model / alpha (they can exceed the fixed slot stride)
                 CU(cudaMalloc(&m.model_ptr, sizeof(float2) * KCF_CHAN * S_)); CU(cudaMalloc(&m.alpha_ptr, sizeof(float) * S_));
                 CU(cudaMemsetAsync(m.model_ptr, 0, sizeof(float2) * KCF_CHAN * S_, c->stream)); CU(cudaMemsetAsync(m.alpha_ptr, 0, sizeof(float) * S_, c->stream));
@@ -613,7 +637,7 @@ int mot_tracker_new_batch(mot_ctx_t *c, int n, const mot_bbox_t *boxes, int *han
             const int slot = c->free_slots.back(); c->free_slots.pop_back();
             c->used[slot] = 1; c->meta_h[slot] = m; c->classes[cls].live++;
             c->h_slots.p[i] = slot; c->h_meta_stage.p[i] = m; handles_out[i] = slot;
-            if (c->classes[cls].fast || (c->classes[cls].any_smem && S_ <= NB_MAX)) { max_model = std::max(max_model, KCF_CHAN * S_); max_alpha = std::max(max_alpha, S_); }
+            if (c->classes[cls].fast || (c->classes[cls].any_smem && S_ <= c->alpha_stride)) { max_model = std::max(max_model, KCF_CHAN * S_); max_alpha = std::max(max_alpha, S_); }
         }
         CU(cudaMemcpyAsync(c->d_slots.p, c->h_slots.p, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_meta_stage.p, c->h_meta_stage.p, sizeof(KcfMeta) * n, cudaMemcpyHostToDevice, c->stream));
@@ -647,7 +671,7 @@ int mot_tracker_spawnable(mot_ctx_t *c, const mot_bbox_t *box)
     const mot_bbox_t wb = padded ? kcf_pad_box(*box, c->ext.padding) : *box;
     const int rows = wb.b - wb.t + 1, cols = wb.r - wb.l + 1, hr = rows / KCF_CELL, wc = cols / KCF_CELL;
     if (hr < 2 || wc < 2) return 0;
-    if (c->ext_on) return kcf_any_smem_bytes(hr, wc, c->lut_floats) != 0 && hr <= c->any.nmax && wc <= c->any.nmax && (long)wc * (hr / 2 + 1) <= NB_MAX;
+    if (c->ext_on) return kcf_any_smem_bytes(hr, wc, c->lut_floats) != 0 && hr <= c->any.nmax && wc <= c->any.nmax && (long)wc * (hr / 2 + 1) <= c->alpha_stride;
     return rows <= c->H && cols <= c->W;
 }
 

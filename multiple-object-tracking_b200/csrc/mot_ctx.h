@@ -105,9 +105,10 @@ struct mot_ctx_s {
     int dump_hr = 0, dump_wc = 0, dump_rows = 0, dump_cols = 0;
 };
 
-// the same over an any-size job list: every job's shared-memory plan fits `smem_bytes` (csrc/kcf_any.cuh)
+// the same over an any-size job list: every job's shared-memory plan fits `smem_bytes` (csrc/kcf_any.cuh); scratch != null: a list
+// of STRIP-MODE windows, each of the (at most scratch_ctas) CTAs parking its histograms in scratch_stride_floats of global memory
 int mot_ctx_kcf_launch_any(mot_ctx_t *c, int mode, size_t smem_bytes, int n_max, const int *n_dev, const int *slots, const int *frames,
-                           mot_bbox_t *boxes, const int *box_index, int clamp);
+                           mot_bbox_t *boxes, const int *box_index, int clamp, float *scratch, long scratch_stride_floats, int scratch_ctas);
 // ---- internal services of mot_capi.cu used by the device-resident frame loop (csrc/td_device.cu) ---------------------------
 int mot_ctx_kcf_class(mot_ctx_t *c, int hr, int wc, int *cls_out);       // index of the (created on demand) per-size constant tables
 int mot_ctx_frames_ready(mot_ctx_t *c);                                  // frame pointer table on the device, pending uploads waited for

@@ -11,14 +11,17 @@
 // window size a track has in a form the host could read without synchronising, so every frame a small kernel sorts the
 // live tracks into job lists: one per fixed-size fused kernel (cell grids with sides 8/16/32) and three for the fused
 // any-size kernel (kcf_any.cu), by the shared memory a window needs (four, two or one CTA per SM); the kernels take their
-// job count from the device and exit at once when their list is empty.  A tracker of ANY size a CTA can hold is therefore
+// job count from the device and exit at once when their list is empty; a fourth any-size list holds the STRIP-MODE windows (those
+// beyond one CTA's shared memory, about 1400 to 8000 cells), launched with a per-CTA scratch area owned by the loop object.  A tracker
+// of ANY size the fused any-size kernel serves is therefore
 // born on the device: its constants come from the per-N tables, nothing is computed on the host.  tracker_new (trackers/kcf.cpp:484-491, :139-213) runs
 // inside the lifecycle kernel (metadata only: model and alpha are fully written by the first update), followed by one
 // more update launch over the tracks spawned in this frame (the reference's first update, top/td.cpp:629-641).  Stream s
 // reads frame slot frame_base + s (mot_tdd_frame_base: alternate two bases to upload frame k+1 under the kernels of frame k).
-// Only detections no tracker can be built for (smaller than 2x2 cells, larger than the frame, or too large for one CTA's shared
-// memory -- about 1400 cells) are skipped and counted (mot_tdd_dropped); the host-side loop (host/td_loop.cpp) serves the last kind
-// through the unfused path.
+// Only detections no tracker can be built for here -- smaller than 2x2 cells, larger than the frame, beyond the any-size kernel's
+// strip mode (about 8000 cells), or with more half-spectrum bins than a slot of the context's arena holds (1152 by default,
+// mot_ctx_reserve_window raises it) -- are skipped and counted (mot_tdd_dropped); the host-side loop (host/td_loop.cpp) serves the
+// last two kinds through individually allocated models and the unfused path.
 #include "mot_ctx.h"
 
 namespace mot {
@@ -34,7 +37,9 @@ struct TddState {
     int kcf, frame_w, frame_h;
     int frame_base;                              // stream s reads frame slot frame_base + s
     int cls_id[9];                               // context class index of fused class 3*hi + wi (cell sides 8, 16, 32); -1: disabled
-    int any_on[3];                               // any-size job lists (list 9 + b) enabled
+    int any_on[4];                               // any-size job lists (list 9 + b) enabled; b = 3: strip-mode windows
+    int bins_max;                                // half-spectrum bins one slot of the context's model arena holds
+    long strip_floats;                           // per-CTA scratch of the strip-mode list (floats)
     int lut_floats;                              // what any_geo needs to size a window's shared memory
     KcfMeta *meta;
     int *jl_slot, *jl_frame, *jl_box, *jl_count; // [TDD_LISTS][S*cap] x 3, [TDD_LISTS]: live tracks grouped by kernel
@@ -42,7 +47,7 @@ struct TddState {
     int *dropped;                                // [S] detections that could not spawn (no fused kernel for their window)
 };
 
-constexpr int TDD_LISTS = 12;                    // 9 fixed-size fused classes + 3 any-size lists
+constexpr int TDD_LISTS = 13;                    // 9 fixed-size fused classes + 3 any-size lists by shared-memory bucket + the strip-mode list
 
 // any-size list of a window that needs `floats` of shared memory: 0 -> four CTAs per SM, 1 -> two, 2 -> one (mot_capi.cu: any_launch_shape)
 __host__ __device__ inline size_t tdd_any_list_bytes(int b) { return b == 0 ? (size_t)(227 * 1024) / 4 - 1024 : b == 1 ? (size_t)(227 * 1024) / 2 - 1024 : (size_t)ANY_SMEM_BUDGET_FLOATS * 4; }
@@ -63,7 +68,8 @@ __device__ __forceinline__ int kcf_list_of(const TddState &st, int rows, int col
     if (k >= 0) return k;
     if (fused_side(rows / KCF_CELL) >= 0 && fused_side(cols / KCF_CELL) >= 0) return -1;      // a fixed-size class that was switched off
     const AnyGeo g = any_geo(rows / KCF_CELL, cols / KCF_CELL, st.lut_floats);
-    if (!g.ok || g.strips || g.S > NB_MAX) return -1;      // strip-mode windows need per-CTA scratch and, beyond NB_MAX bins, their own model storage: host loop only
+    if (!g.ok || g.S > st.bins_max) return -1;             // no fused kernel, or the model does not fit a slot of the arena
+    if (g.strips) return (st.any_on[3] && 18L * g.os <= st.strip_floats) ? 12 : -1;
     const size_t bytes = (size_t)g.total * 4;
     const int b = bytes <= tdd_any_list_bytes(0) ? 0 : bytes <= tdd_any_list_bytes(1) ? 1 : 2;
     return st.any_on[b] ? 9 + b : -1;
@@ -245,6 +251,7 @@ struct mot_tdd_s {
     TddState st{};
     int cost_mode;
     double *d_dist = nullptr, *d_cost = nullptr, *d_work = nullptr;      // cost matrices, totals, the solver's working copy (owned: graph-safe)
+    float *d_strip = nullptr; int strip_ctas = 0;                        // strip-mode list: per-CTA histogram scratch (L2-resident)
     DevBuf<mot_bbox_t> d_dets; DevBuf<int> d_ndet;
     PinBuf<mot_bbox_t> h_dets; PinBuf<int> h_ndet;
     // The host-array step is launch-latency bound (two copies + six kernels for a few hundred tracks): its fixed sequence is
@@ -263,7 +270,7 @@ static void tdd_release(mot_tdd_t *t)
     cudaFree(st.ntracks); cudaFree(st.tracker_id); cudaFree(st.tid); cudaFree(st.slot); cudaFree(st.age); cudaFree(st.vis); cudaFree(st.invis);
     cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost); cudaFree(t->d_work);
     cudaFree(st.jl_slot); cudaFree(st.jl_frame); cudaFree(st.jl_box); cudaFree(st.sp_slot); cudaFree(st.sp_frame); cudaFree(st.sp_box);
-    cudaFree(st.jl_count); cudaFree(st.dropped);
+    cudaFree(st.jl_count); cudaFree(st.dropped); cudaFree(t->d_strip);
     if (t->graph) cudaGraphExecDestroy(t->graph);
     t->d_dets.release(); t->d_ndet.release(); t->h_dets.release(); t->h_ndet.release();
 }
@@ -286,8 +293,8 @@ static int tdd_alloc(mot_tdd_t *t, mot_ctx_t *c, int n_streams, int cap, int max
     CU(cudaMemsetAsync(st.bbox, 0, sizeof(mot_bbox_t) * n, c->stream)); CU(cudaMemsetAsync(st.tid, 0, sizeof(uint32_t) * n, c->stream));
     st.kcf = kcf ? 1 : 0; st.frame_w = c->W; st.frame_h = c->H; st.meta = c->d_meta; st.frame_base = 0;
     for (int k = 0; k < 9; ++k) st.cls_id[k] = -1;
-    for (int b = 0; b < 3; ++b) st.any_on[b] = kcf ? 1 : 0;
-    st.lut_floats = c->lut_floats;
+    for (int b = 0; b < 4; ++b) st.any_on[b] = kcf ? 1 : 0;
+    st.lut_floats = c->lut_floats; st.bins_max = (int)c->alpha_stride; st.strip_floats = 0;
     if (kcf) {
         static const int side[3] = { 8, 16, 32 };
         for (int hi = 0; hi < 3; ++hi)
@@ -296,6 +303,11 @@ static int tdd_alloc(mot_tdd_t *t, mot_ctx_t *c, int n_streams, int cap, int max
         CU(cudaMalloc(&st.sp_slot, sizeof(int) * TDD_LISTS * n)); CU(cudaMalloc(&st.sp_frame, sizeof(int) * TDD_LISTS * n)); CU(cudaMalloc(&st.sp_box, sizeof(int) * TDD_LISTS * n));
         CU(cudaMalloc(&st.jl_count, sizeof(int) * 2 * TDD_LISTS)); st.sp_count = st.jl_count + TDD_LISTS;
         CU(cudaMalloc(&st.dropped, sizeof(int) * n_streams));
+        // strip-mode windows: 18 orientation planes of the cell grid per resident CTA (one CTA per SM); a window has fewer than
+        // 2 * bins cells, and the any-size kernel ends at about 8200
+        t->strip_ctas = c->sm_count;
+        st.strip_floats = 18L * ((std::min(2 * st.bins_max, 8448) + 31) & ~31);
+        CU(cudaMalloc(&t->d_strip, sizeof(float) * st.strip_floats * t->strip_ctas));
         CU(cudaMemsetAsync(st.dropped, 0, sizeof(int) * n_streams, c->stream));
     }
     return 0;
@@ -347,7 +359,13 @@ static int tdd_step_kcf(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_nde
         for (int b = 0; b < 3; ++b) {
             if (!st.any_on[b]) continue;
             const int k = 9 + b;
-            const int r = mot_ctx_kcf_launch_any(c, mode, tdd_any_list_bytes(b), n, count + k, slot + (long)k * n, frame + (long)k * n, st.bbox, box + (long)k * n, clamp);
+            const int r = mot_ctx_kcf_launch_any(c, mode, tdd_any_list_bytes(b), n, count + k, slot + (long)k * n, frame + (long)k * n, st.bbox, box + (long)k * n, clamp, nullptr, 0, 0);
+            if (r) return r;
+        }
+        if (st.any_on[3]) {
+            const int k = 12;
+            const int r = mot_ctx_kcf_launch_any(c, mode, tdd_any_list_bytes(2), n, count + k, slot + (long)k * n, frame + (long)k * n, st.bbox, box + (long)k * n, clamp,
+                                                 t->d_strip, st.strip_floats, t->strip_ctas);
             if (r) return r;
         }
         return 0;
@@ -462,14 +480,16 @@ int mot_tdd_kcf_windows(mot_tdd_t *t, int n, const int *rows, const int *cols)
     if (!t || n < 0 || (n && (!rows || !cols))) return mot_fail(MOT_ERR_ARG, "mot_tdd_kcf_windows: bad argument");
     if (!t->st.kcf) return mot_fail(MOT_ERR_KIND, "not a KCF frame loop");
     static const int side[3] = { 8, 16, 32 };
-    int keep[9] = { 0 }, any_keep[3] = { 0 };
+    int keep[9] = { 0 }, any_keep[4] = { 0 };
     for (int i = 0; i < n; ++i) {
         const int hr = rows[i] / KCF_CELL, wc = cols[i] / KCF_CELL;
         int hi = -1, wi = -1;
         for (int q = 0; q < 3; ++q) { if (hr == side[q]) hi = q; if (wc == side[q]) wi = q; }
         if (hi >= 0 && wi >= 0) { keep[3 * hi + wi] = 1; continue; }
         const AnyGeo g = (hr >= 2 && wc >= 2) ? any_geo(hr, wc, t->st.lut_floats) : AnyGeo{};
-        if (hr < 2 || wc < 2 || !g.ok || g.strips || g.S > NB_MAX) return mot_fail(MOT_ERR_SHAPE, "window %dx%d px: no fused kernel holds it (2x2 cells up to about 1400 cells)", rows[i], cols[i]);
+        if (hr < 2 || wc < 2 || !g.ok || g.S > t->st.bins_max || (g.strips && 18L * g.os > t->st.strip_floats))
+            return mot_fail(MOT_ERR_SHAPE, "window %dx%d px: no fused kernel holds it (2x2 cells up to about 8000 cells) or its %d spectrum bins exceed the slot size %d (mot_ctx_reserve_window)", rows[i], cols[i], g.S, t->st.bins_max);
+        if (g.strips) { any_keep[3] = 1; continue; }
         const size_t bytes = (size_t)g.total * 4;
         any_keep[bytes <= tdd_any_list_bytes(0) ? 0 : bytes <= tdd_any_list_bytes(1) ? 1 : 2] = 1;
     }
@@ -479,7 +499,7 @@ int mot_tdd_kcf_windows(mot_tdd_t *t, int n, const int *rows, const int *cols)
             if (!keep[3 * hi + wi]) id = -1;
             else if (id < 0) { const int rc = mot_ctx_kcf_class(t->ctx, side[hi], side[wi], &id); if (rc) return rc; }
         }
-    for (int b = 0; b < 3; ++b) t->st.any_on[b] = any_keep[b];
+    for (int b = 0; b < 4; ++b) t->st.any_on[b] = any_keep[b];
     return 0;
 }
 

@@ -28,7 +28,7 @@ def make_chain(dets):
     return c
 
 EXPORTS = [
-    "mot_ctx_create", "mot_ctx_destroy", "mot_ctx_set_kcf_options", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
+    "mot_ctx_create", "mot_ctx_destroy", "mot_ctx_set_kcf_options", "mot_ctx_reserve_window", "mot_last_error", "mot_ctx_set_stream", "mot_sync", "mot_ctx_kind", "mot_launch_count",
     "mot_frame_upload", "mot_frame_bind_device", "mot_frame_download", "mot_overlay_batch", "mot_track_color", "mot_yolo_post", "mot_tracker_new_batch", "mot_tracker_delete_batch", "mot_tracker_spawnable",
     "mot_predict_batch", "mot_update_batch", "mot_track_batch", "mot_predict_batch_dev", "mot_update_batch_dev", "mot_predict_gray", "mot_update_gray",
     "mot_crop_gray_resize", "mot_rgb2gray_host", "mot_resize_gray_host", "mot_associate_batch", "mot_assign_batch", "mot_associate_batch_dev",
@@ -166,6 +166,10 @@ class Context:
             _fields_ = [("gaussian_kernel", C.c_int), ("kernel_sigma", C.c_float), ("subpixel_peak", C.c_int), ("padding", C.c_float), ("output_sigma_factor", C.c_float)]
         o = Opt(1 if gaussian else 0, sigma, 1 if subpixel else 0, padding, osf)
         _chk(lib().mot_ctx_set_kcf_options(self.h, C.byref(o)))
+
+    def reserve_window(self, max_rows, max_cols):
+        """Size the model arena for windows up to max_rows x max_cols px (mot_ctx_reserve_window); before the first tracker."""
+        _chk(lib().mot_ctx_reserve_window(self.h, int(max_rows), int(max_cols)))
 
     def set_stream(self, cuda_stream_ptr):
         _chk(lib().mot_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

@@ -230,6 +230,54 @@ def test_device_resident_kcf_loop_with_detections_of_any_size(oracle):
     ctx.close()
 
 
+def test_device_resident_kcf_loop_spawns_strip_mode_windows(oracle):
+    """Detections the size of real detector boxes (150..300 px per side: 1400..5600 cells, beyond one CTA's shared memory) are born on
+    the device too: the strip-mode job list of the any-size kernel with the loop's own per-CTA scratch, models in an arena sized by
+    mot_ctx_reserve_window.  Trace-identical to the oracle's loop; nothing is dropped.  Without the reservation the same detections
+    whose spectra exceed the default slot are counted as dropped and nothing else happens."""
+    require_gpu()
+    M = mot()
+    W, H, cap = 1280, 720, 8
+    sc = Scene(314, W, H, 3, tsize=110, win=160)
+    ctx = M.Context(W, H, max_tracks=cap, n_frame_slots=2, kind=M.TRACKER_KCF)
+    ctx.reserve_window(320, 320)
+    loop = M.DeviceLoop(ctx, 1, cap=cap, max_det=8, cost_mode=0)
+    ref = oracle.td_new("kcf", W, H, cap, 0)
+    rng = np.random.default_rng(5)
+    grow = np.array([[0, 60], [139, 20], [40, 110]])                              # 160x220, 299x180, 200x270 px windows (40x55, 74x45, 50x67 cells)
+    for f in range(6):
+        sc.step()
+        frame = sc.render()
+        d = sc.windows(jitter=1)
+        jig = rng.integers(-2, 3, size=(3, 2))
+        d["r"] = np.clip(d["r"] + grow[:, 0] + jig[:, 0], d["l"] + 16, W - 1)
+        d["b"] = np.clip(d["b"] + grow[:, 1] + jig[:, 1], d["t"] + 16, H - 1)
+        if f == 3:
+            d = d[:2]
+        d = np.ascontiguousarray(d)
+        ctx.upload(f & 1, frame)
+        loop.frame_base(f & 1)
+        loop.step([d])
+        ref.step(frame, d)
+        a, b = loop.tracks(0), ref.tracks()
+        assert len(a["tid"]) >= 2
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (f, k)
+    assert loop.dropped(0) == 0
+    from test_any_plan import plan
+    plans = [plan((int(b["b"] - b["t"] + 1)) // 4, (int(b["r"] - b["l"] + 1)) // 4) for b in d]
+    assert any(p["strips"] for p in plans), "the test must reach strip mode"
+    loop.close(); ref.close(); ctx.close()
+    # the default arena: 1152 bins per slot
+    ctx = M.Context(W, H, max_tracks=cap, n_frame_slots=2, kind=M.TRACKER_KCF)
+    loop = M.DeviceLoop(ctx, 1, cap=cap, max_det=8, cost_mode=0)
+    ctx.upload(0, frame)
+    loop.step([d])
+    big = sum(((int(b["r"] - b["l"] + 1)) // 4) * (((int(b["b"] - b["t"] + 1)) // 4) // 2 + 1) > 1152 for b in d)
+    assert big >= 2 and loop.dropped(0) == big and len(loop.tracks(0)["tid"]) == len(d) - big
+    loop.close(); ctx.close()
+
+
 def test_detector_wire_format_gives_the_same_trace(oracle):
     """detections arrive as bbox_chain_t (top/cnntype.h:43-47), in batches of up to four frames as tensorRunB delivers
     them (top/td.cpp:178-204).  Feeding chains -- one by one, batched, and to the device-resident loop -- gives exactly the track tables
