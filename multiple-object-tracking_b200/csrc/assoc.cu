@@ -59,7 +59,8 @@ struct MunkresSmem {
     uint32_t *cand, *candAll; // columns that may hold an UNCOVERED zero (superset) / that hold any zero
     uint32_t *Zr;           // [nR][nWc] row-major copy of the zero bitmap for the greedy start (null when it does not fit)
     int *starOfRow, *starOfCol, *primeOfRow;
-    double *redd;           // [16] reduction scratch
+    double *redd;           // [32] reduction scratch
+    double *rmin;           // [1024] partial row minima of the reduction pass
     int *ctrl;              // [4]: 0 = control word, 1 = aug row, 2 = aug col
 };
 
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
         unsigned char *q = smem_raw;
         s.mat = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)smem_mat_doubles;
         s.redd = reinterpret_cast<double *>(q); q += sizeof(double) * 32;
+        s.rmin = reinterpret_cast<double *>(q); q += sizeof(double) * 1024;
         s.Zc = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * (size_t)md * (mdW | 1);
         s.covR = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
         s.covC = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * mdW;
@@ -125,34 +127,81 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
     }
     double *const d = ((long)nR * nC <= smem_mat_doubles) ? s.mat : p.work + (long)m * p.work_stride;
 
-    // working copy (hungarian.cpp:41-54) and state
-    for (int i = tid; i < nR * nC; i += NT) d[i] = distIn[i];
+    // state
     for (int i = tid; i < nR; i += NT) { s.starOfRow[i] = -1; s.primeOfRow[i] = -1; assign[i] = -1; }
     for (int i = tid; i < nC; i += NT) s.starOfCol[i] = -1;
     for (int i = tid; i < mdW; i += NT) { s.covR[i] = 0; s.covC[i] = 0; }
-    __syncthreads();
 
-    // reduction (hungarian.cpp:65-89 rows, :104-124 columns)
+    // Working copy (hungarian.cpp:41-54) + reduction (:65-89 rows, :104-124 columns) + zero bitmap in TWO passes over the input with
+    // eight independent loads in flight per thread (the passes are latency-bound: a 256 x 256 matrix is 512 KB in L2).  The minimum
+    // of a row / column is taken in any order: `v < mn` over all entries gives the same value whatever the order (the sign of a
+    // zero minimum may differ, which no later comparison can see).
+    constexpr int UR = 8;
     if (nR <= nC) {
-        for (int r = tid; r < nR; r += NT) {
-            double mn = d[r];
-            for (int c = 1; c < nC; ++c) { const double v = d[r + (long)nR * c]; if (v < mn) mn = v; }
-            for (int c = 0; c < nC; ++c) d[r + (long)nR * c] = __dsub_rn(d[r + (long)nR * c], mn);
+        // warp = (32-row word w, column group g): a contiguous run of columns per group; per-lane running minimum, groups combined
+        // through shared memory.  The second pass also collects, per lane = per row, the zero bits of the columns it visits and
+        // ORs them word by word into the row-major bitmap Zr that the greedy start reads (no separate transposition pass).
+        const int G = NW / nWr, w = warp % nWr, g = warp / nWr, r = (w << 5) + lane;
+        const int per = (nC + G - 1) / G, cbeg = g * per, cend = min(nC, cbeg + per);
+        const bool on = g < G && r < nR;
+        double mn = INFINITY;
+        if (s.Zr) for (int i = tid; i < nR * nWc; i += NT) s.Zr[i] = 0u;
+        if (g < G) {
+            for (int c0 = cbeg; c0 < cend; c0 += UR) {
+                double v[UR];
+#pragma unroll
+                for (int u = 0; u < UR; ++u) { const int c = c0 + u; v[u] = (on && c < cend) ? distIn[r + (long)nR * c] : INFINITY; }
+#pragma unroll
+                for (int u = 0; u < UR; ++u) if (v[u] < mn) mn = v[u];
+            }
+            s.rmin[g * (nWr << 5) + (w << 5) + lane] = mn;
+        }
+        __syncthreads();
+        if (g < G) {
+            mn = s.rmin[(w << 5) + lane];
+            for (int q = 1; q < G; ++q) { const double o = s.rmin[q * (nWr << 5) + (w << 5) + lane]; if (o < mn) mn = o; }
+            uint32_t acc = 0; int cw = cbeg >> 5;
+            for (int c0 = cbeg; c0 < cend; c0 += UR) {
+                double v[UR];
+#pragma unroll
+                for (int u = 0; u < UR; ++u) { const int c = c0 + u; v[u] = (on && c < cend) ? distIn[r + (long)nR * c] : 1.0; }
+#pragma unroll
+                for (int u = 0; u < UR; ++u) {
+                    const int c = c0 + u;
+                    if (c >= cend) break;                                  // warp-uniform
+                    const double x = __dsub_rn(v[u], mn);
+                    if (on) d[r + (long)nR * c] = x;
+                    const bool z = on && fabs(x) < DBL_EPSILON;
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
+                    if (lane == 0) s.Zc[c * zs + w] = word;
+                    if ((c >> 5) != cw) { if (s.Zr && acc) atomicOr(&s.Zr[r * nWc + cw], acc); acc = 0; cw = c >> 5; }
+                    acc |= (z ? 1u : 0u) << (c & 31);
+                }
+            }
+            if (s.Zr && acc) atomicOr(&s.Zr[r * nWc + cw], acc);
         }
     } else {
-        for (int c = tid; c < nC; c += NT) {
-            double *col = d + (long)nR * c, mn = col[0];
-            for (int r = 1; r < nR; ++r) if (col[r] < mn) mn = col[r];
-            for (int r = 0; r < nR; ++r) col[r] = __dsub_rn(col[r], mn);
+        // one warp per column, lanes along the rows
+        for (int c = warp; c < nC; c += NW) {
+            const double *col = distIn + (long)nR * c;
+            double mn = INFINITY;
+            for (int r0 = lane; r0 < nR; r0 += 32 * UR) {
+                double v[UR];
+#pragma unroll
+                for (int u = 0; u < UR; ++u) { const int r = r0 + 32 * u; v[u] = r < nR ? col[r] : INFINITY; }
+#pragma unroll
+                for (int u = 0; u < UR; ++u) if (v[u] < mn) mn = v[u];
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_xor_sync(0xFFFFFFFFu, mn, off); if (o < mn) mn = o; }
+            for (int w = 0; w < nWr; ++w) {
+                const int r = (w << 5) + lane;
+                bool z = false;
+                if (r < nR) { const double x = __dsub_rn(col[r], mn); d[r + (long)nR * c] = x; z = fabs(x) < DBL_EPSILON; }
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
+                if (lane == 0) s.Zc[c * zs + w] = word;
+            }
         }
-    }
-    __syncthreads();
-    // zero bitmap
-    for (int task = warp; task < nC * nWr; task += NW) {
-        const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
-        const bool z = (r < nR) && (fabs(d[r + (long)nR * c]) < DBL_EPSILON);
-        const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
-        if (lane == 0) s.Zc[c * zs + w] = word;
     }
     __syncthreads();
     // Column filters for step 3: candAll = columns with a zero, cand = columns with a zero in an uncovered row.  While step 3
@@ -168,19 +217,39 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
         }
     };
     refresh_candidates();
-    if (s.Zr && nR <= nC) {
-        // row-major copy of the bitmap: row r, word w = columns 32w..32w+31
-        for (int task = warp; task < nR * nWc; task += NW) {
-            const int r = task / nWc, w = task - r * nWc, c = (w << 5) + lane;
-            const bool z = (c < nC) && ((s.Zc[c * zs + (r >> 5)] >> (r & 31)) & 1u);
-            const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
-            if (lane == 0) s.Zr[r * nWc + w] = word;
-        }
-    }
     __syncthreads();
 
-    // greedy initial stars (hungarian.cpp:91-101 / :126-140) -- sequential by nature, one warp
-    if (warp == 0) {
+    // Greedy initial stars (hungarian.cpp:91-101 / :126-140) are sequential by nature: row r takes its first zero column that no
+    // earlier row took.  When the FIRST zero columns of all rows are distinct -- the normal case of tracking, where every track has
+    // its own nearest detection -- that is what the greedy does for every row (by induction no earlier row can have covered it), so
+    // all rows star their first zero in parallel and only a collision falls back to the one-warp sequential form.
+    bool stars_done = false;
+    if (nR <= nC && s.Zr) {
+        if (tid == 0) s.ctrl[3] = 0;
+        __syncthreads();
+        for (int r = tid; r < nR; r += NT) {
+            int f = -1;
+            for (int w = 0; w < nWc; ++w) { const uint32_t word = s.Zr[r * nWc + w]; if (word) { f = (w << 5) + __ffs(word) - 1; break; } }
+            if (f >= 0) {
+                if (atomicCAS(&s.starOfCol[f], -1, r) != -1) s.ctrl[3] = 1;
+                else s.starOfRow[r] = f;
+            }
+        }
+        __syncthreads();
+        stars_done = s.ctrl[3] == 0;
+        if (stars_done) {
+            for (int cb = warp * 32; cb < nC; cb += NT) {
+                const int c = cb + lane;
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, c < nC && s.starOfCol[c] >= 0);
+                if (lane == 0) s.covC[cb >> 5] = word;
+            }
+        } else {
+            for (int i = tid; i < nR; i += NT) s.starOfRow[i] = -1;
+            for (int i = tid; i < nC; i += NT) s.starOfCol[i] = -1;
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && !stars_done) {
         if (nR <= nC && s.Zr) {
             // first uncovered zero column of each row, rows ascending (hungarian.cpp:91-101): one ballot per row
             for (int r = 0; r < nR; ++r) {
@@ -371,9 +440,21 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
     if (tid == 0) {
         double cst = 0.0;
         if (fail) cst = nan("");
-        else for (int r = 0; r < nR; ++r) {
+        else if (stage) {
+            // unassigned rows hold +0.0, and x + 0.0 == x for every x this sum can reach (it starts at +0.0, so it is never -0.0):
+            // no branch, loads ahead of the chain of additions
+            int r = 0;
+            for (; r + 8 <= nR; r += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = rowcost[r + u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cst = __dadd_rn(cst, v[u]);
+            }
+            for (; r < nR; ++r) cst = __dadd_rn(cst, rowcost[r]);
+        } else for (int r = 0; r < nR; ++r) {
             const int c = s.starOfRow[r];
-            if (c >= 0) cst = __dadd_rn(cst, stage ? rowcost[r] : distIn[r + (long)nR * c]);
+            if (c >= 0) cst = __dadd_rn(cst, distIn[r + (long)nR * c]);
         }
         p.cost[m] = cst;
     }
@@ -382,7 +463,7 @@ __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const Assoc
 static size_t munkres_smem(int md, int mat_doubles)
 {
     const int mdW = (md + 31) >> 5;
-    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * 32 + sizeof(uint32_t) * ((size_t)md * (mdW | 1) + 4 * mdW + (md <= 512 ? (size_t)md * mdW : 0)) +
+    return sizeof(double) * (size_t)mat_doubles + sizeof(double) * (32 + 1024) + sizeof(uint32_t) * ((size_t)md * (mdW | 1) + 4 * mdW + (md <= 512 ? (size_t)md * mdW : 0)) +
            sizeof(int) * (3 * (size_t)md + 4);
 }
 
