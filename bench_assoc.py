@@ -172,6 +172,9 @@ def config1(args):
     frames = []
     for f in range(F):
         frames.append(sc.render()); sc.step()
+    import torch
+    pin = torch.from_numpy(np.stack(frames)).pin_memory().numpy()      # frames in pinned host memory (pageable: the driver stages every upload)
+    frames = [pin[f] for f in range(F)]
     b = boxes_array(1); b["l"], b["t"], b["r"], b["b"], b["type"], b["score"] = 256, 176, 383, 303, 1, 1.0
     ctx = M.Context(W, H, max_tracks=2, n_frame_slots=1, kind=M.TRACKER_KCF)
     ctx.upload(0, frames[0]); h = ctx.new(b); ctx.update(h, [0], b)
@@ -218,6 +221,11 @@ def config3(args):
     frames, dets = [], []
     for f in range(F):
         sc.step(); frames.append(sc.render()); dets.append(sc.windows(jitter=2))
+    # the timed loops read their frames from PINNED host memory (like bench.py's e2e leg); the same loop fed from pageable arrays,
+    # where every upload is staged by the driver (a 6.2 MB host memcpy per frame), is reported next to it
+    import torch
+    pin = torch.from_numpy(np.stack(frames)).pin_memory().numpy()
+    pageable, frames = frames, [pin[f] for f in range(F)]
     out = {}
     ctx = M.Context(W, H, max_tracks=512, n_frame_slots=1, kind=M.TRACKER_KCF)
     td = ctx.td(0, cap=256, cost_mode=0)
@@ -242,6 +250,16 @@ def config3(args):
             dev_tab = loop.tracks(0)
     ctx.sync()
     out["gpu_frames_per_s_device_loop"] = (F - WARM) / (time.perf_counter() - t0)
+    loop.close(); ctx.close()
+    ctx = M.Context(W, H, max_tracks=256, n_frame_slots=2, kind=M.TRACKER_KCF)
+    loop = M.DeviceLoop(ctx, 1, cap=256, max_det=256, cost_mode=0)
+    loop.kcf_windows([(128, 128)])
+    for f in range(F):
+        if f == WARM:
+            ctx.sync(); t0 = time.perf_counter()
+        ctx.upload(f & 1, pageable[f]); loop.frame_base(f & 1); loop.step([dets[f]])
+    ctx.sync()
+    out["gpu_frames_per_s_device_loop_pageable_frames"] = (F - WARM) / (time.perf_counter() - t0)
     loop.close(); ctx.close()
     orc = oraclelib.Oracle(oraclelib.best())
     ref = orc.td_new("kcf", W, H, 256, 0)

@@ -23,6 +23,9 @@
 // mot_ctx_reserve_window raises it) -- are skipped and counted (mot_tdd_dropped); the host-side loop (host/td_loop.cpp) serves the
 // last two kinds through individually allocated models and the unfused path.
 #include "mot_ctx.h"
+#include "kalman.cuh"
+#include "assoc.cuh"
+#include <cstdlib>
 
 namespace mot {
 
@@ -91,10 +94,9 @@ __global__ void td_joblist_kernel(TddState st)
 }
 
 // scatter of the assignment + bookkeeping of assigned / unassigned tracks (top/td.cpp:472-502, 512-556)
-__global__ void td_scatter_kernel(TddState st, const mot_bbox_t *dets, const int *ndet)
+__device__ __forceinline__ void td_scatter_cta(const TddState &st, const mot_bbox_t *dets, const int *ndet, int *at /* [1024] shared */)
 {
     const int s = blockIdx.x, T = st.ntracks[s], D = ndet[s];
-    __shared__ int at[1024];
     for (int i = threadIdx.x; i < T; i += blockDim.x) at[i] = -1;
     for (int j = threadIdx.x; j < D; j += blockDim.x) st.assigned_detected[(long)s * st.max_det + j] = -1;
     __syncthreads();
@@ -112,9 +114,15 @@ __global__ void td_scatter_kernel(TddState st, const mot_bbox_t *dets, const int
     }
 }
 
-// Exclusive scan of 0/1 flags v[0..n), n <= 1024, by a CTA of 256 threads (four consecutive entries per thread, warp shuffles,
-// one pass over the eight warp totals): on return v[i] = number of set flags before i; returns the number of set flags.
-__device__ int block_scan_flags(int *v, int n, int *wsum /* [9] shared */)
+__global__ void td_scatter_kernel(TddState st, const mot_bbox_t *dets, const int *ndet)
+{
+    __shared__ int at[1024];
+    td_scatter_cta(st, dets, ndet, at);
+}
+
+// Exclusive scan of 0/1 flags v[0..n), n <= 1024, by a CTA of 256..1024 threads (four consecutive entries per thread, warp shuffles,
+// one pass over the warp totals): on return v[i] = number of set flags before i; returns the number of set flags.
+__device__ int block_scan_flags(int *v, int n, int *wsum /* [33] shared */)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int a[4];
@@ -127,12 +135,13 @@ __device__ int block_scan_flags(int *v, int n, int *wsum /* [9] shared */)
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        const int w = lane < 8 ? wsum[lane] : 0;
+        const int nw = blockDim.x >> 5;
+        const int w = lane < nw ? wsum[lane] : 0;
         int winc = w;
 #pragma unroll
-        for (int off = 1; off < 8; off <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, winc, off); if (lane >= off) winc += t; }
-        if (lane < 8) wsum[lane] = winc - w;
-        if (lane == 7) wsum[8] = winc;
+        for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, winc, off); if (lane >= off) winc += t; }
+        if (lane < nw) wsum[lane] = winc - w;
+        if (lane == 31) wsum[32] = winc;
     }
     __syncthreads();
     const int base = wsum[warp] + inc - sum;
@@ -140,18 +149,17 @@ __device__ int block_scan_flags(int *v, int n, int *wsum /* [9] shared */)
 #pragma unroll
     for (int q = 0; q < 4; ++q) { const int i = 4 * tid + q; if (i < n) v[i] = base + ex[q]; }
     __syncthreads();
-    return wsum[8];
+    return wsum[32];
 }
 
 // delete lost tracks with stable compaction (top/td.cpp:585-609), then spawn (top/td.cpp:612-644)
-__global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox_t *dets, const int *ndet)
+__device__ __forceinline__ void td_lifecycle_cta(const TddState &st, const KalmanState &kal, const mot_bbox_t *dets, const int *ndet, int *sm /* [3072] shared */)
 {
     const int s = blockIdx.x, T = st.ntracks[s], D = ndet[s], cap = st.cap, tid = threadIdx.x, NTH = blockDim.x;
-    extern __shared__ int sm[];
     int *pos = sm;                    // [cap] new position of a kept track / [max_det] rank of a spawning detection
     int *freeid = sm + 1024;          // [cap] free local slot ids in ascending order
     int *flag = sm + 2048;            // [1024] scratch flags of the scans
-    __shared__ int wsum[9];
+    __shared__ int wsum[33];
     // ---- keep flags and their exclusive scan -------------------------------------------------------------------------------
     for (int i = tid; i < T; i += NTH) {
         const long o = (long)s * cap + i;
@@ -242,6 +250,67 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
     if (tid == 0) { st.ntracks[s] = n2 + spawned; st.tracker_id[s] = id0 + (uint32_t)spawned; }
 }
 
+__global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox_t *dets, const int *ndet)
+{
+    extern __shared__ int sm[];
+    td_lifecycle_cta(st, kal, dets, ndet, sm);
+}
+
+// ---- the Kalman kind's whole frame in ONE launch: a CTA per stream runs predict (+clamp), the cost matrix, the Munkres solver, the
+// scatter + bookkeeping, the update and the lifecycle back to back (the phases of one stream only depend on each other, and a few
+// hundred tracks are a CTA's worth of work), so a frame costs one launch latency instead of six.  Same device code as the separate
+// kernels (kalman.cuh, assoc.cuh, the *_cta functions above): the results are the same bit for bit.
+constexpr int TDF_THREADS = 256;      // 255 registers per thread: the Kalman update keeps its 6x6 FP64 algebra in registers (no spills)
+struct TdFrameArgs { double *dist, *work, *cost; int cost_mode; double screen_dis; int mat_doubles; };
+
+__global__ void __launch_bounds__(TDF_THREADS, 1) td_frame_kalman_kernel(TddState st, KalmanState kal, const mot_bbox_t *dets, const int *ndet, TdFrameArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int at[1024];
+    const int s = blockIdx.x, tid = threadIdx.x, cap = st.cap, md = st.md;
+    const int T = st.ntracks[s], D = ndet[s];
+    mot_bbox_t *const trk = st.bbox + (long)s * cap;
+    const mot_bbox_t *const det = dets + (long)s * st.max_det;
+    // predict + clamp (top/td.cpp:344-384)
+    for (int i = tid; i < cap; i += TDF_THREADS) { const int sl = st.slot[(long)s * cap + i]; if (sl >= 0) kalman_predict_one(kal, sl, trk + i, 1, st.frame_w, st.frame_h); }
+    __syncthreads();
+    // cost matrix (top/td.cpp:386-457), column-major with rows = the smaller side.  The boxes are staged in shared memory (the
+    // solver's area, not yet in use) and a thread keeps ONE row, so a cell costs no division and no global load, and four cells
+    // are in flight per thread (the FP64 square root is a long dependent chain).
+    double *const dist = a.dist + (long)s * md * md;
+    {
+        mot_bbox_t *const sb = reinterpret_cast<mot_bbox_t *>(smem_raw);            // [T] track boxes, then [D] detections: <= 2 * 256 * 24 bytes
+        for (int i = tid; i < T; i += TDF_THREADS) sb[i] = trk[i];
+        for (int j = tid; j < D; j += TDF_THREADS) sb[T + j] = det[j];
+        __syncthreads();
+        const int nR = T < D ? T : D, nC = T < D ? D : T;
+        const mot_bbox_t *const rowb = T < D ? sb : sb + T, *const colb = T < D ? sb + T : sb;      // rows = trackers when T < D, else detections
+        if (nR > 0) {                                                                                  // nR <= md <= TDF_THREADS (checked at creation)
+            const int G = TDF_THREADS / nR, r = tid % nR, g = tid / nR;                                 // column groups when there are threads to spare
+            if (g < G) {
+                const mot_bbox_t rb = rowb[r];
+                for (int c0 = g; c0 < nC; c0 += 4 * G) {
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int c = c0 + u * G; if (c < nC) v[u] = T < D ? cost_cell(rb, colb[c], a.cost_mode, a.screen_dis) : cost_cell(colb[c], rb, a.cost_mode, a.screen_dis); }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int c = c0 + u * G; if (c < nC) dist[r + (long)nR * c] = v[u]; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // assignment (trackers/hungarian/hungarian.cpp:29-368)
+    munkres_cta<TDF_THREADS>(dist, a.work + (long)s * md * md, T < D ? T : D, T < D ? D : T, md, st.assign + (long)s * md, a.cost + s, smem_raw, a.mat_doubles);
+    __syncthreads();
+    td_scatter_cta(st, dets, ndet, at);
+    __syncthreads();
+    // update with the assigned detection, or with the predicted box itself (top/td.cpp:539, 581)
+    for (int i = tid; i < cap; i += TDF_THREADS) { const int sl = st.slot[(long)s * cap + i]; if (sl >= 0) kalman_update_one(kal, sl, trk[i]); }
+    __syncthreads();
+    td_lifecycle_cta(st, kal, dets, ndet, reinterpret_cast<int *>(smem_raw));
+}
+
 }  // namespace mot
 
 using namespace mot;
@@ -251,12 +320,17 @@ struct mot_tdd_s {
     TddState st{};
     int cost_mode;
     double *d_dist = nullptr, *d_cost = nullptr, *d_work = nullptr;      // cost matrices, totals, the solver's working copy (owned: graph-safe)
+    bool fused_frame = false;                                            // Kalman kind: the whole frame in one launch (td_frame_kalman_kernel)
     float *d_strip = nullptr; int strip_ctas = 0;                        // strip-mode list: per-CTA histogram scratch (L2-resident)
-    DevBuf<mot_bbox_t> d_dets; DevBuf<int> d_ndet;
-    PinBuf<mot_bbox_t> h_dets; PinBuf<int> h_ndet;
-    // The host-array step is launch-latency bound (two copies + six kernels for a few hundred tracks): its fixed sequence is
-    // captured once into a CUDA graph and replayed.
-    cudaGraphExec_t graph = nullptr;
+    // Host-array steps: detections are staged in pinned memory and uploaded.  Two staging sets used alternately, each with its own
+    // "consumed" event, so that the host prepares step k+1 while step k runs and only ever waits for step k-1.
+    DevBuf<mot_bbox_t> d_dets[2]; DevBuf<int> d_ndet[2];
+    PinBuf<mot_bbox_t> h_dets[2]; PinBuf<int> h_ndet[2];
+    cudaEvent_t consumed[2] = { nullptr, nullptr };
+    int flip = 0;
+    // The host-array step of the Kalman kind is launch-latency bound (two copies + six kernels for a few hundred tracks): its fixed
+    // sequence is captured once per staging set into a CUDA graph and replayed.
+    cudaGraphExec_t graph[2] = { nullptr, nullptr };
     cudaStream_t graph_stream = nullptr;
 };
 
@@ -271,8 +345,11 @@ static void tdd_release(mot_tdd_t *t)
     cudaFree(st.bbox); cudaFree(st.assign); cudaFree(st.assigned_detected); cudaFree(t->d_dist); cudaFree(t->d_cost); cudaFree(t->d_work);
     cudaFree(st.jl_slot); cudaFree(st.jl_frame); cudaFree(st.jl_box); cudaFree(st.sp_slot); cudaFree(st.sp_frame); cudaFree(st.sp_box);
     cudaFree(st.jl_count); cudaFree(st.dropped); cudaFree(t->d_strip);
-    if (t->graph) cudaGraphExecDestroy(t->graph);
-    t->d_dets.release(); t->d_ndet.release(); t->h_dets.release(); t->h_ndet.release();
+    for (int q = 0; q < 2; ++q) {
+        if (t->graph[q]) cudaGraphExecDestroy(t->graph[q]);
+        if (t->consumed[q]) cudaEventDestroy(t->consumed[q]);
+        t->d_dets[q].release(); t->d_ndet[q].release(); t->h_dets[q].release(); t->h_ndet[q].release();
+    }
 }
 
 // every allocation of a loop object; on failure the caller releases whatever was obtained (all pointers start out null)
@@ -326,6 +403,10 @@ int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int ma
     t->ctx = c; t->cost_mode = cost_mode;
     const int rc = tdd_alloc(t, c, n_streams, cap, max_det, kcf);
     if (rc) { tdd_release(t); delete t; return rc; }
+    if (!kcf && t->st.md <= TDF_THREADS && !getenv("MOT_TDD_UNFUSED")) {      // larger problems want the 1024-thread solver: separate launches
+        const size_t bytes = std::max(munkres_smem_bytes(t->st.md, munkres_mat_doubles(t->st.md)), sizeof(int) * 3072);
+        t->fused_frame = cudaFuncSetAttribute((const void *)td_frame_kalman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+    }
     for (long i = 0; i < (long)n_streams * cap; ++i) c->used[i] = 1;        // these slots now belong to the device-side tables
     c->free_slots.erase(std::remove_if(c->free_slots.begin(), c->free_slots.end(), [&](int s) { return s < n_streams * cap; }), c->free_slots.end());
     *out = t;
@@ -391,6 +472,14 @@ int mot_tdd_step_dev(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet)
     CU(cudaSetDevice(c->device));
     const int n = st.S * st.cap;
     if (st.kcf) return tdd_step_kcf(t, d_dets, d_ndet);
+    if (t->fused_frame) {
+        TdFrameArgs a{ t->d_dist, t->d_work, t->d_cost, t->cost_mode, 1.0 / (double)c->W, munkres_mat_doubles(st.md) };
+        const size_t bytes = std::max(munkres_smem_bytes(st.md, a.mat_doubles), sizeof(int) * 3072);
+        td_frame_kalman_kernel<<<st.S, TDF_THREADS, bytes, c->stream>>>(st, c->kal, d_dets, d_ndet, a);
+        CU(cudaGetLastError());
+        c->launches += 1;
+        return 0;
+    }
     int rc = kalman_predict(c->kal, n, st.slot, st.bbox, 1, c->W, c->H, c->stream);
     if (rc) return mot_fail(MOT_ERR_CUDA, "kalman_predict launch failed (%d)", rc);
     rc = mot_ctx_associate_dev(c, st.S, st.ntracks, d_ndet, st.bbox, st.cap, d_dets, st.max_det, t->cost_mode,
@@ -411,39 +500,51 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
     if (!t || !dets || !ndet) return mot_fail(MOT_ERR_ARG, "mot_tdd_step: null argument");
     mot_ctx_t *c = t->ctx; TddState &st = t->st;
     CU(cudaSetDevice(c->device));
-    CU(t->h_dets.ensure((size_t)st.S * st.max_det)); CU(t->d_dets.ensure((size_t)st.S * st.max_det)); CU(t->h_ndet.ensure(st.S)); CU(t->d_ndet.ensure(st.S));
-    CU(cudaStreamSynchronize(c->stream));        // the staging buffers of the previous step have been consumed
-    for (int s = 0; s < st.S; ++s) {
+    for (int s = 0; s < st.S; ++s)
         if (ndet[s] < 0 || ndet[s] > st.max_det) return mot_fail(MOT_ERR_ARG, "stream %d has %d detections (max %d)", s, ndet[s], st.max_det);
-        t->h_ndet.p[s] = ndet[s];
-        if (ndet[s]) memcpy(t->h_dets.p + (size_t)s * st.max_det, dets[s], sizeof(mot_bbox_t) * ndet[s]);
+    const int q = t->flip; t->flip ^= 1;
+    const bool fresh = t->h_dets[q].n < (size_t)st.S * st.max_det;      // first use of this staging set: its graph (if any) is stale
+    CU(t->h_dets[q].ensure((size_t)st.S * st.max_det)); CU(t->d_dets[q].ensure((size_t)st.S * st.max_det)); CU(t->h_ndet[q].ensure(st.S)); CU(t->d_ndet[q].ensure(st.S));
+    if (!t->consumed[q]) CU(cudaEventCreateWithFlags(&t->consumed[q], cudaEventDisableTiming));
+    else CU(cudaEventSynchronize(t->consumed[q]));   // the step that last used this staging set (two steps ago) has read it
+    for (int s = 0; s < st.S; ++s) {
+        t->h_ndet[q].p[s] = ndet[s];
+        if (ndet[s]) memcpy(t->h_dets[q].p + (size_t)s * st.max_det, dets[s], sizeof(mot_bbox_t) * ndet[s]);
     }
+    const size_t det_bytes = sizeof(mot_bbox_t) * (size_t)st.S * st.max_det;
     if (st.kcf) {
         // the KCF sequence waits for frame uploads recorded on another stream, which a captured graph would freeze: plain launches
-        CU(cudaMemcpyAsync(t->d_dets.p, t->h_dets.p, sizeof(mot_bbox_t) * (size_t)st.S * st.max_det, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(t->d_ndet.p, t->h_ndet.p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream));
-        return mot_tdd_step_dev(t, t->d_dets.p, t->d_ndet.p);
+        CU(cudaMemcpyAsync(t->d_dets[q].p, t->h_dets[q].p, det_bytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(t->d_ndet[q].p, t->h_ndet[q].p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream));
+        const int rc = mot_tdd_step_dev(t, t->d_dets[q].p, t->d_ndet[q].p);
+        if (rc) return rc;
+        CU(cudaEventRecord(t->consumed[q], c->stream));
+        return 0;
     }
-    if (t->graph && t->graph_stream == c->stream) { CU(cudaGraphLaunch(t->graph, c->stream)); c->launches += 6; return 0; }
-    if (t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
-    // first call (or the stream changed): record the sequence.  Every buffer the captured kernels touch belongs to this loop
-    // object (tables, cost matrices, the solver's working copy) or to the context's fixed Kalman state: nothing a later call on
-    // the context can reallocate.
-    cudaGraph_t g = nullptr;
-    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    cudaError_t e1 = cudaMemcpyAsync(t->d_dets.p, t->h_dets.p, sizeof(mot_bbox_t) * (size_t)st.S * st.max_det, cudaMemcpyHostToDevice, c->stream);
-    cudaError_t e2 = cudaMemcpyAsync(t->d_ndet.p, t->h_ndet.p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream);
-    const long l0 = c->launches;
-    const int rc = (e1 == cudaSuccess && e2 == cudaSuccess) ? mot_tdd_step_dev(t, t->d_dets.p, t->d_ndet.p) : MOT_ERR_CUDA;
-    c->launches = l0;
-    const cudaError_t e3 = cudaStreamEndCapture(c->stream, &g);
-    if (rc || e3 != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); return rc ? rc : mot_fail(MOT_ERR_CUDA, "graph capture of the frame loop failed: %s", cudaGetErrorString(e3)); }
-    const cudaError_t e4 = cudaGraphInstantiate(&t->graph, g, 0);
-    cudaGraphDestroy(g);
-    if (e4 != cudaSuccess) { t->graph = nullptr; return mot_fail(MOT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e4)); }
-    t->graph_stream = c->stream;
-    CU(cudaGraphLaunch(t->graph, c->stream));
-    c->launches += 6;
+    if (t->graph_stream != c->stream || fresh) {
+        for (int k = 0; k < 2; ++k) if ((t->graph_stream != c->stream || k == q) && t->graph[k]) { cudaGraphExecDestroy(t->graph[k]); t->graph[k] = nullptr; }
+        t->graph_stream = c->stream;
+    }
+    if (!t->graph[q]) {
+        // first call with this staging set (or the stream changed): record the sequence.  Every buffer the captured kernels touch
+        // belongs to this loop object (tables, cost matrices, the solver's working copy, the staging set) or to the context's fixed
+        // Kalman state: nothing a later call on the context can reallocate.
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e1 = cudaMemcpyAsync(t->d_dets[q].p, t->h_dets[q].p, det_bytes, cudaMemcpyHostToDevice, c->stream);
+        cudaError_t e2 = cudaMemcpyAsync(t->d_ndet[q].p, t->h_ndet[q].p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream);
+        const long l0 = c->launches;
+        const int rc = (e1 == cudaSuccess && e2 == cudaSuccess) ? mot_tdd_step_dev(t, t->d_dets[q].p, t->d_ndet[q].p) : MOT_ERR_CUDA;
+        c->launches = l0;
+        const cudaError_t e3 = cudaStreamEndCapture(c->stream, &g);
+        if (rc || e3 != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); return rc ? rc : mot_fail(MOT_ERR_CUDA, "graph capture of the frame loop failed: %s", cudaGetErrorString(e3)); }
+        const cudaError_t e4 = cudaGraphInstantiate(&t->graph[q], g, 0);
+        cudaGraphDestroy(g);
+        if (e4 != cudaSuccess) { t->graph[q] = nullptr; return mot_fail(MOT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e4)); }
+    }
+    CU(cudaGraphLaunch(t->graph[q], c->stream));
+    CU(cudaEventRecord(t->consumed[q], c->stream));
+    c->launches += t->fused_frame ? 1 : 6;
     return 0;
 }
 
