@@ -13,6 +13,8 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src)
 }
 // barrier among a subset of the CTA's warps (id 1..15; __syncthreads is id 0)
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// the non-blocking half: signal arrival at named barrier `id` (nthreads = arrivers + waiters) and carry on
+__device__ __forceinline__ void bar_arrive_named(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 

@@ -14,7 +14,7 @@
 //   F   [31*NB]              gray patch -> (M/16, orientation bin) -> packed half spectra of all 31 channels, in place
 //   R1  [18*WC*(HR+1)]       SSE look-up tables (gradient phase) -> 18-bin cell histograms -> Nyquist column, zf, response
 //   MQ  [2 float2 / thread]  cp.async landing slots of the model stream in the column pass
-//   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies (both later: raw transform of the packed DC/Nyquist column);  wy[HR], wx[WC] Hann vectors
+//   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies;  wy[HR], wx[WC] Hann vectors
 // The 31-channel feature tensor is never materialised: each channel column is generated from R1 and N in registers,
 // windowed, transformed (real FFT of HR points as a complex FFT of HR/2) and stored PACKED (DC.re, Nyquist.re share one
 // complex slot), so the column pass is exactly HR/2 complex FFTs per channel: 31*16 = 496 thread-sized transforms at 32x32.
@@ -53,9 +53,10 @@ template <int HR, int WC> struct Geo {
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
     static constexpr int MQ_FLOATS = 4 * KCF_THREADS;      // P5: two model values (float2) per thread in flight through cp.async
-    // P5: raw transform of the packed (DC, Nyquist) column, [31][WC] float2; lives on the dead normalisers + energies when they are big enough
-    static constexpr bool ZB_OWN = 2 * KCF_CHAN * WC > N_FLOATS + NB;
-    static constexpr int ZB_FLOATS = ZB_OWN ? 2 * KCF_CHAN * WC : 0;
+    static constexpr int ZB_FLOATS = 0;                    // (the raw transform of the packed (DC, Nyquist) column stays in its own spectrum slots)
+    // Square grids: channel c is produced (P4b) and column-transformed (P5) by the same aligned group of WC threads, so the barrier
+    // between the two phases is a warp-level one and the fast warps' model streaming overlaps the slow warps' feature generation.
+    static constexpr bool FUSE45 = HR == WC;
     static constexpr int PIX_PER_THREAD = (H0 * W0 + KCF_THREADS - 1) / KCF_THREADS;
     static_assert(3 * CMAX + 30 <= RAW_PITCH, "staged row pitch");
     static_assert((F_FLOATS & 1) == 0, "float2 alignment of the R1 region");
@@ -618,7 +619,13 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             }
         }
     }
-    __syncthreads();
+    if (G::FUSE45) {
+        // The rows of channel c were written by the WC threads that transform its columns next: a warp-level barrier is all P5 needs.
+        // The staging warp alone waits (named barrier 3) until EVERY warp is done with the histograms before it lets the next job's
+        // crop stream into their place; the other warps only signal their arrival and move on.
+        __syncwarp();
+        if ((tid >> 5) == ROI_WARP) bar_sync_named(3, NT); else bar_arrive_named(3, NT);
+    } else __syncthreads();
     // The histograms are consumed: the staging area is free again -> start streaming the next job's crop underneath P5..P7
     if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < n_jobs) {
         const JobDesc &nd = s_desc[(it + 1) & 3];
@@ -633,7 +640,6 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // two real-input columns (DC and Nyquist): its raw transform is parked in ZB and P5b, one row per thread on all threads,
     // separates and finishes both columns (the bin-0 lanes only park 16 values while the other lanes of their warp work).
     float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column [31][WC]
-    float2 *const ZB = G::ZB_OWN ? MQ + 2 * NT : reinterpret_cast<float2 *>(Ns);   // raw transform of the packed (DC, Nyquist) column [31][WC]
     // (job-level values are re-read from the descriptor where they are needed instead of living in registers across the phases)
     float2 *const model = p.model + (long)jd.slot * p.model_stride;
     const bool first = (MODE == KCF_MODE_UPDATE) && jd.first_update != 0;
@@ -672,9 +678,10 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
                 fft_pair_ld<WC, -1>(a, half, msk, [&](int j) { return col[j * HK + fpos<HK, WC>(k, j)]; });
             }
             if (k0) {
-                // slot 0 = FFT(DC_j + i Nyq_j): parked as it is; P5b separates the two columns with all threads
+                // slot 0 = FFT(DC_j + i Nyq_j): parked as it is, in place (row j' of the transform in the bin-0 slot of row j');
+                // P5b separates the two columns with all threads
 #pragma unroll
-                for (int m = 0; m < HW; ++m) ZB[c * WC + 2 * m + half] = a[brev<HW>(m)];
+                for (int m = 0; m < HW; ++m) { const int jp = 2 * m + half; F2[(c * WC + jp) * HK + fpos<HK, WC>(0, jp)] = a[brev<HW>(m)]; }
             } else
 #pragma unroll
             for (int mb = 0; mb < HW; mb += CH) {
@@ -725,9 +732,11 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     }
     __syncthreads();
     // ---- P5b: the DC (k = 0) and Nyquist (k = HR/2) columns, one row j' per thread: Z[j'] and Z[-j'] give both
+    const unsigned p5b_mask = __ballot_sync(0xFFFFFFFFu, tid < KCF_CHAN * WC);
     if (tid < KCF_CHAN * WC) {
-        const int e = tid, c = e / WC, jp = e - c * WC;
-        const float2 v = ZB[e], y = ZB[c * WC + ((WC - jp) & (WC - 1))];
+        const int e = tid, c = e / WC, jp = e - c * WC, jm = (WC - jp) & (WC - 1);
+        const float2 v = F2[(c * WC + jp) * HK + fpos<HK, WC>(0, jp)], y = F2[(c * WC + jm) * HK + fpos<HK, WC>(0, jm)];
+        __syncwarp(p5b_mask);          // rows j' and -j' of a channel sit in the same warp: both have read before either slot is overwritten
         const float2 dc = make_float2(0.5f * (v.x + y.x), 0.5f * (v.y - y.y));
         const float2 nq = make_float2(0.5f * (v.y + y.y), 0.5f * (y.x - v.x));
         const int sp0 = c * S + jp * SK, sp1 = sp0 + HK;
