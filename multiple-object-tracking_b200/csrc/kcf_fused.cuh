@@ -12,8 +12,8 @@
 //
 // Shared-memory plan for HR x WC cells (floats; 32x32 -> 223 KB, one CTA of 1024 threads per SM):
 //   F   [31*NB]              gray patch -> (M/16, orientation bin) -> packed half spectra of all 31 channels, in place
-//   R1  [18*WC*(HR+1)]       SSE look-up tables (gradient phase) -> 18-bin cell histograms -> Nyquist column, zf, response
-//   MQ  [2 float2 / thread]  cp.async landing slots of the model stream in the column pass
+//   R1  [18*WC*(HR+1)]       SSE look-up tables (gradient phase) -> 18-bin cell histograms -> zf, response
+//   MQ  [2 float2 / thread]  cp.async landing slots of the model stream in the column pass -> Nyquist column
 //   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies;  wy[HR], wx[WC] Hann vectors
 // The 31-channel feature tensor is never materialised: each channel column is generated from R1 and N in registers,
 // windowed, transformed (real FFT of HR points as a complex FFT of HR/2) and stored PACKED (DC.re, Nyquist.re share one
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // Lane `half` of a pair ends up with the output rows j' = 2m + half.  Bins k >= 1 are ordinary columns; bin 0 carries
     // two real-input columns (DC and Nyquist): its raw transform is parked in ZB and P5b, one row per thread on all threads,
     // separates and finishes both columns (the bin-0 lanes only park 16 values while the other lanes of their warp work).
-    float2 *const FN = reinterpret_cast<float2 *>(R1);                 // Nyquist column [31][WC]
+    float2 *const FN = MQ;                                             // Nyquist column [31][WC]: row e lands in thread e's own first cp.async slot, free once its P5 is done
     // (job-level values are re-read from the descriptor where they are needed instead of living in registers across the phases)
     float2 *const model = p.model + (long)jd.slot * p.model_stride;
     const bool first = (MODE == KCF_MODE_UPDATE) && jd.first_update != 0;
@@ -730,7 +730,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         const float2 *mr = model + (tid / WC) * S + (tid % WC) * SK;
         m0n = mr[0]; m1n = mr[HK];
     }
-    __syncthreads();
+    // square grids: P5b's row (c, j') reads what the bin-0 pair of the SAME channel group parked, and writes only its own slots
+    if (G::FUSE45) __syncwarp(); else __syncthreads();
     // ---- P5b: the DC (k = 0) and Nyquist (k = HR/2) columns, one row j' per thread: Z[j'] and Z[-j'] give both
     const unsigned p5b_mask = __ballot_sync(0xFFFFFFFFu, tid < KCF_CHAN * WC);
     if (tid < KCF_CHAN * WC) {
