@@ -39,7 +39,7 @@ template <int HR, int WC> struct Geo {
     static constexpr int S = WC * SK;
     static constexpr int H0 = 4 * HR, W0 = 4 * WC;
     static constexpr int RMAX = 4 * HR + 3, CMAX = 4 * WC + 3;
-    static constexpr int GS = RMAX + 2;                  // gray column stride incl. a 1-pixel replicated apron (odd -> conflict-free both ways)
+    static constexpr int GS = RMAX + 2;                  // gray column stride incl. a (now unused) 1-pixel border (odd -> conflict-free both ways)
     static constexpr int RS = HR + 1;                    // histogram / normaliser column stride
     // (M/16, bin) per pixel with a 2..5-pixel zero border, de-interleaved along y: [x+2][(y+2)&3][(y+2)>>2]
     static constexpr int PS = ((HR + 2 - 8 + 15) / 16) * 16 + 8;   // sub-column pitch: >= HR + 2 and = 8 (mod 16), so that a warp's P1 stores spread over the banks
@@ -374,12 +374,6 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         mbar_wait(&mbar, phase);
     }
     __syncthreads();
-    // replicated 1-pixel apron: grad1's one-sided border differences become plain central differences (factor 1)
-    for (int k = tid; k < 2 * (rows + cols); k += NT) {
-        if (k < 2 * rows) { const int y = k >> 1, right = k & 1; float *q = F + (right ? cols : 1) * GS + y + 1; q[right ? GS : -GS] = *q; }
-        else { const int k2 = k - 2 * rows, x = k2 >> 1, bot = k2 & 1; float *q = F + (x + 1) * GS + (bot ? rows : 1); q[bot ? 1 : -1] = *q; }
-    }
-    __syncthreads();
     if (DUMP && p.dump.gray) {
         float *d = p.dump.gray + (long)job * p.dump.stride_px;
         for (int idx = tid; idx < rows * cols; idx += NT) { const int x = idx / rows, y = idx - x * rows; d[idx] = F[(x + 1) * GS + y + 1]; }
@@ -396,17 +390,21 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         const int y = tid & (H0 - 1), x0 = tid / H0;
         const float ry = (y == 0 || y == rows - 1) ? 1.f : .5f;
         const float *const g0 = F + (x0 + 1) * GS + y + 1;
+        // grad1's one-sided differences on the border (factor 1) are central differences against the pixel itself: the neighbour
+        // offsets of a border pixel collapse to 0.  y is fixed per thread, so the vertical pair is two per-thread pointers.
+        const float *const gup = g0 - (y == 0 ? 0 : 1), *const gdn = g0 + (y == rows - 1 ? 0 : 1);
         auto p1_pixels = [&](const float2 *rsrc, const uint32_t *bn) {
 #pragma unroll
             for (int q = 0; q < G::PIX_PER_THREAD; ++q) {
                 const int x = x0 + q * XS;
                 const float *g = g0 + q * XS * GS;
-                // grad1: one-sided difference (x1) on the border, central difference (x0.5) inside; the apron makes both one form
+                // grad1: one-sided difference (x1) on the border, central difference (x0.5) inside
                 // only the first and the last pixel of a thread can sit on the left / right border (cols >= W0): the selects of
                 // the others fold away
                 const float rx = (q == 0 || q == G::PIX_PER_THREAD - 1) ? ((x == 0 || x == cols - 1) ? 1.f : .5f) : .5f;
-                const float gx = __fmul_rn(__fsub_rn(g[GS], g[-GS]), rx);
-                const float gy = __fmul_rn(__fsub_rn(g[1], g[-1]), ry);
+                const int oL = (q == 0 && x == 0) ? 0 : -GS, oR = (q == G::PIX_PER_THREAD - 1 && x == cols - 1) ? 0 : GS;
+                const float gx = __fmul_rn(__fsub_rn(g[oR], g[oL]), rx);
+                const float gy = __fmul_rn(__fsub_rn(gdn[q * XS * GS], gup[q * XS * GS]), ry);
                 mbr[q] = grad_pixel_k(gx, gy, rsrc, bn, lk);
             }
         };
