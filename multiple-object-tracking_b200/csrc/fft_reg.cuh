@@ -75,7 +75,7 @@ template <int N, int DIR> __device__ __forceinline__ void fft_pair(float2 (&a)[N
 // The same transform with the first stage fed straight from memory: ld(i) returns point i, both lanes of a pair read all N
 // points (identical addresses inside a pair: one shared-memory broadcast, no shuffles) and each keeps its half of the
 // butterflies: lane 0 u + v, lane 1 (u - v) w^i, written branch-free (sign and twiddle selected per lane).
-template <int N, int DIR, class LD> __device__ __forceinline__ void fft_pair_ld(float2 (&a)[N / 2], int half, unsigned mask, LD ld)
+template <int N, int DIR, class LD, class MID> __device__ __forceinline__ void fft_pair_ld(float2 (&a)[N / 2], int half, unsigned mask, LD ld, MID after_loads)
 {
     constexpr int H = N / 2;
     const float sg = half ? -1.f : 1.f;
@@ -92,7 +92,12 @@ template <int N, int DIR, class LD> __device__ __forceinline__ void fft_pair_ld(
         }
     }
     __syncwarp(mask);       // in-place callers: every load of the pair precedes either lane's stores
+    after_loads();          // the points are in registers: the memory they came from may be overwritten from here on
     fft_dif<H, DIR>(a);
+}
+template <int N, int DIR, class LD> __device__ __forceinline__ void fft_pair_ld(float2 (&a)[N / 2], int half, unsigned mask, LD ld)
+{
+    fft_pair_ld<N, DIR>(a, half, mask, ld, [] {});
 }
 
 // position of packed bin k in row j of the spectrum buffer: k XOR f(j), with f chosen so that every access pattern of the

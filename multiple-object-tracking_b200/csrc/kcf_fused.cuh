@@ -13,7 +13,7 @@
 // Shared-memory plan for HR x WC cells (floats; 32x32 -> 223 KB, one CTA of 1024 threads per SM):
 //   F   [31*NB]              gray patch -> (M/16, orientation bin) -> packed half spectra of all 31 channels, in place
 //   R1  [18*WC*(HR+1)]       SSE look-up tables (gradient phase) -> 18-bin cell histograms -> zf, response
-//   MQ  [2 float2 / thread]  cp.async landing slots of the model stream in the column pass -> Nyquist column
+//   MQ  [1 float2 / thread]  Nyquist column of the spectra
 //   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies;  wy[HR], wx[WC] Hann vectors
 // The 31-channel feature tensor is never materialised: each channel column is generated from R1 and N in registers,
 // windowed, transformed (real FFT of HR points as a complex FFT of HR/2) and stored PACKED (DC.re, Nyquist.re share one
@@ -52,7 +52,7 @@ template <int HR, int WC> struct Geo {
     static constexpr int F_FLOATS = ((F_MIN > F_A ? F_MIN : F_A) + 31) & ~31;       // the regions behind it stay 128-byte aligned (2-D TMA destination)
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
-    static constexpr int MQ_FLOATS = 4 * KCF_THREADS;      // P5: two model values (float2) per thread in flight through cp.async
+    static constexpr int MQ_FLOATS = 2 * KCF_THREADS;      // Nyquist column of the spectra, [31][WC] float2 (one slot per thread)
     static constexpr int ZB_FLOATS = 0;                    // (the raw transform of the packed (DC, Nyquist) column stays in its own spectrum slots)
     // Square grids: channel c is produced (P4b) and column-transformed (P5) by the same aligned group of WC threads, so the barrier
     // between the two phases is a warp-level one and the fast warps' model streaming overlaps the slow warps' feature generation.
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // Lane `half` of a pair ends up with the output rows j' = 2m + half.  Bins k >= 1 are ordinary columns; bin 0 carries
     // two real-input columns (DC and Nyquist): its raw transform is parked in ZB and P5b, one row per thread on all threads,
     // separates and finishes both columns (the bin-0 lanes only park 16 values while the other lanes of their warp work).
-    float2 *const FN = MQ;                                             // Nyquist column [31][WC]: row e lands in thread e's own first cp.async slot, free once its P5 is done
+    float2 *const FN = MQ;                                             // Nyquist column [31][WC], its own area: written warp-locally while other warps still read the histograms
     // (job-level values are re-read from the descriptor where they are needed instead of living in registers across the phases)
     float2 *const model = p.model + (long)jd.slot * p.model_stride;
     const bool first = (MODE == KCF_MODE_UPDATE) && jd.first_update != 0;
@@ -656,67 +656,45 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             const int c = task / HK, k = task - c * HK;
             const bool k0 = k == 0;
             float2 *const mrow = model + c * S + half * SK + k;        // FFTW layout [c][wc][hr/2+1] (kcf.cpp:180-186): row j' = 2m + half
-            // The model column streams in CH values at a time on two paths that alternate chunk by chunk: registers (plain loads)
-            // and a private pair of shared-memory slots (cp.async), so 2 * CH values per thread are in flight without
-            // holding more registers; the first chunk of each path is issued before the transform and hides behind it.
-            constexpr int CH = 2;
-            static_assert(HW % (2 * CH) == 0, "P5 chunking");
-            float2 *const mq = MQ + tid;                               // slots tid, tid + NT
-            float2 mpre[CH];
-#pragma unroll
-            for (int q = 0; q < CH; ++q) mpre[q] = (need_model && !k0) ? mrow[q * 2 * SK] : make_float2(0.f, 0.f);
-            if (need_model && !k0) {
-#pragma unroll
-                for (int q = 0; q < CH; ++q) cp_async8(mq + q * NT, mrow + (CH + q) * 2 * SK);
-                cp_async_commit();
-            }
+            // The model column of this bin (HW values per lane) streams straight into the spectrum slots the lane will overwrite with
+            // its results: once the pair has the column in registers those slots are dead, so all HW values are in flight through
+            // cp.async (SASS LDGSTS) during the transform, without a register or an extra byte of shared memory.
+            const bool stream = need_model && !k0;
             float2 a[HW];
             {
                 const float2 *const col = F2 + c * WC * HK;
-                fft_pair_ld<WC, -1>(a, half, msk, [&](int j) { return col[j * HK + fpos<HK, WC>(k, j)]; });
+                fft_pair_ld<WC, -1>(a, half, msk, [&](int j) { return col[j * HK + fpos<HK, WC>(k, j)]; }, [&] {
+                    if (stream) {
+#pragma unroll
+                        for (int m = 0; m < HW; ++m) { const int jp = 2 * m + half; cp_async8(F2 + (c * WC + jp) * HK + fpos<HK, WC>(k, jp), mrow + m * 2 * SK); }
+                        cp_async_commit();
+                    }
+                });
             }
             if (k0) {
                 // slot 0 = FFT(DC_j + i Nyq_j): parked as it is, in place (row j' of the transform in the bin-0 slot of row j');
                 // P5b separates the two columns with all threads
 #pragma unroll
                 for (int m = 0; m < HW; ++m) { const int jp = 2 * m + half; F2[(c * WC + jp) * HK + fpos<HK, WC>(0, jp)] = a[brev<HW>(m)]; }
-            } else
+            } else {
+                if (stream) cp_async_wait_all();
 #pragma unroll
-            for (int mb = 0; mb < HW; mb += CH) {
-                const bool via_smem = ((mb / CH) & 1) != 0;
-                float2 mv[CH];
-                if (!via_smem) {
-#pragma unroll
-                    for (int q = 0; q < CH; ++q) mv[q] = mpre[q];
-                    if (need_model && mb + 2 * CH < HW) {
-#pragma unroll
-                        for (int q = 0; q < CH; ++q) mpre[q] = mrow[(mb + 2 * CH + q) * 2 * SK];
-                    }
-                } else {
-                    if (need_model) cp_async_wait_all();
-#pragma unroll
-                    for (int q = 0; q < CH; ++q) mv[q] = need_model ? mq[q * NT] : make_float2(0.f, 0.f);
-                }
-#pragma unroll
-                for (int q = 0; q < CH; ++q) {
-                    const int m = mb + q, jp = 2 * m + half;
+                for (int m = 0; m < HW; ++m) {
+                    const int jp = 2 * m + half;
+                    float2 *const slot = F2 + (c * WC + jp) * HK + fpos<HK, WC>(k, jp);
+                    const float2 mv = stream ? *slot : make_float2(0.f, 0.f);
                     const float2 v = a[brev<HW>(m)];
                     if (DUMP && p.dump.spec) p.dump.spec[(long)job * p.dump.stride_spec * KCF_CHAN + c * S + jp * SK + k] = v;
                     float2 o;
                     if (MODE == KCF_MODE_PREDICT) {
-                        o = make_float2(v.x * mv[q].x + v.y * mv[q].y, v.y * mv[q].x - v.x * mv[q].y);     // xf * conj(model), kcf.cpp:306-345
+                        o = make_float2(v.x * mv.x + v.y * mv.y, v.y * mv.x - v.x * mv.y);                 // xf * conj(model), kcf.cpp:306-345
                     } else {
                         o = make_float2(v.x * v.x + v.y * v.y, 0.f);                                         // |xf|^2, kcf.cpp:269-293
                         // model = (1-f) model + f xf, kcf.cpp:380-395 (f = 1 on the first update: the old model drops out)
-                        mrow[m * 2 * SK] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, mv[q].x), __fmul_rn(fac, v.x)),
-                                                                   __fadd_rn(__fmul_rn(omf, mv[q].y), __fmul_rn(fac, v.y)));
+                        mrow[m * 2 * SK] = first ? v : make_float2(__fadd_rn(__fmul_rn(omf, mv.x), __fmul_rn(fac, v.x)),
+                                                                   __fadd_rn(__fmul_rn(omf, mv.y), __fmul_rn(fac, v.y)));
                     }
-                    F2[(c * WC + jp) * HK + fpos<HK, WC>(k, jp)] = o;
-                }
-                if (via_smem && need_model && mb + 2 * CH < HW) {      // slots were read (and their values used) above
-#pragma unroll
-                    for (int q = 0; q < CH; ++q) cp_async8(mq + q * NT, mrow + (mb + 2 * CH + q) * 2 * SK);
-                    cp_async_commit();
+                    *slot = o;
                 }
             }
         }
