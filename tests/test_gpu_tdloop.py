@@ -131,6 +131,47 @@ def test_device_resident_loop_trace(oracle, mode):
     ctx.close()
 
 
+def test_device_resident_loop_separate_launches_for_large_tables(oracle):
+    """Streams with more than 256 tracks / detections keep the separate launches (1024-thread solver) instead of the one-launch frame
+    kernel: same traces as the oracle's loop, and the same as the one-launch form on a table that both can run (MOT_TDD_UNFUSED)."""
+    require_gpu()
+    M = mot()
+    W, H, cap = 1920, 1080, 320
+    sc = Scene(4242, W, H, 280, tsize=24, win=32)
+    ctx = M.Context(W, H, max_tracks=cap, kind=M.TRACKER_KALMAN)
+    loop = M.DeviceLoop(ctx, 1, cap=cap, max_det=320, cost_mode=0)
+    ref = oracle.td_new("kal", W, H, cap, 0)
+    drng = np.random.default_rng(3)
+    for f in range(12):
+        sc.step()
+        d = sc.windows(jitter=1)
+        d = np.ascontiguousarray(d[drng.random(len(d)) > 0.05])
+        loop.step([d]); ref.step(None, d)
+        a, b = loop.tracks(0), ref.tracks()
+        assert len(a["tid"]) > 256
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (f, k)
+    loop.close(); ref.close(); ctx.close()
+    import os
+    tabs = []
+    for unfused in (False, True):
+        if unfused:
+            os.environ["MOT_TDD_UNFUSED"] = "1"
+        try:
+            sc = Scene(99, W, H, 40, tsize=24, win=32)
+            ctx = M.Context(W, H, max_tracks=64, kind=M.TRACKER_KALMAN)
+            loop = M.DeviceLoop(ctx, 1, cap=64, max_det=64, cost_mode=1)
+            for f in range(15):
+                sc.step(); loop.step([sc.windows(jitter=2)])
+            tabs.append(loop.tracks(0))
+            assert ctx.launches() >= (15 * 6 if unfused else 15) and (unfused or ctx.launches() < 15 * 3)
+            loop.close(); ctx.close()
+        finally:
+            os.environ.pop("MOT_TDD_UNFUSED", None)
+    for k in tabs[0]:
+        assert np.array_equal(tabs[0][k], tabs[1][k]), k
+
+
 def test_device_resident_kcf_loop_trace(oracle):
     """The KCF kind of mot_tdd_*: job lists per window class built on the device, fused predict / update over them,
     tracker_new + first update inside the loop.  Trace-identical to the oracle's KCF loop for three streams with different
