@@ -1,5 +1,6 @@
 // assoc.cu -- batched association launches: cost matrices and the reference's Munkres solver, one CTA per problem (device code: assoc.cuh).
 #include "assoc.cuh"
+#include <cstdlib>
 
 namespace mot {
 
@@ -22,12 +23,15 @@ __global__ void cost_kernel(const AssocLaunch p)
 __global__ void __launch_bounds__(MUNKRES_THREADS, 1) munkres_kernel(const AssocLaunch p, const int *rows_cols, const int smem_mat_doubles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int m = blockIdx.x;
-    int nR, nC;
-    if (rows_cols) { nR = rows_cols[2 * m]; nC = rows_cols[2 * m + 1]; }
-    else { const int T = p.T[m], D = p.D[m]; if (T < D) { nR = T; nC = D; } else { nR = D; nC = T; } }
-    munkres_cta<MUNKRES_THREADS>(p.dist + (long)m * p.dist_stride, p.work + (long)m * p.work_stride, nR, nC, p.max_dim, p.assign + (long)m * p.assign_stride,
-                                 p.cost + m, smem_raw, smem_mat_doubles);
+    // persistent CTAs over the problems (the launch may hold fewer CTAs than problems: see assoc_solve)
+    for (int m = blockIdx.x; m < p.n_mat; m += gridDim.x) {
+        int nR, nC;
+        if (rows_cols) { nR = rows_cols[2 * m]; nC = rows_cols[2 * m + 1]; }
+        else { const int T = p.T[m], D = p.D[m]; if (T < D) { nR = T; nC = D; } else { nR = D; nC = T; } }
+        munkres_cta<MUNKRES_THREADS>(p.dist + (long)m * p.dist_stride, p.work + (long)m * p.work_stride, nR, nC, p.max_dim, p.assign + (long)m * p.assign_stride,
+                                     p.cost + m, smem_raw, smem_mat_doubles);
+        __syncthreads();
+    }
 }
 
 int assoc_cost(const AssocLaunch &p, cudaStream_t s)
@@ -48,7 +52,16 @@ int assoc_solve(const AssocLaunch &p, const int *rows_cols, cudaStream_t s)
     const size_t bytes = munkres_smem_bytes(p.max_dim, mat_doubles);
     cudaError_t e = cudaFuncSetAttribute((const void *)munkres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    munkres_kernel<<<p.n_mat, MUNKRES_THREADS, bytes, s>>>(p, rows_cols, mat_doubles);
+    // Matrices that do not fit shared memory are worked on in global memory, pass after pass: with one CTA per SM all at once their
+    // working copies (max_dim^2 doubles each) overflow the L2 and every pass of every round comes from HBM.  Fewer CTAs at a time,
+    // sized so that the copies stay L2-resident, finish the whole batch sooner.
+    int grid = p.n_mat;
+    if (mat_doubles == 0) {
+        int cap = 0;
+        if (const char *e = getenv("MOT_MUNKRES_CTAS")) cap = atoi(e);
+        if (cap > 0 && cap < grid) grid = cap;
+    }
+    munkres_kernel<<<grid, MUNKRES_THREADS, bytes, s>>>(p, rows_cols, mat_doubles);
     return (int)cudaGetLastError();
 }
 

@@ -345,24 +345,29 @@ __device__ void munkres_cta(const double *distIn, double *work, const int nR, co
         if (ctrl != CTRL_STEP5) break;
         if (++guard > guard_max) { if (tid == 0) s.ctrl[0] = CTRL_FAIL; __syncthreads(); break; }
 
-        // step 5 (hungarian.cpp:337-368), whole CTA.  h = smallest uncovered element.  Both passes walk (column, 32-row word)
-        // tasks four at a time per warp so that four independent global loads are in flight (the passes are latency-bound).
+        // step 5 (hungarian.cpp:337-368), whole CTA.  h = smallest uncovered element.  A warp keeps ONE 32-row word of the matrix (its
+        // row-cover bits live in a register, nothing is divided per cell) and walks over a contiguous run of columns, eight at a time so
+        // that eight independent loads are in flight; words without an uncovered row (first pass) and covered columns without a covered
+        // row in the word (second pass) are skipped by the whole warp.  The passes are bound by instruction issue, not by memory.
         constexpr int U = 8;
-        const int nTask = nC * nWr;
+        const int G5 = NW >= nWr ? NW / nWr : 1, per5 = (nC + G5 - 1) / G5;
         double h = DBL_MAX;
-        for (int t0 = warp; t0 < nTask; t0 += NW * U) {
-            double v[U];
+        for (int wt = warp; wt < nWr * G5; wt += NW) {
+            const int w = wt % nWr, g = wt / nWr, r = (w << 5) + lane;
+            const bool rowu = r < nR && !((s.covR[w] >> lane) & 1u);
+            if (__ballot_sync(0xFFFFFFFFu, rowu) == 0u) continue;             // warp-uniform
+            const int cbeg = g * per5, cend = min(nC, cbeg + per5);
+            const double *const dr = d + r;
+            for (int c0 = cbeg; c0 < cend; c0 += U) {
+                double v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int task = t0 + u * NW;
-                v[u] = DBL_MAX;
-                if (task < nTask) {
-                    const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
-                    if (!tst(s.covC, c) && r < nR && !tst(s.covR, r)) v[u] = d[r + (long)nR * c];
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + u;
+                    v[u] = (rowu && c < cend && !tst(s.covC, c)) ? dr[(long)nR * c] : DBL_MAX;
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < U; ++u) if (v[u] < h) h = v[u];
+                for (int u = 0; u < U; ++u) if (v[u] < h) h = v[u];
+            }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_xor_sync(0xFFFFFFFFu, h, off); if (o < h) h = o; }
@@ -372,40 +377,39 @@ __device__ void munkres_cta(const double *distIn, double *work, const int nR, co
 #pragma unroll
         for (int w = 1; w < NW; ++w) { const double o = s.redd[w]; if (o < h) h = o; }
         // add h to covered rows, then subtract h from uncovered columns; refresh the zero bits of touched cells
-        for (int t0 = warp; t0 < nTask; t0 += NW * U) {
-            double v[U]; bool touch[U], live[U], rcv[U], ccv[U]; long off[U]; int zi[U];
+        for (int wt = warp; wt < nWr * G5; wt += NW) {
+            const int w = wt % nWr, g = wt / nWr, r = (w << 5) + lane;
+            const uint32_t crw = s.covR[w];
+            const bool inr = r < nR, rc = inr && ((crw >> lane) & 1u);
+            const int cbeg = g * per5, cend = min(nC, cbeg + per5);
+            double *const dr = d + r;
+            for (int c0 = cbeg; c0 < cend; c0 += U) {
+                double v[U]; uint32_t st5[U];                                  // bit 0: column covered, bit 1: task live, bit 2: this cell is touched
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int task = t0 + u * NW;
-                touch[u] = false; live[u] = false; rcv[u] = false; ccv[u] = true; off[u] = 0; zi[u] = 0; v[u] = 0.0;
-                if (task < nTask) {
-                    const int c = task / nWr, w = task - c * nWr, r = (w << 5) + lane;
-                    const bool cc = tst(s.covC, c);
-                    const uint32_t crw = s.covR[w];
-                    live[u] = !(cc && crw == 0);                  // covered column, no covered row in this word: untouched
-                    zi[u] = c * zs + w; ccv[u] = cc;
-                    if (live[u] && r < nR) {
-                        rcv[u] = (crw >> lane) & 1u;
-                        touch[u] = rcv[u] || !cc;
-                        off[u] = r + (long)nR * c;
-                        if (touch[u]) v[u] = d[off[u]];
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + u;
+                    const bool in = c < cend, cc = in && tst(s.covC, c);
+                    const bool live = in && !(cc && crw == 0u);                // covered column, no covered row in this word: untouched
+                    const bool touch = live && inr && (rc || !cc);
+                    st5[u] = (cc ? 1u : 0u) | (live ? 2u : 0u) | (touch ? 4u : 0u);
+                    v[u] = touch ? dr[(long)nR * c] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (!(st5[u] & 2u)) continue;                              // warp-uniform (depends on the column and the word only)
+                    const int c = c0 + u;
+                    bool z = (s.Zc[c * zs + w] >> lane) & 1u;
+                    if (st5[u] & 4u) {
+                        double x = v[u];
+                        if (rc) x = __dadd_rn(x, h);
+                        if (!(st5[u] & 1u)) x = __dsub_rn(x, h);
+                        dr[(long)nR * c] = x;
+                        z = fabs(x) < DBL_EPSILON;
                     }
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
+                    __syncwarp();                                             // every lane has read the old word
+                    if (lane == 0) s.Zc[c * zs + w] = word;
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!live[u]) continue;                            // warp-uniform (depends on the task only)
-                bool z = (s.Zc[zi[u]] >> lane) & 1u;
-                if (touch[u]) {
-                    double x = v[u];
-                    if (rcv[u]) x = __dadd_rn(x, h);
-                    if (!ccv[u]) x = __dsub_rn(x, h);
-                    d[off[u]] = x;
-                    z = fabs(x) < DBL_EPSILON;
-                }
-                const uint32_t word = __ballot_sync(0xFFFFFFFFu, z);
-                __syncwarp();                                     // every lane has read the old word
-                if (lane == 0) s.Zc[zi[u]] = word;
             }
         }
         after_step5 = true;
