@@ -1,6 +1,5 @@
 // assoc.cu -- batched association launches: cost matrices and the reference's Munkres solver, one CTA per problem (device code: assoc.cuh).
 #include "assoc.cuh"
-#include <cstdlib>
 
 namespace mot {
 
@@ -52,15 +51,9 @@ int assoc_solve(const AssocLaunch &p, const int *rows_cols, cudaStream_t s)
     const size_t bytes = munkres_smem_bytes(p.max_dim, mat_doubles);
     cudaError_t e = cudaFuncSetAttribute((const void *)munkres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    // Matrices that do not fit shared memory are worked on in global memory, pass after pass: with one CTA per SM all at once their
-    // working copies (max_dim^2 doubles each) overflow the L2 and every pass of every round comes from HBM.  Fewer CTAs at a time,
-    // sized so that the copies stay L2-resident, finish the whole batch sooner.
-    int grid = p.n_mat;
-    if (mat_doubles == 0) {
-        int cap = 0;
-        if (const char *e = getenv("MOT_MUNKRES_CTAS")) cap = atoi(e);
-        if (cap > 0 && cap < grid) grid = cap;
-    }
+    // one CTA per problem (measured on config 5: capping the resident CTAs so that the working copies stay in L2 does not pay --
+    // a problem's rate is set by its own dependent passes, not by HBM)
+    const int grid = p.n_mat;
     munkres_kernel<<<grid, MUNKRES_THREADS, bytes, s>>>(p, rows_cols, mat_doubles);
     return (int)cudaGetLastError();
 }
