@@ -261,13 +261,27 @@ __global__ void td_lifecycle_kernel(TddState st, KalmanState kal, const mot_bbox
 // hundred tracks are a CTA's worth of work), so a frame costs one launch latency instead of six.  Same device code as the separate
 // kernels (kalman.cuh, assoc.cuh, the *_cta functions above): the results are the same bit for bit.
 constexpr int TDF_THREADS = 256;      // 255 registers per thread: the Kalman update keeps its 6x6 FP64 algebra in registers (no spills)
-struct TdFrameArgs { double *dist, *work, *cost; int cost_mode; double screen_dis; int mat_doubles; };
+struct TdFrameArgs {
+    double *dist, *work, *cost; int cost_mode; double screen_dis; int mat_doubles;
+    // host-array steps: the detections are read by the kernel itself from the pinned staging set (device-accessible under unified
+    // addressing) into the device arrays it then works on -- no copy-engine transfers in front of a one-launch frame (null: device arrays given)
+    const mot_bbox_t *host_dets; const int *host_ndet; mot_bbox_t *dets_w; int *ndet_w;
+};
 
 __global__ void __launch_bounds__(TDF_THREADS, 1) td_frame_kalman_kernel(TddState st, KalmanState kal, const mot_bbox_t *dets, const int *ndet, TdFrameArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int at[1024];
     const int s = blockIdx.x, tid = threadIdx.x, cap = st.cap, md = st.md;
+    if (a.host_dets) {
+        // this stream's detections: pinned host memory -> the device arrays (dets == a.dets_w, ndet == a.ndet_w), 8 bytes per thread and trip
+        const int D0 = a.host_ndet[s];
+        const long long *src = reinterpret_cast<const long long *>(a.host_dets + (long)s * st.max_det);
+        long long *dst = reinterpret_cast<long long *>(a.dets_w + (long)s * st.max_det);
+        for (int i = tid; i < D0 * 3; i += TDF_THREADS) dst[i] = src[i];
+        if (tid == 0) a.ndet_w[s] = D0;
+        __syncthreads();
+    }
     const int T = st.ntracks[s], D = ndet[s];
     mot_bbox_t *const trk = st.bbox + (long)s * cap;
     const mot_bbox_t *const det = dets + (long)s * st.max_det;
@@ -321,6 +335,7 @@ struct mot_tdd_s {
     int cost_mode;
     double *d_dist = nullptr, *d_cost = nullptr, *d_work = nullptr;      // cost matrices, totals, the solver's working copy (owned: graph-safe)
     bool fused_frame = false;                                            // Kalman kind: the whole frame in one launch (td_frame_kalman_kernel)
+    const mot_bbox_t *host_dets_next = nullptr; const int *host_ndet_next = nullptr;   // set by mot_tdd_step for the launch it makes next
     float *d_strip = nullptr; int strip_ctas = 0;                        // strip-mode list: per-CTA histogram scratch (L2-resident)
     // Host-array steps: detections are staged in pinned memory and uploaded.  Two staging sets used alternately, each with its own
     // "consumed" event, so that the host prepares step k+1 while step k runs and only ever waits for step k-1.
@@ -473,7 +488,9 @@ int mot_tdd_step_dev(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet)
     const int n = st.S * st.cap;
     if (st.kcf) return tdd_step_kcf(t, d_dets, d_ndet);
     if (t->fused_frame) {
-        TdFrameArgs a{ t->d_dist, t->d_work, t->d_cost, t->cost_mode, 1.0 / (double)c->W, munkres_mat_doubles(st.md) };
+        TdFrameArgs a{ t->d_dist, t->d_work, t->d_cost, t->cost_mode, 1.0 / (double)c->W, munkres_mat_doubles(st.md), t->host_dets_next, t->host_ndet_next,
+                       const_cast<mot_bbox_t *>(d_dets), const_cast<int *>(d_ndet) };
+        t->host_dets_next = nullptr; t->host_ndet_next = nullptr;
         const size_t bytes = std::max(munkres_smem_bytes(st.md, a.mat_doubles), sizeof(int) * 3072);
         td_frame_kalman_kernel<<<st.S, TDF_THREADS, bytes, c->stream>>>(st, c->kal, d_dets, d_ndet, a);
         CU(cudaGetLastError());
@@ -516,6 +533,14 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
         // the KCF sequence waits for frame uploads recorded on another stream, which a captured graph would freeze: plain launches
         CU(cudaMemcpyAsync(t->d_dets[q].p, t->h_dets[q].p, det_bytes, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(t->d_ndet[q].p, t->h_ndet[q].p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream));
+        const int rc = mot_tdd_step_dev(t, t->d_dets[q].p, t->d_ndet[q].p);
+        if (rc) return rc;
+        CU(cudaEventRecord(t->consumed[q], c->stream));
+        return 0;
+    }
+    if (t->fused_frame) {
+        // one launch, and the kernel fetches the detections from the pinned staging set itself
+        t->host_dets_next = t->h_dets[q].p; t->host_ndet_next = t->h_ndet[q].p;
         const int rc = mot_tdd_step_dev(t, t->d_dets[q].p, t->d_ndet[q].p);
         if (rc) return rc;
         CU(cudaEventRecord(t->consumed[q], c->stream));
