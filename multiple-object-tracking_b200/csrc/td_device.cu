@@ -79,9 +79,18 @@ __device__ __forceinline__ int kcf_list_of(const TddState &st, int rows, int col
 }
 
 // live tracks -> one job list per window class (order inside a list is irrelevant: jobs are independent)
-__global__ void td_joblist_kernel(TddState st)
+// (host-array steps: the CTA of stream s first fetches the stream's detections from the pinned staging set into the device arrays
+// that the later kernels of the frame read -- no copy-engine transfer in front of the frame)
+__global__ void td_joblist_kernel(TddState st, const mot_bbox_t *host_dets, const int *host_ndet, mot_bbox_t *dets_w, int *ndet_w)
 {
     const int s = blockIdx.x, T = st.ntracks[s];
+    if (host_dets) {
+        const int D0 = host_ndet[s];
+        const long long *src = reinterpret_cast<const long long *>(host_dets + (long)s * st.max_det);
+        long long *dst = reinterpret_cast<long long *>(dets_w + (long)s * st.max_det);
+        for (int i = threadIdx.x; i < D0 * 3; i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x == 0) ndet_w[s] = D0;
+    }
     const long N = (long)st.S * st.cap;
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
         const long e = (long)s * st.cap + i;
@@ -445,7 +454,8 @@ static int tdd_step_kcf(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_nde
     const int n = st.S * st.cap;
     int rc = mot_ctx_frames_ready(c); if (rc) return rc;
     CU(cudaMemsetAsync(st.jl_count, 0, sizeof(int) * 2 * TDD_LISTS, c->stream));
-    td_joblist_kernel<<<st.S, 256, 0, c->stream>>>(st);
+    td_joblist_kernel<<<st.S, 256, 0, c->stream>>>(st, t->host_dets_next, t->host_ndet_next, const_cast<mot_bbox_t *>(d_dets), const_cast<int *>(d_ndet));
+    t->host_dets_next = nullptr; t->host_ndet_next = nullptr;
     auto per_class = [&](int mode, const int *count, const int *slot, const int *frame, const int *box, int clamp) {
         for (int k = 0; k < 9; ++k) {
             if (st.cls_id[k] < 0) continue;
@@ -530,10 +540,11 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
     }
     const size_t det_bytes = sizeof(mot_bbox_t) * (size_t)st.S * st.max_det;
     if (st.kcf) {
-        // the KCF sequence waits for frame uploads recorded on another stream, which a captured graph would freeze: plain launches
-        CU(cudaMemcpyAsync(t->d_dets[q].p, t->h_dets[q].p, det_bytes, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(t->d_ndet[q].p, t->h_ndet[q].p, sizeof(int) * st.S, cudaMemcpyHostToDevice, c->stream));
+        // plain launches (the sequence waits for frame uploads recorded on another stream); the first kernel of the frame fetches the
+        // detections from the pinned staging set itself
+        t->host_dets_next = t->h_dets[q].p; t->host_ndet_next = t->h_ndet[q].p;
         const int rc = mot_tdd_step_dev(t, t->d_dets[q].p, t->d_ndet[q].p);
+        t->host_dets_next = nullptr; t->host_ndet_next = nullptr;      // (consumed by the launch; cleared here too in case the step failed before it)
         if (rc) return rc;
         CU(cudaEventRecord(t->consumed[q], c->stream));
         return 0;
@@ -542,6 +553,7 @@ int mot_tdd_step(mot_tdd_t *t, const mot_bbox_t *const *dets, const int *ndet)
         // one launch, and the kernel fetches the detections from the pinned staging set itself
         t->host_dets_next = t->h_dets[q].p; t->host_ndet_next = t->h_ndet[q].p;
         const int rc = mot_tdd_step_dev(t, t->d_dets[q].p, t->d_ndet[q].p);
+        t->host_dets_next = nullptr; t->host_ndet_next = nullptr;      // (consumed by the launch; cleared here too in case the step failed before it)
         if (rc) return rc;
         CU(cudaEventRecord(t->consumed[q], c->stream));
         return 0;
