@@ -528,64 +528,62 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
         for (int i = tid; i < G::N_FLOATS; i += NT) d[i] = Ns[i];
     }
 
-    // ------------------------------------------------------------------ P4a: the four texture channels (hogChannels type 2)
-    // gradientMex.cpp:271-275: channel 27+blk = sum over the 18 orientations of min(R1*N_blk, 0.2) * 0.2357, accumulated in
-    // orientation order.  One thread per cell shares each R1 load between the four block normalisers.  The values go, as
-    // plain floats rotated by the column index (bank-conflict free for the column-wise reader below), into the F slots of
-    // channels 27..30, which P4b then transforms in place.
-    for (int cell = tid; cell < NB; cell += NT) {
-        const int j = cell / HR, i = cell - j * HR;
+    // ------------------------------------------------------------------ P4x: all 31 windowed features of a cell, one thread per cell
+    // hogChannels (gradientMex.cpp:256-280): the clipped products min(R1[o] * N_blk, 0.2) of the 18 orientations feed BOTH the
+    // contrast-sensitive channels (type 1, :266-270: the four are added in block order; the x0.5 commutes exactly with the additions
+    // and sits in the stored window rows) and the four texture channels (type 2, :271-275: x0.2357, accumulated in orientation
+    // order), so a cell computes them once; the contrast-insensitive channels take R2 = R1[o] + R1[o+9] (:308-309).  Every feature
+    // is multiplied by cos_win (kcf.cpp:251-258) here and parked as a plain float in the spectrum slot of its (channel, column),
+    // rotated by the column index so that the column-wise reader below is bank-conflict free.
+    static_assert(NB <= NT, "P4x: one cell per thread");
+    if (tid < NB) {
+        const int j = tid / HR, i = tid - j * HR;
         const float *const n0 = Ns + j * (HR + 1) + i, *const n1 = n0 + (HR + 1);
         const float nv0 = n1[1], nv1 = n1[0], nv2 = n0[1], nv3 = n0[0];      // GETT(0), GETT(1), GETT(hb1), GETT(hb1+1)
+        const float w = __fmul_rn(wy_s[i], wx_s[j]);                         // (0.5 wy) * wx
+        const float *const rp = R1 + j * RS + i;
+        float *const fp = F + j * HR + ((i + j) & (HR - 1));                 // channel c: fp[c * NB]
         float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
-        const float *rp = R1 + j * RS + i;
-#pragma unroll 6
+        float rlo[9];
+#pragma unroll
         for (int o = 0; o < 18; ++o) {
             const float rv = rp[o * (WC * RS)];
-            h0 = __fadd_rn(h0, __fmul_rn(fminf(__fmul_rn(rv, nv0), 0.2f), .2357f));
-            h1 = __fadd_rn(h1, __fmul_rn(fminf(__fmul_rn(rv, nv1), 0.2f), .2357f));
-            h2 = __fadd_rn(h2, __fmul_rn(fminf(__fmul_rn(rv, nv2), 0.2f), .2357f));
-            h3 = __fadd_rn(h3, __fmul_rn(fminf(__fmul_rn(rv, nv3), 0.2f), .2357f));
+            const float t0 = fminf(__fmul_rn(rv, nv0), 0.2f), t1 = fminf(__fmul_rn(rv, nv1), 0.2f);
+            const float t2 = fminf(__fmul_rn(rv, nv2), 0.2f), t3 = fminf(__fmul_rn(rv, nv3), 0.2f);
+            fp[o * NB] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3), w);
+            h0 = __fadd_rn(h0, __fmul_rn(t0, .2357f)); h1 = __fadd_rn(h1, __fmul_rn(t1, .2357f));
+            h2 = __fadd_rn(h2, __fmul_rn(t2, .2357f)); h3 = __fadd_rn(h3, __fmul_rn(t3, .2357f));
+            if (o < 9) rlo[o] = rv;
+            else {
+                const float r2 = __fadd_rn(rlo[o - 9], rv);
+                const float u0 = fminf(__fmul_rn(r2, nv0), 0.2f), u1 = fminf(__fmul_rn(r2, nv1), 0.2f);
+                const float u2 = fminf(__fmul_rn(r2, nv2), 0.2f), u3 = fminf(__fmul_rn(r2, nv3), 0.2f);
+                fp[(9 + o) * NB] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(u0, u1), u2), u3), w);
+            }
         }
-        const int rot = (i + j) & (HR - 1);
         // doubled (exact) because the window rows are stored halved
-        F[(27 * WC + j) * HR + rot] = h0 + h0; F[(28 * WC + j) * HR + rot] = h1 + h1;
-        F[(29 * WC + j) * HR + rot] = h2 + h2; F[(30 * WC + j) * HR + rot] = h3 + h3;
+        fp[27 * NB] = __fmul_rn(h0 + h0, w); fp[28 * NB] = __fmul_rn(h1 + h1, w);
+        fp[29 * NB] = __fmul_rn(h2 + h2, w); fp[30 * NB] = __fmul_rn(h3 + h3, w);
     }
     __syncthreads();
+    // The histograms are consumed: the staging area is free again -> start streaming the next job's crop underneath P4y..P7
+    if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < n_jobs) {
+        const JobDesc &nd = s_desc[(it + 1) & 3];
+        issue_roi(nd.box, nd.frame, nd.fslot);
+        if ((tid & 31) == 0 && job + 2 * (int)gridDim.x < n_jobs) fetch_desc(job + 2 * gridDim.x, &s_desc[(it + 2) & 3]);
+    }
 
-    // ------------------------------------------------------------------ P4b: channel columns -> window -> real FFT along rows
-    // hogChannels type 1 (gradientMex.cpp:266-270) generates channel c of column j straight into registers: the four
-    // clipped products are halved and added in block order; halving commutes exactly with the additions, so the sum is
-    // formed first and halved once.  x cos_win (kcf.cpp:251-258); r2c along the HR rows as ONE complex FFT of HR/2 points;
-    // packed store (DC and Nyquist, both real, share slot 0).
+    // ------------------------------------------------------------------ P4y: real FFT along the rows of every (channel, column)
+    // r2c along the HR rows as ONE complex FFT of HR/2 points, in place; packed store (DC and Nyquist, both real, share slot 0).
     float2 *const F2 = reinterpret_cast<float2 *>(F);
     for (int task = tid; task < KCF_CHAN * WC; task += NT) {
         const int c = task / WC, j = task - c * WC;
         float2 z[HK];
-        const float wxj = wx_s[j];
-        if (c < 27) {
-            const float *const n0 = Ns + j * (HR + 1), *const n1 = n0 + (HR + 1);
-            const float *const ra = R1 + (c < 18 ? c : c - 18) * (WC * RS) + j * RS;
-            const float *const rb = R1 + (c < 18 ? c : c - 9) * (WC * RS) + j * RS;
-            auto column = [&](auto insensitive) {
-#pragma unroll
-                for (int i = 0; i < HR; ++i) {
-                    const float rv = insensitive ? __fadd_rn(ra[i], rb[i]) : ra[i];     // R2 = R1[o] + R1[o+9] (gradientMex.cpp:308-309)
-                    float hsum = __fadd_rn(fminf(__fmul_rn(rv, n1[i + 1]), 0.2f), fminf(__fmul_rn(rv, n1[i]), 0.2f));
-                    hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i + 1]), 0.2f));
-                    hsum = __fadd_rn(hsum, fminf(__fmul_rn(rv, n0[i]), 0.2f));
-                    const float f = __fmul_rn(hsum, __fmul_rn(wy_s[i], wxj));           // (hsum * 0.5) * (wy * wx): the 0.5 sits in wy_s
-                    if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
-                }
-            };
-            // warp-uniform: a warp holds one channel, so the two forms are separate loops rather than a select per point
-            if (c < 18) column(std::false_type{}); else column(std::true_type{});
-        } else {
+        {
             const float *const tp = F + (c * WC + j) * HR;
 #pragma unroll
             for (int i = 0; i < HR; ++i) {
-                const float f = __fmul_rn(tp[(i + j) & (HR - 1)], __fmul_rn(wy_s[i], wxj));
+                const float f = tp[(i + j) & (HR - 1)];
                 if (i & 1) z[i >> 1].y = f; else z[i >> 1].x = f;
             }
         }
@@ -617,19 +615,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             }
         }
     }
-    if (G::FUSE45) {
-        // The rows of channel c were written by the WC threads that transform its columns next: a warp-level barrier is all P5 needs.
-        // The staging warp alone waits (named barrier 3) until EVERY warp is done with the histograms before it lets the next job's
-        // crop stream into their place; the other warps only signal their arrival and move on.
-        __syncwarp();
-        if ((tid >> 5) == ROI_WARP) bar_sync_named(3, NT); else bar_arrive_named(3, NT);
-    } else __syncthreads();
-    // The histograms are consumed: the staging area is free again -> start streaming the next job's crop underneath P5..P7
-    if ((tid >> 5) == ROI_WARP && job + (int)gridDim.x < n_jobs) {
-        const JobDesc &nd = s_desc[(it + 1) & 3];
-        issue_roi(nd.box, nd.frame, nd.fslot);
-        if ((tid & 31) == 0 && job + 2 * (int)gridDim.x < n_jobs) fetch_desc(job + 2 * gridDim.x, &s_desc[(it + 2) & 3]);
-    }
+    // square grids: the rows of channel c were written by the WC threads that transform its columns next -- a warp-level barrier
+    if (G::FUSE45) __syncwarp(); else __syncthreads();
 
     // ------------------------------------------------------------------ P5: complex FFT along the WC columns + spectral work
     // Tasks (channel c, packed bin k), each run by a PAIR of adjacent lanes that hold half of the WC points each (the
