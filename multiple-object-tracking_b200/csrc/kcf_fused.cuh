@@ -11,13 +11,14 @@
 //   update : kcf_linear_correlation_kf + kcf_update_alpha + kcf_update_xf                         kcf.cpp:269-304, 364-395, 441-476
 //
 // Shared-memory plan for HR x WC cells (floats; 32x32 -> 223 KB, one CTA of 1024 threads per SM):
-//   F   [31*NB]              gray patch -> (M/16, orientation bin) -> packed half spectra of all 31 channels, in place
+//   F   [31*NB]              gray patch -> (M/16, orientation bin) -> windowed features of all 31 channels -> their packed half spectra, in place
 //   R1  [18*WC*(HR+1)]       SSE look-up tables (gradient phase) -> 18-bin cell histograms -> zf, response
 //   MQ  [1 float2 / thread]  Nyquist column of the spectra
 //   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies;  wy[HR], wx[WC] Hann vectors
-// The 31-channel feature tensor is never materialised: each channel column is generated from R1 and N in registers,
-// windowed, transformed (real FFT of HR points as a complex FFT of HR/2) and stored PACKED (DC.re, Nyquist.re share one
-// complex slot), so the column pass is exactly HR/2 complex FFTs per channel: 31*16 = 496 thread-sized transforms at 32x32.
+// The 31-channel feature tensor never leaves shared memory: one thread per cell generates its 31 windowed features from R1 and N
+// (P4x), one thread per (channel, column) transforms them in place (P4y: real FFT of HR points as a complex FFT of HR/2) and stores
+// them PACKED (DC.re, Nyquist.re share one complex slot), so the column pass is exactly HR/2 complex FFTs per channel: 31*16 = 496
+// thread-sized transforms at 32x32.
 //
 // Arithmetic follows the reference operation by operation where its rounding is observable (gray: the double expression
 // reproduced exactly in integers + three f32 operations, unfused
