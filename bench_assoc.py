@@ -113,7 +113,7 @@ def config2(args):
     for t in tds:
         t.close()
     ctx.close()
-    # device-resident loop (mot_tdd_*): detections resident too, five launches per frame, one sync at the very end
+    # device-resident loop (mot_tdd_*): detections resident too, one launch per frame, one sync at the very end
     import torch
     for ns2, key in ((1, "device_resident_1_stream"), (64, "device_resident_64_streams")):
         ctx = M.Context(W, H, max_tracks=ns2 * 128, kind=M.TRACKER_KALMAN)

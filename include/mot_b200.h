@@ -207,8 +207,8 @@ void mot_td_get(mot_td_t *td, uint32_t *tid, mot_bbox_t *boxes, int *age, int *v
 int mot_td_overlay(mot_td_t *td);
 int mot_td_last(mot_td_t *td, mot_bbox_t *predicted, int *assigned_trackers);
 
-/* ---- the same frame loop with the track tables resident on the DEVICE: for the Kalman kind five launches per frame for all
- *      streams, for the KCF kind the fused kernels over per-class job lists built on the device; no host synchronisation (replaces top/td.cpp:343-644 including the bookkeeping,
+/* ---- the same frame loop with the track tables resident on the DEVICE: for the Kalman kind ONE launch per frame for all
+ *      streams (a CTA per stream; six launches beyond 256 tracks or detections per stream), for the KCF kind the fused kernels over per-class job lists built on the device; no host synchronisation (replaces top/td.cpp:343-644 including the bookkeeping,
  *      the stable compaction of lost tracks :585-609 and the spawn order :612-644) --------------------------------- */
 typedef struct mot_tdd_s mot_tdd_t;
 /* n_streams independent streams, at most cap tracks (reference: 256, top/td.cpp:12) and max_det detections

@@ -1,6 +1,7 @@
 // td_device.cu -- the frame loop of the reference with the track table RESIDENT ON THE DEVICE (both tracker kinds).
 //
-// One iteration of pthread_mtcnn_trkn (top/td.cpp:343-644) for S independent streams is five launches and no host
+// One iteration of pthread_mtcnn_trkn (top/td.cpp:343-644) for S independent streams is ONE launch (td_frame_kalman_kernel, a CTA per
+// stream, up to 256 tracks / detections per stream) or six and no host
 // synchronisation: kalman_predict (+clamp, :344-384) -> cost matrices + Munkres (:386-470) -> td_scatter (:472-547,
 // :550-556 bookkeeping) -> kalman_update (:539, :581) -> td_lifecycle (delete lost with stable compaction :585-609, spawn
 // per unassigned detection in ascending order :612-644).  The bookkeeping, the order of the track table and the ids are
