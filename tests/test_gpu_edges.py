@@ -124,6 +124,41 @@ def test_slot_capacity_reuse_and_invalid_handles():
     ctx.close()
 
 
+def test_reserved_window_arena_gives_the_same_filter(oracle):
+    """mot_ctx_reserve_window only changes WHERE a model lives (a larger slot of the arena instead of an individually allocated block):
+    a 200x260 px window (50x65 cells, 1650 half-spectrum bins, strip mode) tracks identically with and without the reservation and
+    like the compiled reference; the call is refused once a tracker exists."""
+    require_gpu()
+    M = mot()
+    W, H, rows, cols = 1280, 720, 260, 200
+    sc = Scene(12, W, H, 1, tsize=150, win=200, vmax=3.0)
+    sc.pos[:] = [[400.0, 330.0]]
+    frames = []
+    for _ in range(2):
+        frames.append(sc.render()); sc.step()
+    outs = []
+    for reserve in (False, True):
+        ctx = M.Context(W, H, max_tracks=2, n_frame_slots=1, kind=M.TRACKER_KCF)
+        if reserve:
+            ctx.reserve_window(320, 320)
+        b = one_box(300, 200, rows, cols)
+        ctx.upload(0, frames[0]); h = ctx.new(b); ctx.update(h, [0], b)
+        if reserve:
+            with pytest.raises(M.MotError):
+                ctx.reserve_window(400, 400)             # a tracker exists
+        ctx.upload(0, frames[1]); g = ctx.predict(h, [0], b.copy(), clamp=1); ctx.update(h, [0], g)
+        outs.append((g.copy(), ctx.state(h[0], "alpha").copy()))
+        ctx.close()
+    assert outs[0][0].tobytes() == outs[1][0].tobytes() and np.array_equal(outs[0][1], outs[1][1])
+    ob = box_of(outs[0][0][0])
+    rb = box_of(one_box(300, 200, rows, cols)[0]); oh = oracle.kcf_new(rb)
+    oracle.kcf_update(oh, crop_gray(oracle, frames[0], rb, rows, cols), rb)
+    oracle.kcf_predict(oh, crop_gray(oracle, frames[1], rb, rows, cols), rb)
+    rb.l, rb.r = min(max(0, rb.l), W - 1), min(max(0, rb.r), W - 1); rb.t, rb.b = min(max(0, rb.t), H - 1), min(max(0, rb.b), H - 1)
+    assert ob.tup() == rb.tup()
+    oracle.kcf_delete(oh)
+
+
 def test_many_tracks_one_launch_equals_per_track_oracle(oracle):
     """A 300-track batch (more CTAs than SMs: the persistent kernel loops) against per-track oracle calls."""
     require_gpu()
