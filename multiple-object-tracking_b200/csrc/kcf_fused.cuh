@@ -13,7 +13,7 @@
 // Shared-memory plan for HR x WC cells (floats; 32x32 -> 223 KB, one CTA of 1024 threads per SM):
 //   F   [31*NB]              gray patch -> (M/16, orientation bin) -> windowed features of all 31 channels -> their packed half spectra, in place
 //   R1  [18*WC*(HR+1)]       SSE look-up tables (gradient phase) -> 18-bin cell histograms -> zf, response
-//   MQ  [1 float2 / thread]  Nyquist column of the spectra
+//   MQ  [2 float2 / thread]  cp.async landing slots of the two model values of P5b -> Nyquist column of the spectra
 //   N   [(WC+1)*(HR+1)]      block normalisers;  E [NB] cell energies;  wy[HR], wx[WC] Hann vectors
 // The 31-channel feature tensor never leaves shared memory: one thread per cell generates its 31 windowed features from R1 and N
 // (P4x), one thread per (channel, column) transforms them in place (P4y: real FFT of HR points as a complex FFT of HR/2) and stores
@@ -53,7 +53,7 @@ template <int HR, int WC> struct Geo {
     static constexpr int F_FLOATS = ((F_MIN > F_A ? F_MIN : F_A) + 31) & ~31;       // the regions behind it stay 128-byte aligned (2-D TMA destination)
     static constexpr int R1_MIN = 18 * WC * RS;
     static constexpr int N_FLOATS = (WC + 1) * (HR + 1);
-    static constexpr int MQ_FLOATS = 2 * KCF_THREADS;      // Nyquist column of the spectra, [31][WC] float2 (one slot per thread)
+    static constexpr int MQ_FLOATS = 4 * KCF_THREADS;      // [2][NT] float2: cp.async landing slots of the two model values of P5b; the first row then holds the Nyquist column [31][WC]
     static constexpr int ZB_FLOATS = 0;                    // (the raw transform of the packed (DC, Nyquist) column stays in its own spectrum slots)
     // Square grids: channel c is produced (P4b) and column-transformed (P5) by the same aligned group of WC threads, so the barrier
     // between the two phases is a warp-level one and the fast warps' model streaming overlaps the slow warps' feature generation.
@@ -625,13 +625,20 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     // Lane `half` of a pair ends up with the output rows j' = 2m + half.  Bins k >= 1 are ordinary columns; bin 0 carries
     // two real-input columns (DC and Nyquist): its raw transform is parked in ZB and P5b, one row per thread on all threads,
     // separates and finishes both columns (the bin-0 lanes only park 16 values while the other lanes of their warp work).
-    float2 *const FN = MQ;                                             // Nyquist column [31][WC], its own area: written warp-locally while other warps still read the histograms
+    float2 *const FN = MQ;                                             // Nyquist column [31][WC]: row e replaces the model value thread e fetched into its own first slot
     // (job-level values are re-read from the descriptor where they are needed instead of living in registers across the phases)
     float2 *const model = p.model + (long)jd.slot * p.model_stride;
     const bool first = (MODE == KCF_MODE_UPDATE) && jd.first_update != 0;
     const float fac = first ? 1.0f : p.factor;                         // kcf.cpp:443
     const float omf = __fsub_rn(1.0f, fac);
     const bool need_model = (MODE == KCF_MODE_PREDICT) || !first;
+    // the two model values of P5b (DC and Nyquist bin of this thread's row) start their way into the thread's own slots now, through
+    // cp.async: they arrive underneath the column pass, without holding registers across it
+    if (tid < KCF_CHAN * WC && need_model) {
+        const float2 *mr = model + (tid / WC) * S + (tid % WC) * SK;
+        cp_async8(MQ + tid, mr); cp_async8(MQ + NT + tid, mr + HK);
+        cp_async_commit();
+    }
     {
         constexpr int HW = WC / 2;
         // task = (channel, bin): HK bins per channel, so a half-warp holds an aligned run of bins (bank-conflict free with
@@ -687,13 +694,7 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
             }
         }
     }
-    // the two model values of P5b: issue the loads before the barrier so that their latency overlaps the wait
     static_assert(KCF_CHAN * WC <= NT, "P5b: one row per thread");
-    float2 m0n = make_float2(0.f, 0.f), m1n = make_float2(0.f, 0.f);
-    if (tid < KCF_CHAN * WC && need_model) {
-        const float2 *mr = model + (tid / WC) * S + (tid % WC) * SK;
-        m0n = mr[0]; m1n = mr[HK];
-    }
     // square grids: P5b's row (c, j') reads what the bin-0 pair of the SAME channel group parked, and writes only its own slots
     if (G::FUSE45) __syncwarp(); else __syncthreads();
     // ---- P5b: the DC (k = 0) and Nyquist (k = HR/2) columns, one row j' per thread: Z[j'] and Z[-j'] give both
@@ -701,6 +702,8 @@ __global__ void __launch_bounds__(KCF_THREADS, 1) kcf_fused_kernel(const KcfLaun
     if (tid < KCF_CHAN * WC) {
         const int e = tid, c = e / WC, jp = e - c * WC, jm = (WC - jp) & (WC - 1);
         const float2 v = F2[(c * WC + jp) * HK + fpos<HK, WC>(0, jp)], y = F2[(c * WC + jm) * HK + fpos<HK, WC>(0, jm)];
+        cp_async_wait_all();
+        const float2 m0n = need_model ? MQ[tid] : make_float2(0.f, 0.f), m1n = need_model ? MQ[NT + tid] : make_float2(0.f, 0.f);
         __syncwarp(p5b_mask);          // rows j' and -j' of a channel sit in the same warp: both have read before either slot is overwritten
         const float2 dc = make_float2(0.5f * (v.x + y.x), 0.5f * (v.y - y.y));
         const float2 nq = make_float2(0.5f * (v.y + y.y), 0.5f * (y.x - v.x));
