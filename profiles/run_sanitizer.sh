@@ -3,4 +3,4 @@
 O=gpurun_out
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_golden.py tests/test_gpu_kalman_assoc.py "tests/test_gpu_tdloop.py::test_device_resident_loop_trace" -x -q -m gpu > $O/r2_sanitizer_memcheck.txt 2>&1; echo "memcheck rc=$?" >> $O/r2_sanitizer_memcheck.txt
 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_golden.py "tests/test_gpu_tdloop.py::test_device_resident_loop_trace" -x -q -m gpu > $O/r2_sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?" >> $O/r2_sanitizer_racecheck.txt
-tail -5 $O/r2_sanitizer_memcheck.txt $O/r2_sanitizer_racecheck.txt
+tail -n 5 $O/r2_sanitizer_memcheck.txt; tail -n 5 $O/r2_sanitizer_racecheck.txt
