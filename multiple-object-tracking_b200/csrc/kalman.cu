@@ -24,13 +24,13 @@ __global__ void kalman_predict_kernel(KalmanState st, int n, const int *slots, m
     kalman_predict_one(st, s, boxes + i, clamp, fw, fh);
 }
 
+// eight lanes per track (kalman_update_coop), eight tracks per 64-thread CTA
 __global__ void kalman_update_kernel(KalmanState st, int n, const int *slots, const mot_bbox_t *boxes)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int s = slots[i];
-    if (s < 0) return;
-    kalman_update_one(st, s, boxes[i]);
+    __shared__ double sm[8 * KALMAN_COOP_DOUBLES];
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 3);
+    const int s = i < n ? slots[i] : -1;
+    kalman_update_coop(st, s, s >= 0 ? boxes[i] : mot_bbox_t{}, sm + (threadIdx.x >> 3) * KALMAN_COOP_DOUBLES, threadIdx.x & 7);
 }
 
 int kalman_init(const KalmanState &st, int n, const int *d_slots, const mot_bbox_t *d_boxes, cudaStream_t s)
@@ -48,7 +48,7 @@ int kalman_predict(const KalmanState &st, int n, const int *d_slots, mot_bbox_t 
 int kalman_update(const KalmanState &st, int n, const int *d_slots, const mot_bbox_t *d_boxes, cudaStream_t s)
 {
     if (n <= 0) return 0;
-    kalman_update_kernel<<<(n + 63) / 64, 64, 0, s>>>(st, n, d_slots, d_boxes);
+    kalman_update_kernel<<<(n + 7) / 8, 64, 0, s>>>(st, n, d_slots, d_boxes);
     return (int)cudaGetLastError();
 }
 

@@ -160,4 +160,108 @@ __device__ __forceinline__ void kalman_update_one(const KalmanState &st, int s, 
         for (int r = 0; r < 6; ++r) st.P[(long)(c * 6 + r) * st.cap + s] = P[r][c];
 }
 
+// ---- the same update spread over the lanes of an 8-lane group (lanes 0..5 = the six rows of P / K / Jf, lanes 0..3 also the four
+// rows of the cofactor matrix): every element is produced by exactly the expression of kalman_update_one above -- same operands, same
+// order of the sums -- so the result is the same bit for bit, but a lane's chain of dependent FP64 operations is a sixth as long.
+// sm = 132 doubles of shared memory owned by the group; all 32 lanes of the warp must call (s < 0: a group without a track).
+constexpr int KALMAN_COOP_DOUBLES = 132;
+
+template <int R> __device__ __forceinline__ void kalman_cof_row(const double (&S)[4][4], double *out)
+{
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double m[9]; int k = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i != R)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j != c) m[k++] = S[i][j];
+        const double d = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+        out[c] = ((R + c) & 1) ? -d : d;
+    }
+}
+
+__device__ __forceinline__ void kalman_update_coop(const KalmanState &st, int s, const mot_bbox_t b, double *sm, int q)
+{
+    double *const Ps = sm, *const cof = sm + 36, *const Sis = sm + 52, *const Ks = sm + 68, *const Jfs = sm + 92, *const zes = sm + 128;
+    const bool row = s >= 0 && q < 6, row4 = s >= 0 && q < 4;
+    double xq = 0.0;
+    if (row) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) Ps[q * 6 + c] = st.P[(long)(c * 6 + q) * st.cap + s];
+        xq = st.x[(long)q * st.cap + s];
+    }
+    if (row4) {
+        const double z = (double)(q == 0 ? b.l : q == 1 ? b.t : q == 2 ? b.r : b.b);     // kalman.cpp:122-125
+        zes[q] = z - xq;
+    }
+    __syncwarp();
+    // S = H P H^T + R = P[0:4,0:4] + 512 I (kalman.cpp:87-88); cofactors of row q
+    double S[4][4];
+    if (row4) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) S[r][c] = Ps[r * 6 + c] + (r == c ? 512.0 : 0.0);
+        switch (q) {
+        case 0: kalman_cof_row<0>(S, cof + 0); break;
+        case 1: kalman_cof_row<1>(S, cof + 4); break;
+        case 2: kalman_cof_row<2>(S, cof + 8); break;
+        default: kalman_cof_row<3>(S, cof + 12); break;
+        }
+    }
+    __syncwarp();
+    if (row4) {
+        double det = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) det += S[0][c] * cof[c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Sis[q * 4 + c] = cof[c * 4 + q] / det;       // Si[q][c] = cof[c][q] / det
+    }
+    __syncwarp();
+    double Kr[4], JPr[6];
+    if (row) {
+        // K = P H^T inv(S) = P[:,0:4] Si  (kalman.h:228)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a += Ps[q * 6 + k] * Sis[k * 4 + c];
+            Kr[c] = a; Ks[q * 4 + c] = a;
+        }
+        // x += K (z - H x)  (kalman.h:231-232)
+        {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a += Kr[k] * zes[k];
+            xq += a;
+            st.x[(long)q * st.cap + s] = xq;
+        }
+        // Joseph form (kalman.h:235-236): Jf = I - K H; P = Jf P Jf^T + K R K^T
+        double Jfr[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { Jfr[c] = (q == c ? 1.0 : 0.0) - (c < 4 ? Kr[c] : 0.0); Jfs[q * 6 + c] = Jfr[c]; }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a += Jfr[k] * Ps[k * 6 + c];
+            JPr[c] = a;
+        }
+    }
+    __syncwarp();
+    if (row) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a += JPr[k] * Jfs[c * 6 + k];
+            double kr = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) kr += (Kr[k] * 512.0) * Ks[c * 4 + k];
+            st.P[(long)(c * 6 + q) * st.cap + s] = a + kr;
+        }
+    }
+    __syncwarp();                          // the group's shared memory may be reused by the caller's next track
+}
+
 }  // namespace mot
