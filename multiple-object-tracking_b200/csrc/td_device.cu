@@ -330,15 +330,9 @@ __global__ void __launch_bounds__(TDF_THREADS, 1) td_frame_kalman_kernel(TddStat
     td_scatter_cta(st, dets, ndet, at);
     __syncthreads();
     // update with the assigned detection, or with the predicted box itself (top/td.cpp:539, 581)
-    // (eight lanes per track -- the six rows of the covariance algebra side by side, kalman.cuh -- on the solver's shared memory, now free)
-    {
-        double *const ksm = reinterpret_cast<double *>(smem_raw) + (tid >> 3) * KALMAN_COOP_DOUBLES;
-        for (int i0 = 0; i0 < cap; i0 += TDF_THREADS / 8) {
-            const int i = i0 + (tid >> 3);
-            const int sl = i < cap ? st.slot[(long)s * cap + i] : -1;
-            kalman_update_coop(kal, sl, sl >= 0 ? trk[i] : mot_bbox_t{}, ksm, tid & 7);
-        }
-    }
+    // (one thread per track here: the update is a chain of ~90 dependent FP64 operations whatever the number of lanes that share it, so
+    // the eight-lane form of kalman.cuh, which needs two passes over 64 tracks in a 256-thread CTA, is slower in this kernel -- measured)
+    for (int i = tid; i < cap; i += TDF_THREADS) { const int sl = st.slot[(long)s * cap + i]; if (sl >= 0) kalman_update_one(kal, sl, trk[i]); }
     __syncthreads();
     td_lifecycle_cta(st, kal, dets, ndet, reinterpret_cast<int *>(smem_raw));
 }
@@ -437,7 +431,7 @@ int mot_tdd_create(mot_tdd_t **out, mot_ctx_t *c, int n_streams, int cap, int ma
     const int rc = tdd_alloc(t, c, n_streams, cap, max_det, kcf);
     if (rc) { tdd_release(t); delete t; return rc; }
     if (!kcf && t->st.md <= TDF_THREADS && !getenv("MOT_TDD_UNFUSED")) {      // larger problems want the 1024-thread solver: separate launches
-        const size_t bytes = std::max(std::max(munkres_smem_bytes(t->st.md, munkres_mat_doubles(t->st.md)), sizeof(int) * 3072), sizeof(double) * KALMAN_COOP_DOUBLES * (TDF_THREADS / 8));
+        const size_t bytes = std::max(munkres_smem_bytes(t->st.md, munkres_mat_doubles(t->st.md)), sizeof(int) * 3072);
         t->fused_frame = cudaFuncSetAttribute((const void *)td_frame_kalman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
     }
     for (long i = 0; i < (long)n_streams * cap; ++i) c->used[i] = 1;        // these slots now belong to the device-side tables
@@ -510,7 +504,7 @@ int mot_tdd_step_dev(mot_tdd_t *t, const mot_bbox_t *d_dets, const int *d_ndet)
         TdFrameArgs a{ t->d_dist, t->d_work, t->d_cost, t->cost_mode, 1.0 / (double)c->W, munkres_mat_doubles(st.md), t->host_dets_next, t->host_ndet_next,
                        const_cast<mot_bbox_t *>(d_dets), const_cast<int *>(d_ndet) };
         t->host_dets_next = nullptr; t->host_ndet_next = nullptr;
-        const size_t bytes = std::max(std::max(munkres_smem_bytes(st.md, a.mat_doubles), sizeof(int) * 3072), sizeof(double) * KALMAN_COOP_DOUBLES * (TDF_THREADS / 8));
+        const size_t bytes = std::max(munkres_smem_bytes(st.md, a.mat_doubles), sizeof(int) * 3072);
         td_frame_kalman_kernel<<<st.S, TDF_THREADS, bytes, c->stream>>>(st, c->kal, d_dets, d_ndet, a);
         CU(cudaGetLastError());
         c->launches += 1;
